@@ -1,0 +1,149 @@
+/*
+ * lbmpc.h — C ABI of the B200-native batched interior-point QP engine for (LB)MPC.
+ *
+ * Drop-in seam: the reference (bevanda/Learning-Based-MPC, 100 % MATLAB) has no FFI of its own;
+ * the seam is the third-party solver call inside its closed-loop drivers
+ *     opt_var = fmincon(COSTFUN,opt_var,[],[],[],[],[],[],CONSFUN,options);   functions/ocpLBMPC.m:27-31
+ *                                                                           functions/ocpLMPC.m:20-24
+ *     res = solver('x0',y_init,'lbx',lb,'ubx',ub,'lbg',con_lb,'ubg',con_ub);   examples/DMS_tracking_LMPC_casadi.m:163-167
+ *                                                                           examples/LBMPC_casadi.m:170-174
+ * Every entry point below replaces one piece of that path; the MATLAB-side binding (MEX gateway
+ * + ocpLBMPC_gpu.m) is in learning-based-mpc_b200/matlab/ and described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - all matrices are COLUMN-major doubles (MATLAB layout), dimensions passed explicitly;
+ *  - batch arrays are "one column per QP": dx0 is nx x batch, u_or_c is (nu*N) x batch, ...;
+ *  - the caller owns every array; the handle owns device scratch sized at create;
+ *  - return value 0 = ok, negative = error (text via lbmpc_last_error()); per-QP outcome only
+ *    through status[];
+ *  - there is NO CPU fallback: every call fails with LBMPC_ECUDA if no sm_100 device is usable.
+ */
+#ifndef LBMPC_H
+#define LBMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define LBMPC_OK 0
+#define LBMPC_EINVAL (-1)       /* bad argument / NULL pointer                         */
+#define LBMPC_ESHAPE (-2)       /* unsupported dimensions or constraint structure      */
+#define LBMPC_ECUDA (-3)        /* CUDA runtime error or no usable device              */
+#define LBMPC_ENOMEM (-4)
+
+/* problem form: which reference script family the QP reproduces */
+#define LBMPC_FORM_F 0          /* fmincon scripts: opt_var=[c;theta], u = K x + c (transitionNominal.m:12),
+                                   cost costLMPC.m:25-45, rows constraintsLMPC.m:20-41                      */
+#define LBMPC_FORM_C 1          /* CasADi scripts: y=[x;u;theta], delta-scaled stage cost
+                                   (DMS_tracking_LMPC_casadi.m:223-251), rows :254-287                       */
+#define LBMPC_VARIANT_LMPC 0    /* terminal invariant set F_w_N [x_last;theta] <= h_w_N (getCONS.m:57-58)    */
+#define LBMPC_VARIANT_LBMPC 1   /* robust rows on x_1: F_x_d, F_w_N (constraintsLBMPC.m:26-31,
+                                   LBMPC_casadi.m:286-290)                                                   */
+
+/* per-QP status */
+#define LBMPC_ST_OPTIMAL 0
+#define LBMPC_ST_MAXITER 1
+#define LBMPC_ST_INFEASIBLE 2
+#define LBMPC_ST_NUMERICAL 3
+
+typedef struct lbmpc_handle lbmpc_handle;
+
+/* The reference's model/constraint matrices, exactly the arguments of ocpLBMPC.m:1-6
+ * (A,B,Kstabil,Q,R,P,T,LAMBDA,PSI,F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d). */
+typedef struct lbmpc_model {
+    int32_t nx, nu, nt;        /* states, inputs, dim(theta) (= m in matOCP.m:14-16)            */
+    const double *A;           /* nx x nx   mgcmDLTI.m:38 / nominalModel.m:14-17                 */
+    const double *B;           /* nx x nu   mgcmDLTI.m:39 / nominalModel.m:18-21                 */
+    const double *K;           /* nu x nx   Kstabil, matOCP.m:7-9                                */
+    const double *Q;           /* nx x nx   matOCP.m:27                                          */
+    const double *R;           /* nu x nu                                                        */
+    const double *P;           /* nx x nx   matOCP.m:30                                          */
+    const double *T;           /* nx x nx, or 1 x 1 when T_is_scalar (matOCP.m:31: T = 1000)     */
+    int32_t T_is_scalar;
+    const double *LAMBDA;      /* nx x nt   matOCP.m:15                                          */
+    const double *PSI;         /* nu x nt   matOCP.m:16                                          */
+    const double *F_x, *h_x;   /* n_Fx x nx, n_Fx     getCONS.m:16 — one non-zero per row (box)  */
+    int32_t n_Fx;
+    const double *F_u, *h_u;   /* n_Fu x nu, n_Fu     getCONS.m:15 — one non-zero per row (box)  */
+    int32_t n_Fu;
+    const double *F_w_N, *h_w_N; /* n_Fw x (nx+nt), n_Fw   getCONS.m:57-58 / getCONSPOLY.m:69    */
+    int32_t n_Fw;
+    const double *F_x_d, *h_x_d; /* n_Fxd x nx, n_Fxd (LBMPC only)  getCONSPOLY.m:28-30          */
+    int32_t n_Fxd;
+} lbmpc_model;
+
+typedef struct lbmpc_config {
+    int32_t form;              /* LBMPC_FORM_*                                                    */
+    int32_t variant;           /* LBMPC_VARIANT_*                                                 */
+    int32_t N;                 /* horizon (LBMPC_RunExample.m:22; N_t/delta in the CasADi files)  */
+    double delta;              /* C-form stage weight (DMS_tracking_LMPC_casadi.m:84); ignored in F-form */
+    double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1,|lambda|inf)           */
+    double tol_mu;             /* 0 -> 1e-10  complementarity gap                                  */
+    double eps_inf;            /* 0 -> 1e-8   Farkas-certificate tolerance (status 2)              */
+    int32_t max_iter;          /* 0 -> 60                                                          */
+    int64_t max_batch;         /* largest batch of one solve call (device I/O staging is sized on it) */
+    int32_t pointers_on_device;/* 0: batch arrays are host pointers (calls are synchronous);
+                                  1: device pointers (calls are asynchronous on `stream`)          */
+} lbmpc_config;
+
+/* replaces the setup the reference does once per script before its loop (LBMPC_RunExample.m:10-85):
+ * copies the model to the device and builds the canonical stage form. */
+int lbmpc_create(const lbmpc_model *model, const lbmpc_config *cfg, int device, lbmpc_handle **out);
+
+/* replaces the solver call fmincon(...) ocpLBMPC.m:31 / solver(...) DMS_tracking_LMPC_casadi.m:163-167
+ * for `batch` independent QPs.
+ *   dx0      nx x batch          measured state minus working point        (ocpLBMPC.m:21-23)
+ *   dx_ref   nx x batch or NULL  tracking reference xs                     (costLMPC.m:38)
+ *   d_off    nx x N x batch or NULL  per-stage dynamics offset d_k = oracle correction frozen on
+ *                                a linearisation trajectory                (learnedModel.m:25)
+ *   warm     (nu*N+nt) x batch or NULL  initial [c;theta] / [du;theta]      (opt_var, ocpLBMPC.m:31)
+ *   u_or_c   (nu*N) x batch  OUT c (F-form) or du = u - u_wp (C-form)
+ *   theta    nt x batch      OUT
+ *   x_traj   nx x (N+1) x batch or NULL  OUT predicted states (delta coordinates)
+ *   obj      batch OUT objective J (costLMPC.m / `res.f`)
+ *   iters, status  batch OUT
+ *   stream   cudaStream_t (may be NULL = default stream) */
+int lbmpc_solve_batch(lbmpc_handle *h, int64_t batch, const double *dx0, const double *dx_ref,
+                      const double *d_off, const double *warm, double *u_or_c, double *theta,
+                      double *x_traj, double *obj, int32_t *iters, int32_t *status, void *stream);
+
+/* replaces learnedModel.m:25 + oracleL2NW.m:2-36 (mask variant casadiL2NW.m:14-28) applied along
+ * the horizon: rolls the learned model x+ = A x + B u + g([x1;x2;u]) for the given input sequence
+ * and returns the per-stage corrections d_k = g(.) (feed them to lbmpc_solve_batch as d_off).
+ *   dx0 nx x batch; du (nu*N) x batch; X 3 x q x batch; Y nx x q x batch; valid q x batch or NULL;
+ *   d_off nx x N x batch OUT.  Pointers follow cfg.pointers_on_device. */
+int lbmpc_oracle_apply(lbmpc_handle *h, int64_t batch, int32_t q, double bandwidth, double lambda,
+                       const double *dx0, const double *du, const double *X, const double *Y,
+                       const double *valid, double *d_off, void *stream);
+
+/* replaces the closed-loop drivers ocpLBMPC.m:10-47 / LBMPC_casadi.m:160-223 for `batch`
+ * independent scenarios: solve, apply the first move to the Moore-Greitzer plant (RK4,
+ * DMS_tracking_LMPC_casadi.m:297-304), add a bounded uniform disturbance (RunExample_robust.m:250-252),
+ * update the q-sample data window (get_data.m:3-9), shift the warm start (…casadi.m:187-189).
+ *   x_init nx x batch (absolute); x_eq nx; wbar nx or NULL;
+ *   x_hist nx x (steps+1) x batch OUT; u_hist steps x batch OUT; theta_hist steps x batch OUT;
+ *   iters_hist/status_hist steps x batch OUT (any OUT may be NULL).  C-form handles only. */
+int lbmpc_closed_loop(lbmpc_handle *h, int64_t batch, int32_t steps, int32_t q, int32_t use_oracle,
+                      int32_t warm_shift, const double *x_eq, double u_eq, const double *x_init,
+                      const double *wbar, uint64_t seed, uint64_t scenario0, double *x_hist,
+                      double *u_hist, double *theta_hist, int32_t *iters_hist,
+                      int32_t *status_hist, void *stream);
+
+/* introspection used by the host mirrors, tests and bench */
+int lbmpc_num_rows(const lbmpc_handle *h);            /* inequality rows m of one QP                     */
+int lbmpc_slots_per_cta(const lbmpc_handle *h);       /* QPs resident per CTA (shared-memory bound)      */
+int64_t lbmpc_kernel_launches(const lbmpc_handle *h); /* kernels launched by this handle so far          */
+/* last solve call: device time of the IPM kernel in ms (CUDA events on the launch stream) */
+float lbmpc_last_kernel_ms(lbmpc_handle *h);
+
+void lbmpc_destroy(lbmpc_handle *h);
+const char *lbmpc_last_error(void);                  /* thread-local message of the last failure         */
+const char *lbmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBMPC_H */

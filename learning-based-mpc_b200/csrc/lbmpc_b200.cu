@@ -1,0 +1,395 @@
+// lbmpc_b200.cu — C ABI (include/lbmpc.h) over the sm_100a kernels.  One translation unit:
+// nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+//
+// No CPU fallback: every entry point needs a CUDA device; errors come back as negative codes with
+// a thread-local message (lbmpc_last_error).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lbmpc.h"
+#include "lbmpc_kernels.cuh"
+#include "lbmpc_problem.hpp"
+
+using namespace lbmpc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(LBMPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+struct LoopScratch {
+    int64_t batch = 0;
+    int q = 0, steps = 0;
+    double *x = nullptr, *dx0 = nullptr, *X = nullptr, *Y = nullptr, *V = nullptr, *warm = nullptr, *uc = nullptr,
+           *theta = nullptr, *obj = nullptr, *doff = nullptr, *x_init = nullptr;
+    int *nd = nullptr, *iters = nullptr, *status = nullptr;
+    double *x_hist = nullptr, *u_hist = nullptr, *t_hist = nullptr;
+    int *i_hist = nullptr, *s_hist = nullptr;
+};
+
+struct lbmpc_handle {
+    int device = 0;
+    HostProblem hp;
+    int shape = 0;  // 0: <4,1,1>  1: <2,2,2>
+    int max_slots = 0, stage_g = 0, num_sms = 0;
+    bool dev_ptrs = false;
+    int64_t max_batch = 0;
+    double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
+    unsigned long long* dqueue = nullptr;
+    // host-pointer staging
+    double *s_dx0 = nullptr, *s_ref = nullptr, *s_doff = nullptr, *s_warm = nullptr, *s_uc = nullptr,
+           *s_theta = nullptr, *s_x = nullptr, *s_obj = nullptr;
+    int *s_it = nullptr, *s_st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    bool timed = false;
+    LoopScratch loop;
+};
+
+template <int NX, int NT, int NU>
+static int plan_slots(lbmpc_handle* h, size_t max_smem) {
+    const HostProblem& hp = h->hp;
+    for (int stage = 1; stage >= 0; --stage) {
+        for (int s = kMaxSlots; s >= 1; --s) {
+            const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, s, stage != 0);
+            // staging the polytope must not cost more than one slot of residency
+            if (plan.bytes <= max_smem) {
+                if (stage == 1) {
+                    const SmemPlan<NX, NT, NU> alt(hp.N, hp.ngp, std::min(s + 1, kMaxSlots), false);
+                    if (s < kMaxSlots && alt.bytes <= max_smem && hp.ng <= 64) continue;  // tiny block: keep it in L1/L2
+                }
+                h->max_slots = s;
+                h->stage_g = stage;
+                return LBMPC_OK;
+            }
+        }
+    }
+    return fail(LBMPC_ESHAPE, "horizon too long: one QP does not fit in shared memory");
+}
+
+template <int NX, int NT, int NU>
+static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io, cudaStream_t st) {
+    const HostProblem& hp = h->hp;
+    const Params<NX, NT, NU> p = to_params<NX, NT, NU>(hp);
+    int slots = (int)std::min<int64_t>(h->max_slots, (io.batch + h->num_sms - 1) / h->num_sms);
+    slots = std::max(slots, 1);
+    const int grid = (int)std::min<int64_t>(h->num_sms, (io.batch + slots - 1) / slots);
+    const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
+    cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
+    h->launches += 1;
+    return cudaGetLastError();
+}
+
+static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int q, double inv_h2, double lambda,
+                          const double* dx0, const double* du, long long du_ld, const double* X, const double* Y,
+                          const double* valid, double* d_off) {
+    const unsigned grid = (unsigned)((batch + 3) / 4);
+    if (q <= 128)
+        oracle_kernel<4, 1, 4><<<grid, 128, 0, st>>>(h->dA, h->dB, h->hp.N, batch, q, inv_h2, lambda, dx0, du, du_ld, X,
+                                                    Y, valid, d_off);
+    else
+        oracle_kernel<4, 1, kOracleMaxPerLane><<<grid, 128, 0, st>>>(h->dA, h->dB, h->hp.N, batch, q, inv_h2, lambda,
+                                                                    dx0, du, du_ld, X, Y, valid, d_off);
+    h->launches += 1;
+}
+
+static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st) {
+    return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
+}
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t n) {
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+extern "C" {
+
+const char* lbmpc_last_error(void) { return g_err.c_str(); }
+const char* lbmpc_version(void) { return "lbmpc_b200 0.1 (sm_100a)"; }
+
+int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, lbmpc_handle** out) {
+    if (!out) return fail(LBMPC_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LBMPC_ECUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(LBMPC_EINVAL, "bad device index");
+    lbmpc_handle* h = new (std::nothrow) lbmpc_handle();
+    if (!h) return fail(LBMPC_ENOMEM, "out of host memory");
+    std::string err;
+    int rc = build_problem(model, cfg, h->hp, err);
+    if (rc != LBMPC_OK) {
+        delete h;
+        return fail(rc, err);
+    }
+    const HostProblem& hp = h->hp;
+    if (hp.nx == 4 && hp.nt == 1 && hp.nu == 1) h->shape = 0;
+    else if (hp.nx == 2 && hp.nt == 2 && hp.nu == 2) h->shape = 1;
+    else {
+        delete h;
+        return fail(LBMPC_ESHAPE, "compiled shapes: (nx,nt,nu) = (4,1,1) Moore-Greitzer, (2,2,2) double integrator");
+    }
+    h->device = device;
+    h->dev_ptrs = cfg->pointers_on_device != 0;
+    h->max_batch = std::max<int64_t>(cfg->max_batch, 1);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete h;
+        return fail(LBMPC_ECUDA, "device is not sm_100 (Blackwell); the library carries sm_100a code only");
+    }
+    h->num_sms = prop.multiProcessorCount;
+    int max_smem = 0;
+    CU_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    rc = h->shape == 0 ? plan_slots<4, 1, 1>(h, (size_t)max_smem) : plan_slots<2, 2, 2>(h, (size_t)max_smem);
+    if (rc != LBMPC_OK) {
+        delete h;
+        return rc;
+    }
+    if (h->shape == 0)
+        CU_TRY(cudaFuncSetAttribute(ipm_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    else
+        CU_TRY(cudaFuncSetAttribute(ipm_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    const int nz = hp.nx + hp.nt;
+    CU_TRY(dmalloc(&h->dG, (size_t)nz * hp.ngp));
+    CU_TRY(dmalloc(&h->dhg, (size_t)hp.ngp));
+    CU_TRY(dmalloc(&h->dA, (size_t)hp.nx * hp.nx));
+    CU_TRY(dmalloc(&h->dB, (size_t)hp.nx * hp.nu));
+    CU_TRY(dmalloc(&h->dqueue, 1));
+    CU_TRY(cudaMemcpy(h->dG, hp.G.data(), sizeof(double) * nz * hp.ngp, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dhg, hp.hg.data(), sizeof(double) * hp.ngp, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dA, hp.A.data(), sizeof(double) * hp.nx * hp.nx, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dB, hp.B.data(), sizeof(double) * hp.nx * hp.nu, cudaMemcpyHostToDevice));
+    CU_TRY(cudaEventCreate(&h->ev0));
+    CU_TRY(cudaEventCreate(&h->ev1));
+    if (!h->dev_ptrs) {
+        const size_t b = (size_t)h->max_batch, N = hp.N, nx = hp.nx, nu = hp.nu, nt = hp.nt;
+        CU_TRY(dmalloc(&h->s_dx0, b * nx));
+        CU_TRY(dmalloc(&h->s_ref, b * nx));
+        CU_TRY(dmalloc(&h->s_doff, b * nx * N));
+        CU_TRY(dmalloc(&h->s_warm, b * (nu * N + nt)));
+        CU_TRY(dmalloc(&h->s_uc, b * nu * N));
+        CU_TRY(dmalloc(&h->s_theta, b * nt));
+        CU_TRY(dmalloc(&h->s_x, b * nx * (N + 1)));
+        CU_TRY(dmalloc(&h->s_obj, b));
+        CU_TRY(dmalloc(&h->s_it, b));
+        CU_TRY(dmalloc(&h->s_st, b));
+    }
+    *out = h;
+    return LBMPC_OK;
+}
+
+int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
+                      const double* warm, double* u_or_c, double* theta, double* x_traj, double* obj, int32_t* iters,
+                      int32_t* status, void* stream) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (batch < 0) return fail(LBMPC_EINVAL, "negative batch");
+    if (batch == 0) return LBMPC_OK;
+    if (!dx0 || !u_or_c || !theta || !obj || !iters || !status) return fail(LBMPC_EINVAL, "required array is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(h->device));
+    const HostProblem& hp = h->hp;
+    const size_t b = (size_t)batch, N = hp.N, nx = hp.nx, nu = hp.nu, nt = hp.nt;
+    BatchIO io{};
+    io.batch = batch;
+    io.queue = h->dqueue;
+    if (h->dev_ptrs) {
+        io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm;
+        io.uc = u_or_c; io.theta = theta; io.xtraj = x_traj; io.obj = obj; io.iters = iters; io.status = status;
+        CU_TRY(cudaEventRecord(h->ev0, st));
+        CU_TRY(launch_ipm_any(h, io, st));
+        CU_TRY(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+        return LBMPC_OK;
+    }
+    if (batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
+    CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
+    if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
+    if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, sizeof(double) * b * nx * N, cudaMemcpyHostToDevice, st));
+    if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, sizeof(double) * b * (nu * N + nt), cudaMemcpyHostToDevice, st));
+    io.dx0 = h->s_dx0; io.dx_ref = dx_ref ? h->s_ref : nullptr; io.d_off = d_off ? h->s_doff : nullptr;
+    io.warm = warm ? h->s_warm : nullptr;
+    io.uc = h->s_uc; io.theta = h->s_theta; io.xtraj = x_traj ? h->s_x : nullptr; io.obj = h->s_obj;
+    io.iters = h->s_it; io.status = h->s_st;
+    CU_TRY(cudaEventRecord(h->ev0, st));
+    CU_TRY(launch_ipm_any(h, io, st));
+    CU_TRY(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    CU_TRY(cudaMemcpyAsync(u_or_c, h->s_uc, sizeof(double) * b * nu * N, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(theta, h->s_theta, sizeof(double) * b * nt, cudaMemcpyDeviceToHost, st));
+    if (x_traj) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, sizeof(double) * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(obj, h->s_obj, sizeof(double) * b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(iters, h->s_it, sizeof(int) * b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(status, h->s_st, sizeof(int) * b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return LBMPC_OK;
+}
+
+int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwidth, double lambda, const double* dx0,
+                       const double* du, const double* X, const double* Y, const double* valid, double* d_off,
+                       void* stream) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (batch <= 0) return batch == 0 ? LBMPC_OK : fail(LBMPC_EINVAL, "negative batch");
+    if (!dx0 || !du || !X || !Y || !d_off) return fail(LBMPC_EINVAL, "required array is NULL");
+    if (h->shape != 0) return fail(LBMPC_ESHAPE, "the L2NW oracle is defined on the 4-state model (xi=[x1;x2;u])");
+    if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
+    if (!(bandwidth > 0)) return fail(LBMPC_EINVAL, "bandwidth must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(h->device));
+    const HostProblem& hp = h->hp;
+    const size_t b = (size_t)batch, N = hp.N;
+    const double inv_h2 = 1.0 / (bandwidth * bandwidth);
+    if (h->dev_ptrs) {
+        launch_oracle(h, st, batch, q, inv_h2, lambda, dx0, du, (long long)N, X, Y, valid, d_off);
+        CU_TRY(cudaGetLastError());
+        return LBMPC_OK;
+    }
+    double *ddx0, *ddu, *dX, *dY, *dV = nullptr, *dd;
+    CU_TRY(dmalloc(&ddx0, b * 4)); CU_TRY(dmalloc(&ddu, b * N)); CU_TRY(dmalloc(&dX, b * 3 * q));
+    CU_TRY(dmalloc(&dY, b * 4 * q)); CU_TRY(dmalloc(&dd, b * 4 * N));
+    if (valid) CU_TRY(dmalloc(&dV, b * q));
+    CU_TRY(cudaMemcpyAsync(ddx0, dx0, 8 * b * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ddu, du, 8 * b * N, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(dX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(dY, Y, 8 * b * 4 * q, cudaMemcpyHostToDevice, st));
+    if (valid) CU_TRY(cudaMemcpyAsync(dV, valid, 8 * b * q, cudaMemcpyHostToDevice, st));
+    launch_oracle(h, st, batch, q, inv_h2, lambda, ddx0, ddu, (long long)N, dX, dY, dV, dd);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(d_off, dd, 8 * b * 4 * N, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(ddx0); cudaFree(ddu); cudaFree(dX); cudaFree(dY); cudaFree(dd); if (dV) cudaFree(dV);
+    return LBMPC_OK;
+}
+
+static void free_loop(LoopScratch& L) {
+    cudaFree(L.x); cudaFree(L.dx0); cudaFree(L.X); cudaFree(L.Y); cudaFree(L.V); cudaFree(L.warm); cudaFree(L.uc);
+    cudaFree(L.theta); cudaFree(L.obj); cudaFree(L.doff); cudaFree(L.x_init); cudaFree(L.nd); cudaFree(L.iters);
+    cudaFree(L.status); cudaFree(L.x_hist); cudaFree(L.u_hist); cudaFree(L.t_hist); cudaFree(L.i_hist);
+    cudaFree(L.s_hist);
+    L = LoopScratch();
+}
+
+int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, int32_t use_oracle,
+                      int32_t warm_shift, const double* x_eq, double u_eq, const double* x_init, const double* wbar,
+                      uint64_t seed, uint64_t scenario0, double* x_hist, double* u_hist, double* theta_hist,
+                      int32_t* iters_hist, int32_t* status_hist, void* stream) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (batch <= 0 || steps <= 0) return fail(LBMPC_EINVAL, "batch and steps must be positive");
+    if (!x_eq || !x_init) return fail(LBMPC_EINVAL, "x_eq / x_init is NULL");
+    if (h->shape != 0 || h->hp.form != LBMPC_FORM_C)
+        return fail(LBMPC_ESHAPE, "closed loop: C-form handle on the 4-state Moore-Greitzer model");
+    if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(h->device));
+    const HostProblem& hp = h->hp;
+    const size_t b = (size_t)batch, N = hp.N, S = (size_t)steps;
+    LoopScratch& L = h->loop;
+    if (L.batch != batch || L.q != q || L.steps != steps) {
+        free_loop(L);
+        CU_TRY(dmalloc(&L.x, b * 4)); CU_TRY(dmalloc(&L.dx0, b * 4)); CU_TRY(dmalloc(&L.X, b * 3 * q));
+        CU_TRY(dmalloc(&L.Y, b * 4 * q)); CU_TRY(dmalloc(&L.V, b * q)); CU_TRY(dmalloc(&L.warm, b * (N + 1)));
+        CU_TRY(dmalloc(&L.uc, b * N)); CU_TRY(dmalloc(&L.theta, b)); CU_TRY(dmalloc(&L.obj, b));
+        CU_TRY(dmalloc(&L.doff, b * 4 * N)); CU_TRY(dmalloc(&L.x_init, b * 4)); CU_TRY(dmalloc(&L.nd, b));
+        CU_TRY(dmalloc(&L.iters, b)); CU_TRY(dmalloc(&L.status, b));
+        if (!h->dev_ptrs) {
+            CU_TRY(dmalloc(&L.x_hist, b * 4 * (S + 1))); CU_TRY(dmalloc(&L.u_hist, b * S));
+            CU_TRY(dmalloc(&L.t_hist, b * S)); CU_TRY(dmalloc(&L.i_hist, b * S)); CU_TRY(dmalloc(&L.s_hist, b * S));
+        }
+        L.batch = batch; L.q = q; L.steps = steps;
+    }
+    CU_TRY(cudaMemsetAsync(L.X, 0, 8 * b * 3 * q, st));
+    CU_TRY(cudaMemsetAsync(L.Y, 0, 8 * b * 4 * q, st));
+    CU_TRY(cudaMemsetAsync(L.V, 0, 8 * b * q, st));
+    const double* xi_dev = x_init;
+    if (!h->dev_ptrs) {
+        CU_TRY(cudaMemcpyAsync(L.x_init, x_init, 8 * b * 4, cudaMemcpyHostToDevice, st));
+        xi_dev = L.x_init;
+    }
+    // x_eq / wbar are tiny parameter vectors: always host pointers
+    const double4 xe = make_double4(x_eq[0], x_eq[1], x_eq[2], x_eq[3]);
+    const double4 wb = wbar ? make_double4(wbar[0], wbar[1], wbar[2], wbar[3]) : make_double4(0, 0, 0, 0);
+    LoopState Sx{};
+    Sx.x = L.x; Sx.dx0 = L.dx0; Sx.X = L.X; Sx.Y = L.Y; Sx.V = L.V; Sx.nd = L.nd; Sx.warm = L.warm;
+    Sx.uc = L.uc; Sx.theta = L.theta; Sx.iters = L.iters; Sx.status = L.status;
+    if (h->dev_ptrs) {
+        Sx.x_hist = x_hist; Sx.u_hist = u_hist; Sx.theta_hist = theta_hist; Sx.iters_hist = iters_hist;
+        Sx.status_hist = status_hist;
+    } else {
+        Sx.x_hist = x_hist ? L.x_hist : nullptr; Sx.u_hist = u_hist ? L.u_hist : nullptr;
+        Sx.theta_hist = theta_hist ? L.t_hist : nullptr; Sx.iters_hist = iters_hist ? L.i_hist : nullptr;
+        Sx.status_hist = status_hist ? L.s_hist : nullptr;
+    }
+    const unsigned tg = (unsigned)((batch + 127) / 128);
+    loop_init_kernel<<<tg, 128, 0, st>>>(Sx, xi_dev, batch, steps, xe);
+    h->launches += 1;
+    CU_TRY(cudaGetLastError());
+    const double inv_h2 = 1.0 / (0.5 * 0.5);  // oracleL2NW.m:9 bandwidth = 0.5
+    for (int it = 0; it < steps; ++it) {
+        const bool have = it > 0;
+        if (use_oracle && have) {
+            launch_oracle(h, st, batch, q, inv_h2, 0.001, L.dx0, L.warm, (long long)(N + 1), L.X, L.Y, L.V, L.doff);
+            CU_TRY(cudaGetLastError());
+        }
+        BatchIO io{};
+        io.batch = batch; io.queue = h->dqueue;
+        io.dx0 = L.dx0; io.dx_ref = nullptr; io.d_off = (use_oracle && have) ? L.doff : nullptr;
+        io.warm = (warm_shift && have) ? L.warm : nullptr;
+        io.uc = L.uc; io.theta = L.theta; io.xtraj = nullptr; io.obj = L.obj; io.iters = L.iters; io.status = L.status;
+        CU_TRY(launch_ipm_any(h, io, st));
+        plant_kernel<<<tg, 128, 0, st>>>(Sx, h->dA, h->dB, batch, hp.N, q, it, steps, xe, u_eq, wb, wbar != nullptr,
+                                         seed, scenario0);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+    }
+    if (!h->dev_ptrs) {
+        if (x_hist) CU_TRY(cudaMemcpyAsync(x_hist, L.x_hist, 8 * b * 4 * (S + 1), cudaMemcpyDeviceToHost, st));
+        if (u_hist) CU_TRY(cudaMemcpyAsync(u_hist, L.u_hist, 8 * b * S, cudaMemcpyDeviceToHost, st));
+        if (theta_hist) CU_TRY(cudaMemcpyAsync(theta_hist, L.t_hist, 8 * b * S, cudaMemcpyDeviceToHost, st));
+        if (iters_hist) CU_TRY(cudaMemcpyAsync(iters_hist, L.i_hist, 4 * b * S, cudaMemcpyDeviceToHost, st));
+        if (status_hist) CU_TRY(cudaMemcpyAsync(status_hist, L.s_hist, 4 * b * S, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    return LBMPC_OK;
+}
+
+int lbmpc_num_rows(const lbmpc_handle* h) { return h ? h->hp.m_rows : 0; }
+int lbmpc_slots_per_cta(const lbmpc_handle* h) { return h ? h->max_slots : 0; }
+int64_t lbmpc_kernel_launches(const lbmpc_handle* h) { return h ? h->launches : 0; }
+
+float lbmpc_last_kernel_ms(lbmpc_handle* h) {
+    if (!h || !h->timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+void lbmpc_destroy(lbmpc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_loop(h->loop);
+    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue);
+    cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
+    cudaFree(h->s_theta); cudaFree(h->s_x); cudaFree(h->s_obj); cudaFree(h->s_it); cudaFree(h->s_st);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+}  // extern "C"

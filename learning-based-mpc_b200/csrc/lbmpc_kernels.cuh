@@ -1,0 +1,581 @@
+// lbmpc_kernels.cuh — sm_100a kernels of the batched (LB)MPC interior-point engine.
+//
+//  ipm_kernel        persistent Mehrotra predictor-corrector solver.  One CTA keeps G QPs ("slots")
+//                    resident in shared memory (whole iterate, factors and directions: no HBM
+//                    traffic inside the solve).  Two thread mappings alternate, separated by
+//                    __syncthreads():
+//                      - stage/row phases : warp g works on slot g, lanes stride over the N+1
+//                        stages and the polytope rows; reductions (duality gap, residual norms,
+//                        step-length max-ratio, polytope Hessian) by warp shuffles;
+//                      - sweep phases     : the Riccati backward / forward recursions run
+//                        thread-local, lane g of warp 0 owns slot g, so one warp advances all G
+//                        QPs of the CTA in lock step with no communication.
+//                    Slots are refilled from a global atomic work queue as soon as their QP
+//                    terminates, so QPs with different iteration counts never wait for each other.
+//                    The polytope matrix (616 x 5 for the LMPC terminal set) is staged once per CTA
+//                    with a 1-D TMA bulk copy (cp.async.bulk + mbarrier).
+//  oracle_kernel     learned-model rollout x+ = A x + B u + g(xi) with the L2-regularised
+//                    Nadaraya-Watson oracle (oracleL2NW.m:26-36 / casadiL2NW.m:14-28); warp per QP,
+//                    lanes over the q data points.
+//  plant_kernel      closed-loop step: RK4 Moore-Greitzer plant, disturbance, data window update,
+//                    warm-start shift (LBMPC_casadi.m:191-208, get_data.m:3-9).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lbmpc_core.cuh"
+
+namespace lbmpc {
+
+constexpr int kMaxSlots = 8;          // slots (= warps) per CTA; bounds registers per thread
+constexpr unsigned kFull = 0xffffffffu;
+
+struct BatchIO {
+    long long batch;
+    const double *dx0, *dx_ref, *d_off, *warm;
+    double *uc, *theta, *xtraj, *obj;
+    int *iters, *status;
+    unsigned long long* queue;  // global work counter (zeroed before launch)
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+// max that propagates NaN (fmax drops it): used for residual norms so that status 3 is seen
+__device__ __forceinline__ double warp_max_nan(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(kFull, v, o);
+        v = (v != v || w != w) ? (v != v ? v : w) : (v > w ? v : w);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// shared-memory carve-up helper, identical on host and device
+template <int NX, int NT, int NU>
+struct SmemPlan {
+    using L = Layout<NX, NT, NU>;
+    int slots, stride, g_off, hg_off, meta_off;  // offsets in doubles
+    size_t bytes;
+    __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
+        const L l(N, ngp);
+        slots = slots_;
+        stride = l.stride;
+        int o = slots * stride;
+        o = (o + 1) & ~1;  // 16-byte alignment for the bulk copy destination
+        g_off = o;
+        if (stage_g) o += (NX + NT) * ngp;
+        hg_off = o;
+        if (stage_g) o += ngp;
+        meta_off = o;
+        o += 2 + kMaxSlots * 4;  // mbarrier (8 B) + pad, then per-slot {state, iters, status, -} ints + qp ids
+        bytes = (size_t)o * sizeof(double);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------
+template <int NX, int NT, int NU>
+__global__ void __launch_bounds__(32 * kMaxSlots, 1)
+ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const double* __restrict__ Gglob,
+           const double* __restrict__ hgglob, const int slots, const int stage_g) {
+    using C = Core<NX, NT, NU>;
+    using L = Layout<NX, NT, NU>;
+    constexpr int NZ = NX + NT, NH = L::NH, NACC = NH + 2 * NZ;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const L l(p.N, p.ngp);
+    const SmemPlan<NX, NT, NU> plan(p.N, p.ngp, slots, stage_g != 0);
+    double* const slot = smem + warp * l.stride;
+    double* const m = slot + l.o_misc;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + plan.meta_off);
+    int* const meta = reinterpret_cast<int*>(smem + plan.meta_off + 2);       // [slot][4]
+    long long* const qpid = reinterpret_cast<long long*>(meta + kMaxSlots * 4);  // [slot]
+    const double* Gs = Gglob;
+    const double* hgs = hgglob;
+    const int N = p.N;
+
+    // ---- one-time CTA setup: stage the polytope with a bulk TMA copy ----
+    if (stage_g) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t gb = (uint32_t)(NZ * p.ngp * sizeof(double)), hb = (uint32_t)(p.ngp * sizeof(double));
+            mbar_expect_tx(bar, gb + hb);
+            tma_bulk_g2s(smem + plan.g_off, Gglob, gb, bar);
+            tma_bulk_g2s(smem + plan.hg_off, hgglob, hb, bar);
+        }
+        Gs = smem + plan.g_off;
+        hgs = smem + plan.hg_off;
+    }
+    if (lane == 0) meta[warp * 4 + 0] = SLOT_EMPTY;
+    if (stage_g) mbar_wait(bar, 0);
+    __syncthreads();
+
+    int state = SLOT_EMPTY;  // warp-uniform copy of meta[warp].state
+    for (;;) {
+        // =====================================================================================
+        // phase C: RUN slots: affine step length, sigma, corrector rhs.  DONE slots: write results.
+        //          Empty slots: fetch the next QP and load its inputs.
+        // =====================================================================================
+        state = meta[warp * 4 + 0];
+        if (state == SLOT_RUN) {
+            RedStep rs{0.0, 0.0, 0.0, 0.0};
+            for (int k = lane; k <= N; k += 32) C::template step_stage<0>(p, l, slot, k, 0.0, rs);
+            for (int i = lane; i < p.ng; i += 32) C::template step_gen_row<0>(p, l, slot, Gs, hgs, i, 0.0, rs);
+            const double ratio = warp_max(rs.ratio);
+            const double s0 = warp_sum(rs.s0), s1 = warp_sum(rs.s1), s2 = warp_sum(rs.s2);
+            const double aaff = ratio > 1.0 ? 1.0 / ratio : 1.0;
+            const double mu = m[L::M_MU];
+            const double mu_aff = (s0 + aaff * s1 + aaff * aaff * s2) * p.inv_m;
+            const double sr = mu_aff / mu;
+            const double sigmu = sr * sr * sr * mu;
+            for (int k = lane; k <= N; k += 32) C::corrector_stage(p, l, slot, k, sigmu);
+            double dg[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) dg[a] = 0.0;
+            for (int i = lane; i < p.ng; i += 32) C::corrector_gen_row(p, l, slot, Gs, hgs, i, sigmu, dg);
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) dg[a] = warp_sum(dg[a]);
+            __syncwarp();
+            if (lane == 0) {
+                m[L::M_SIGMU] = sigmu;
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a];
+            }
+        } else {
+            if (state == SLOT_DONE) {
+                const long long q = qpid[warp];
+                double J = 0.0;
+                for (int k = lane; k <= N; k += 32) J += C::objective_stage(p, l, slot, k);
+                J = warp_sum(J);
+                for (int k = lane; k < N; k += 32) {
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        double v = slot[l.o_u + i * l.Np + k];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * slot[l.o_x + j * l.Np + k];
+                        io.uc[(q * N + k) * NU + i] = v;
+                    }
+                }
+                if (io.xtraj) {
+                    for (int k = lane; k <= N; k += 32)
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = slot[l.o_x + j * l.Np + k];
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) io.theta[q * NT + t] = m[L::M_TH + t];
+                    io.obj[q] = J + m[L::M_CCONST];
+                    io.iters[q] = meta[warp * 4 + 1];
+                    io.status[q] = meta[warp * 4 + 2];
+                }
+                __syncwarp();
+            }
+            // fetch the next QP
+            long long q = -1;
+            if (lane == 0) {
+                const unsigned long long t = atomicAdd(io.queue, 1ULL);
+                q = t < (unsigned long long)io.batch ? (long long)t : -1;
+            }
+            q = __shfl_sync(kFull, q, 0);
+            if (q >= 0) {
+                if (lane < NX) slot[l.o_x + lane * l.Np] = io.dx0[q * NX + lane];
+                for (int k = lane; k < N; k += 32) {
+#pragma unroll
+                    for (int i = 0; i < NU; ++i)
+                        slot[l.o_u + i * l.Np + k] = io.warm ? io.warm[q * (NU * N + NT) + k * NU + i] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; ++j)
+                        slot[l.o_x + j * l.Np + k + 1] = io.d_off ? io.d_off[(q * N + k) * NX + j] : 0.0;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) m[L::M_TH + t] = io.warm ? io.warm[q * (NU * N + NT) + N * NU + t] : 0.0;
+                    double cconst = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) {
+                        double v = 0.0;
+                        if (io.dx_ref) {
+#pragma unroll
+                            for (int j = 0; j < NX; ++j) v += p.Lref[a * NX + j] * io.dx_ref[q * NX + j];
+                        }
+                        m[L::M_LIN + a] = v;
+                    }
+                    if (io.dx_ref) {
+#pragma unroll
+                        for (int i = 0; i < NX; ++i)
+#pragma unroll
+                            for (int j = 0; j < NX; ++j)
+                                cconst += io.dx_ref[q * NX + i] * p.Tm[i * NX + j] * io.dx_ref[q * NX + j];
+                    }
+                    m[L::M_CCONST] = cconst;
+                    qpid[warp] = q;
+                    meta[warp * 4 + 1] = 0;
+                    meta[warp * 4 + 2] = 0;
+                }
+                state = SLOT_FRESH;
+            } else {
+                state = SLOT_EMPTY;
+            }
+            if (lane == 0) meta[warp * 4 + 0] = state;
+        }
+        const int nactive = __syncthreads_count(lane == 0 && state != SLOT_EMPTY);
+        if (nactive == 0) break;
+
+        // =====================================================================================
+        // phase D (sweep): corrector backward/forward substitution; initial rollout of fresh slots
+        // =====================================================================================
+        if (warp == 0 && lane < slots) {
+            double* const sl = smem + lane * l.stride;
+            const int st = meta[lane * 4 + 0];
+            if (st == SLOT_RUN) {
+                C::template backward<false>(p, l, sl, false, false);
+                C::forward(p, l, sl, false);
+            } else if (st == SLOT_FRESH) {
+                C::rollout(p, l, sl);
+            }
+        }
+        __syncthreads();
+
+        // =====================================================================================
+        // phase E+A: step length + update (RUN) or row initialisation (FRESH); then the
+        //            predictor assembly of the next iteration
+        // =====================================================================================
+        if (state == SLOT_RUN) {
+            const double sigmu = m[L::M_SIGMU];
+            RedStep rs{0.0, 0.0, 0.0, 0.0};
+            for (int k = lane; k <= N; k += 32) C::template step_stage<1>(p, l, slot, k, sigmu, rs);
+            for (int i = lane; i < p.ng; i += 32) C::template step_gen_row<1>(p, l, slot, Gs, hgs, i, sigmu, rs);
+            const double ratio = warp_max(rs.ratio);
+            double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
+            alpha = alpha > 1.0 ? 1.0 : alpha;
+            for (int i = lane; i < p.ng; i += 32) C::update_gen_row(p, l, slot, Gs, hgs, i, sigmu, alpha);
+            __syncwarp();
+            for (int k = lane; k <= N; k += 32) C::update_stage(p, l, slot, k, sigmu, alpha);
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
+                meta[warp * 4 + 1] += 1;
+            }
+            __syncwarp();
+        } else if (state == SLOT_FRESH) {
+            for (int k = lane; k <= N; k += 32) C::init_rows_stage(p, l, slot, k);
+            for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
+            state = SLOT_RUN;
+            if (lane == 0) meta[warp * 4 + 0] = SLOT_RUN;
+            __syncwarp();
+        }
+        if (state == SLOT_RUN) {
+            RedAsm ra{0.0, 0.0, 0.0, 0.0};
+            for (int k = lane; k <= N; k += 32) C::assemble_stage(p, l, slot, k, ra);
+            double acc[NACC];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+            for (int i = lane; i < p.ng; i += 32) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
+            const double rp = warp_max_nan(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) {
+                    m[L::M_GGL + a] = acc[NH + a];
+                    m[L::M_DG + a] = acc[NH + NZ + a];
+                }
+                m[L::M_RP] = rp;
+                m[L::M_MU] = sl * p.inv_m;
+                m[L::M_LAM] = lam;
+                m[L::M_HLAM] = hl;
+            }
+        }
+        __syncthreads();
+
+        // =====================================================================================
+        // phase B (sweep): Riccati factorisation + adjoint residual, verdict, affine forward sweep
+        // =====================================================================================
+        if (warp == 0 && lane < slots) {
+            double* const sl = smem + lane * l.stride;
+            if (meta[lane * 4 + 0] == SLOT_RUN) {
+                double* const ms = sl + l.o_misc;
+                int v;
+                if (meta[lane * 4 + 1] >= p.max_iter) {
+                    v = 1;  // LBMPC_ST_MAXITER
+                } else {
+                    const bool cert = ms[L::M_LAM] >= p.inf_trigger;
+                    const bool ok = C::template backward<true>(p, l, sl, true, cert);
+                    v = C::verdict(p, ms, ok, cert);
+                }
+                if (v >= 0) {
+                    meta[lane * 4 + 2] = v;
+                    meta[lane * 4 + 0] = SLOT_DONE;
+                } else {
+                    C::forward(p, l, sl, true);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// learned-model rollout: d_k = g([x1;x2;u_k]) , x_{k+1} = A x_k + B u_k + d_k        (warp per QP)
+// X: 3 x q x batch, Y: NX x q x batch (column-major, "one column per sample"), valid: q x batch
+// ---------------------------------------------------------------------------------------------
+constexpr int kOracleMaxPerLane = 16;  // q <= 512
+
+// PER = data points held in registers per lane (4: q <= 128, the reference's q = 10/50/100; 16: q <= 512)
+template <int NX, int NU, int PER>
+__global__ void __launch_bounds__(128)
+oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N, long long batch, int q,
+              double inv_h2, double lambda, const double* __restrict__ dx0, const double* __restrict__ du,
+              long long du_ld, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ valid,
+              double* __restrict__ d_off) {
+    constexpr int NI = 3;
+    const int lane = threadIdx.x & 31;
+    const long long qp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qp >= batch) return;
+    double xs[PER][NI], ys[PER][NX], vs[PER];
+    const int per = (q + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int i = lane + 32 * r;
+        const bool on = r < per && i < q;
+#pragma unroll
+        for (int a = 0; a < NI; ++a) xs[r][a] = on ? X[(qp * q + i) * NI + a] : 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) ys[r][a] = on ? Y[(qp * q + i) * NX + a] : 0.0;
+        vs[r] = on ? (valid ? valid[qp * q + i] : 1.0) : -1.0;  // -1: slot unused
+    }
+    double Am[NX * NX], Bm[NX * NU], x[NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) Am[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < NX * NU; ++i) Bm[i] = B[i];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = dx0[qp * NX + j];
+    for (int k = 0; k < N; ++k) {
+        double u[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = du[qp * du_ld + k * NU + i];
+        const double xi[NI] = {x[0], x[1], u[0]};
+        double sk = 0.0, g[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) g[a] = 0.0;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            if (r < per && vs[r] >= 0.0) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int a = 0; a < NI; ++a) {
+                    const double d = xs[r][a] - xi[a];
+                    d2 += d * d;
+                }
+                const double kv = exp(-d2 * inv_h2);
+                sk += valid ? kv * vs[r] : kv;
+#pragma unroll
+                for (int a = 0; a < NX; ++a) g[a] += ys[r][a] * kv;
+            }
+        }
+        sk = warp_sum(sk);
+        const double wn = 1.0 / (lambda + sk);
+        double xn[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            g[a] = warp_sum(g[a]) * wn;
+            double v = g[a];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += Am[a * NX + j] * x[j];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) v += Bm[a * NU + i] * u[i];
+            xn[a] = v;
+        }
+        if (lane < NX) {
+            double gv = g[0];
+#pragma unroll
+            for (int a = 1; a < NX; ++a) gv = lane == a ? g[a] : gv;
+            d_off[(qp * N + k) * NX + lane] = gv;
+        }
+#pragma unroll
+        for (int a = 0; a < NX; ++a) x[a] = xn[a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// closed loop plant step (thread per scenario): RK4 Moore-Greitzer, disturbance, data window,
+// warm-start shift, history.  C-form conventions (LBMPC_casadi.m:184-208).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mg_rhs(const double* x, double u, double* f) {
+    f[0] = -x[1] + 1.0 + 3.0 * (x[0] / 2.0) - (x[0] * x[0] * x[0] / 2.0);
+    f[1] = x[0] + 1.0 - x[2] * sqrt(x[1]);
+    f[2] = x[3];
+    f[3] = -1000.0 * x[2] - 2.0 * sqrt(500.0) * x[3] + 1000.0 * u;
+}
+__device__ __forceinline__ double lb_uniform(unsigned long long seed, unsigned long long scen,
+                                             unsigned long long step, unsigned long long comp) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (scen * 0x100000001B3ULL + step * 8ULL + comp + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct LoopState {
+    double* x;      // 4 x batch  absolute plant state
+    double* dx0;    // 4 x batch  x - x_eq (solver input)
+    double* X;      // 3 x q x batch
+    double* Y;      // 4 x q x batch
+    double* V;      // q x batch
+    int* nd;        // batch      samples in the window
+    double* warm;   // (N+1) x batch
+    const double *uc, *theta;  // solver outputs of this step
+    const int *iters, *status;
+    double *x_hist, *u_hist, *theta_hist;  // histories (may be null)
+    int *iters_hist, *status_hist;
+};
+
+__global__ void __launch_bounds__(128)
+plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict__ B, long long batch, int N,
+             int q, int step, int steps, double4 x_eq, double u_eq, double4 wbar, int use_w,
+             unsigned long long seed, unsigned long long scen0) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const double xe[4] = {x_eq.x, x_eq.y, x_eq.z, x_eq.w}, wb[4] = {wbar.x, wbar.y, wbar.z, wbar.w};
+    double x[4], dx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        x[j] = S.x[b * 4 + j];
+        dx[j] = x[j] - xe[j];
+    }
+    const double du0 = S.uc[b * N], u0 = du0 + u_eq;
+    double k1[4], k2[4], k3[4], k4[4], t[4], xn[4];
+    const double delta = 0.01;
+    mg_rhs(x, u0, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = x[i] + delta / 2 * k1[i];
+    mg_rhs(t, u0, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = x[i] + delta / 2 * k2[i];
+    mg_rhs(t, u0, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = x[i] + delta * k3[i];
+    mg_rhs(t, u0, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = x[i] + delta / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    if (use_w) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            xn[j] += wb[j] * (2.0 * lb_uniform(seed, scen0 + (unsigned long long)b, (unsigned long long)step,
+                                               (unsigned long long)j) - 1.0);
+    }
+    // data acquisition: X = [dx1;dx2;du], Y = dx+ - (A dx + B du)
+    double ys[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double v = xn[a] - xe[a];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v -= A[a * 4 + j] * dx[j];
+        v -= B[a] * du0;
+        ys[a] = v;
+    }
+    const double xs[3] = {dx[0], dx[1], du0};
+    int nd = S.nd[b];
+    double* Xb = S.X + b * 3 * q;
+    double* Yb = S.Y + b * 4 * q;
+    double* Vb = S.V + b * q;
+    if (nd >= q) {  // get_data.m:8 : drop the oldest sample
+        for (int i = 0; i + 1 < q; ++i) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) Xb[i * 3 + a] = Xb[(i + 1) * 3 + a];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) Yb[i * 4 + a] = Yb[(i + 1) * 4 + a];
+        }
+        nd = q - 1;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Xb[nd * 3 + a] = xs[a];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) Yb[nd * 4 + a] = ys[a];
+    Vb[nd] = 1.0;
+    S.nd[b] = nd + 1;
+    // warm-start shift
+    double* wm = S.warm + b * (N + 1);
+    for (int k = 0; k + 1 < N; ++k) wm[k] = S.uc[b * N + k + 1];
+    wm[N - 1] = S.uc[b * N + N - 1];
+    wm[N] = S.theta[b];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        S.x[b * 4 + j] = xn[j];
+        S.dx0[b * 4 + j] = xn[j] - xe[j];
+        if (S.x_hist) S.x_hist[(b * (steps + 1) + step + 1) * 4 + j] = xn[j];
+    }
+    if (S.u_hist) S.u_hist[b * steps + step] = u0;
+    if (S.theta_hist) S.theta_hist[b * steps + step] = S.theta[b];
+    if (S.iters_hist) S.iters_hist[b * steps + step] = S.iters[b];
+    if (S.status_hist) S.status_hist[b * steps + step] = S.status[b];
+}
+
+__global__ void loop_init_kernel(LoopState S, const double* __restrict__ x_init, long long batch, int steps,
+                                 double4 x_eq) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const double xe[4] = {x_eq.x, x_eq.y, x_eq.z, x_eq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double v = x_init[b * 4 + j];
+        S.x[b * 4 + j] = v;
+        S.dx0[b * 4 + j] = v - xe[j];
+        if (S.x_hist) S.x_hist[(b * (steps + 1)) * 4 + j] = v;
+    }
+    S.nd[b] = 0;
+}
+
+}  // namespace lbmpc

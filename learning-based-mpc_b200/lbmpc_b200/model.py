@@ -1,0 +1,113 @@
+"""Host-side (offline) model setup — the Python mirror of the reference's setup functions.
+
+These run once per script on the host in the reference too (MATLAB Symbolic/Control toolboxes,
+MPT3); they are inputs of the hot path, not part of it:
+
+  mgcmDLTI()    functions/mgcmDLTI.m:1-43    linearise + exact discretisation (Ts = 0.01)
+  matOCP()      functions/matOCP.m:1-33      K by pole placement, steady-state map, Q,R,P,T
+  getCONS()     functions/getCONS.m:1-60     boxes + precomputed LMPC terminal set (term_set.mat)
+  getCONSPOLY() functions/getCONSPOLY.m:1-74 boxes, X(-)D and the robust terminal set.  MPT3 is not
+                available here: the robust sets for the reference's default uncertainty bound
+                state_uncert=[0.02;5e-4;0;0] (LBMPC_RunExample.m:38) ship as data
+                (data/moore_greitzer_sets.npz, taken from the reference's saved workspace).
+"""
+import os
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.signal as ssig
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "moore_greitzer_sets.npz")
+
+# working point of the Moore-Greitzer compressor (LBMPC_RunExample.m:52-56)
+X_WP = np.array([0.5, 1.6875, 1.1547, 0.0])
+U_WP = 1.1547
+
+
+def mgcmDLTI():
+    """[A,B,C,D,Ts] of mgcmDLTI.m: Jacobian of the MGCM ODE at the working point, then
+    Ad = expm(A Ts), Bd = (Ad - I) A^-1 B (mgcmDLTI.m:24-39)."""
+    wn, zeta, beta = np.sqrt(1000.0), 1.0 / np.sqrt(2.0), 1.0
+    x1, x2, x3 = X_WP[0], X_WP[1], X_WP[2]
+    A = np.array([[1.5 - 1.5 * x1 ** 2, -1.0, 0.0, 0.0],
+                  [1.0 / beta ** 2, -x3 / (2.0 * np.sqrt(x2)) / beta ** 2, -np.sqrt(x2) / beta ** 2, 0.0],
+                  [0.0, 0.0, 0.0, 1.0],
+                  [0.0, 0.0, -wn ** 2, -2.0 * zeta * wn]])
+    B = np.array([[0.0], [0.0], [0.0], [wn ** 2]])
+    Ts = 0.01
+    Ad = sla.expm(A * Ts)
+    Bd = (Ad - np.eye(4)) @ np.linalg.solve(A, B)
+    return Ad, Bd, np.eye(4), np.zeros((4, 1)), Ts
+
+
+def matOCP(A, B, C=None):
+    """[Ks,Klqr,Q,R,P,T,Mtheta,LAMBDA,PSI,LAMBDA_0,PSI_0] of matOCP.m."""
+    n, m = B.shape
+    C = np.eye(n) if C is None else C
+    o = C.shape[0]
+    K = ssig.place_poles(A, B, [0.75, 0.78, 0.98, 0.99][:n]).gain_matrix   # matOCP.m:7-8
+    Ks = -K
+    M = np.block([[A - np.eye(n), B, np.zeros((n, o))], [C, np.zeros((o, m)), -np.eye(o)]])
+    Mtheta = sla.null_space(M)                                             # matOCP.m:12-16
+    if Mtheta[0, 0] < 0:                                                   # MATLAB's null() sign
+        Mtheta = -Mtheta
+    LAMBDA, PSI = Mtheta[:n, :], Mtheta[n:n + m, :]
+    Q, R = np.eye(n), np.eye(m)
+    Klqr = -_dlqr(A, B, Q, R)
+    P = sla.solve_discrete_are(A + B @ Ks, B, Q, R)                        # matOCP.m:30
+    T = 1000.0
+    return Ks, Klqr, Q, R, P, T, Mtheta, LAMBDA, PSI, np.zeros((n, 1)), np.zeros((m, 1))
+
+
+def _dlqr(A, B, Q, R):
+    X = sla.solve_discrete_are(A, B, Q, R)
+    return np.linalg.solve(R + B.T @ X @ B, B.T @ X @ A)
+
+
+def _boxes(xmax, xmin, umax, umin, x_wp, u_wp):
+    xmax, xmin = np.atleast_1d(xmax).astype(float), np.atleast_1d(xmin).astype(float)
+    umax, umin = np.atleast_1d(umax).astype(float), np.atleast_1d(umin).astype(float)
+    n, m = xmax.size, umax.size
+    F_u = np.vstack([np.eye(m), -np.eye(m)]); h_u = np.concatenate([umax - u_wp, -umin + u_wp])
+    F_x = np.vstack([np.eye(n), -np.eye(n)]); h_x = np.concatenate([xmax - x_wp, -xmin + x_wp])
+    return F_x, h_x, F_u, h_u
+
+
+# default physical limits (LBMPC_RunExample.m:26-34)
+XMAX = np.array([1.0, 2.1875, 2.1547, 20.0])
+XMIN = np.array([0.0, 1.1875, 0.1547, -20.0])
+UMAX, UMIN = 2.1547, 0.1547
+
+
+def getCONS(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, x_wp=X_WP, u_wp=U_WP):
+    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N] of getCONS.m: boxes (:15-16) + precomputed terminal set (:57-58)."""
+    F_x, h_x, F_u, h_u = _boxes(xmax, xmin, umax, umin, x_wp, u_wp)
+    d = np.load(_DATA)
+    return F_x, h_x, F_u, h_u, d["term_set_F_w_N"].copy(), d["term_set_h_w_N"].copy()
+
+
+def getCONSPOLY(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, state_uncert=(0.02, 5e-4, 0.0, 0.0), x_wp=X_WP,
+                u_wp=U_WP):
+    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d] of getCONSPOLY.m for the reference's default
+    uncertainty bound; other bounds need the MPT-free set computation (lbmpc_b200.sets, when present)."""
+    if not np.allclose(state_uncert, (0.02, 5e-4, 0.0, 0.0)):
+        raise NotImplementedError("only the reference's default state_uncert ships as data")
+    F_x, h_x, F_u, h_u = _boxes(xmax, xmin, umax, umin, x_wp, u_wp)
+    d = np.load(_DATA)
+    return (F_x, h_x, F_u, h_u, d["lbmpc_F_w_N"].copy(), d["lbmpc_h_w_N"].copy(), d["lbmpc_F_x_d"].copy(),
+            d["lbmpc_h_x_d"].copy())
+
+
+def moore_greitzer_model(variant="LMPC"):
+    """Convenience: dict with every matrix of the ocpLBMPC.m:1-6 argument list."""
+    A, B, C, D, Ts = mgcmDLTI()
+    Ks, Klqr, Q, R, P, T, Mtheta, LAMBDA, PSI, L0, P0 = matOCP(A, B, C)
+    mdl = dict(A=A, B=B, K=Ks, Klqr=Klqr, Q=Q, R=R, P=P, T=T, Mtheta=Mtheta, LAMBDA=LAMBDA, PSI=PSI, Ts=Ts,
+               x_wp=X_WP.copy(), u_wp=U_WP)
+    if variant == "LMPC":
+        F_x, h_x, F_u, h_u, F_w_N, h_w_N = getCONS()
+    else:
+        F_x, h_x, F_u, h_u, F_w_N, h_w_N, F_x_d, h_x_d = getCONSPOLY()
+        mdl.update(F_x_d=F_x_d, h_x_d=h_x_d)
+    mdl.update(F_x=F_x, h_x=h_x, F_u=F_u, h_u=h_u, F_w_N=F_w_N, h_w_N=h_w_N)
+    return mdl

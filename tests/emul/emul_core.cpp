@@ -1,0 +1,128 @@
+// emul_core.cpp — TEST-ONLY host harness for learning-based-mpc_b200/csrc/lbmpc_core.cuh.
+// Runs the per-QP device functions (compiled for the host) in the same phase order the CUDA
+// kernel uses, one QP at a time, so the arithmetic of every phase can be checked against the
+// oracle on a machine without a GPU.  It is never linked into the product library.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../learning-based-mpc_b200/csrc/lbmpc_problem.hpp"
+
+using namespace lbmpc;
+
+template <int NX, int NT, int NU>
+static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off,
+                     const double* warm, double* uc, double* theta, double* xtraj, double* obj, int* iters,
+                     int* status) {
+    using C = Core<NX, NT, NU>;
+    using L = Layout<NX, NT, NU>;
+    constexpr int NZ = NX + NT, NH = L::NH;
+    const Params<NX, NT, NU> p = to_params<NX, NT, NU>(hp);
+    const L l(p.N, p.ngp);
+    std::vector<double> buf(l.stride, 0.0);
+    double* s = buf.data();
+    double* m = s + l.o_misc;
+    const double *G = hp.G.data(), *hg = hp.hg.data();
+    const int N = p.N;
+    // ---- load (kernel: warp-parallel) ----
+    for (int j = 0; j < NX; ++j) s[l.o_x + j * l.Np] = dx0[j];
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < NU; ++i) s[l.o_u + i * l.Np + k] = warm ? warm[k * NU + i] : 0.0;
+        for (int j = 0; j < NX; ++j) s[l.o_x + j * l.Np + k + 1] = d_off ? d_off[k * NX + j] : 0.0;
+    }
+    for (int t = 0; t < NT; ++t) m[L::M_TH + t] = warm ? warm[N * NU + t] : 0.0;
+    double cconst = 0.0;
+    for (int a = 0; a < NZ; ++a) {
+        double v = 0.0;
+        if (dx_ref)
+            for (int j = 0; j < NX; ++j) v += p.Lref[a * NX + j] * dx_ref[j];
+        m[L::M_LIN + a] = v;
+    }
+    if (dx_ref)
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NX; ++j) cconst += dx_ref[i] * p.Tm[i * NX + j] * dx_ref[j];
+    m[L::M_CCONST] = cconst;
+    C::rollout(p, l, s);
+    for (int k = 0; k <= N; ++k) C::init_rows_stage(p, l, s, k);
+    for (int i = 0; i < p.ng; ++i) C::init_rows_gen(p, l, s, G, hg, i);
+    int it = 0, st = 1;
+    for (it = 0; it < p.max_iter; ++it) {
+        RedAsm ra{0, 0, 0, 0};
+        for (int k = 0; k <= N; ++k) C::assemble_stage(p, l, s, k, ra);
+        double acc[NH + 2 * NZ];
+        std::memset(acc, 0, sizeof acc);
+        for (int i = 0; i < p.ng; ++i) C::assemble_gen_row(p, l, s, G, hg, i, acc, ra);
+        for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
+        for (int a = 0; a < NZ; ++a) { m[L::M_GGL + a] = acc[NH + a]; m[L::M_DG + a] = acc[NH + NZ + a]; }
+        m[L::M_RP] = ra.rp; m[L::M_MU] = ra.sl * p.inv_m; m[L::M_LAM] = ra.lam; m[L::M_HLAM] = ra.hl;
+        const bool cert = ra.lam >= p.inf_trigger;
+        const bool ok = C::template backward<true>(p, l, s, true, cert);
+        const int v = C::verdict(p, m, ok, cert);
+        if (v >= 0) { st = v; break; }
+        C::forward(p, l, s, true);
+        RedStep rs{0, 0, 0, 0};
+        for (int k = 0; k <= N; ++k) C::template step_stage<0>(p, l, s, k, 0.0, rs);
+        for (int i = 0; i < p.ng; ++i) C::template step_gen_row<0>(p, l, s, G, hg, i, 0.0, rs);
+        const double aaff = rs.ratio > 1.0 ? 1.0 / rs.ratio : 1.0;
+        const double mu_aff = (rs.s0 + aaff * rs.s1 + aaff * aaff * rs.s2) * p.inv_m;
+        const double sr = mu_aff / m[L::M_MU];
+        const double sigmu = sr * sr * sr * m[L::M_MU];
+        m[L::M_SIGMU] = sigmu;
+        for (int k = 0; k <= N; ++k) C::corrector_stage(p, l, s, k, sigmu);
+        double dg[NZ];
+        std::memset(dg, 0, sizeof dg);
+        for (int i = 0; i < p.ng; ++i) C::corrector_gen_row(p, l, s, G, hg, i, sigmu, dg);
+        for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a];
+        C::template backward<false>(p, l, s, false, false);
+        C::forward(p, l, s, false);
+        RedStep r2{0, 0, 0, 0};
+        for (int k = 0; k <= N; ++k) C::template step_stage<1>(p, l, s, k, sigmu, r2);
+        for (int i = 0; i < p.ng; ++i) C::template step_gen_row<1>(p, l, s, G, hg, i, sigmu, r2);
+        double alpha = r2.ratio > 0.0 ? 0.99 / r2.ratio : 1.0;
+        if (alpha > 1.0) alpha = 1.0;
+        for (int i = 0; i < p.ng; ++i) C::update_gen_row(p, l, s, G, hg, i, sigmu, alpha);
+        for (int k = 0; k <= N; ++k) C::update_stage(p, l, s, k, sigmu, alpha);
+        for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
+    }
+    double J = m[L::M_CCONST];
+    for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k);
+    for (int k = 0; k < N; ++k)
+        for (int i = 0; i < NU; ++i) {
+            double v = s[l.o_u + i * l.Np + k];
+            for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * s[l.o_x + j * l.Np + k];
+            uc[k * NU + i] = v;
+        }
+    for (int t = 0; t < NT; ++t) theta[t] = m[L::M_TH + t];
+    if (xtraj)
+        for (int k = 0; k <= N; ++k)
+            for (int j = 0; j < NX; ++j) xtraj[k * NX + j] = s[l.o_x + j * l.Np + k];
+    *obj = J; *iters = it; *status = st;
+    return 0;
+}
+
+static thread_local std::string g_err;
+
+extern "C" const char* emul_last_error() { return g_err.c_str(); }
+
+// same argument conventions as lbmpc_create + lbmpc_solve_batch (column-major, one column per QP)
+extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg, long batch, const double* dx0,
+                                const double* dx_ref, const double* d_off, const double* warm, double* uc,
+                                double* theta, double* xtraj, double* obj, int* iters, int* status) {
+    HostProblem hp;
+    int rc = build_problem(mdl, cfg, hp, g_err);
+    if (rc) return rc;
+    const int nx = hp.nx, nu = hp.nu, nt = hp.nt, N = hp.N;
+    for (long b = 0; b < batch; ++b) {
+        const double* x0 = dx0 + b * nx;
+        const double* xr = dx_ref ? dx_ref + b * nx : nullptr;
+        const double* dk = d_off ? d_off + b * (long)nx * N : nullptr;
+        const double* wm = warm ? warm + b * (long)(nu * N + nt) : nullptr;
+        double* xt = xtraj ? xtraj + b * (long)nx * (N + 1) : nullptr;
+        if (nx == 4 && nt == 1 && nu == 1)
+            solve_one<4, 1, 1>(hp, x0, xr, dk, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
+        else if (nx == 2 && nt == 2 && nu == 2)
+            solve_one<2, 2, 2>(hp, x0, xr, dk, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
+        else { g_err = "emul: unsupported dims"; return LBMPC_ESHAPE; }
+    }
+    return 0;
+}
