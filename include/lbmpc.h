@@ -82,7 +82,9 @@ typedef struct lbmpc_config {
     double delta;              /* C-form stage weight (DMS_tracking_LMPC_casadi.m:84); ignored in F-form */
     double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1,|lambda|inf)           */
     double tol_mu;             /* 0 -> 1e-10  complementarity gap                                  */
-    double eps_inf;            /* 0 -> 1e-8   Farkas-certificate tolerance (status 2)              */
+    double inf_radius;         /* 0 -> auto   Farkas test radius R: status 2 when h'lambda < 0 and
+                                  |G'lambda|inf R <= -h'lambda (reduced space); auto = 2 x (sum of input
+                                  bounds + 10 per unbounded variable)                               */
     int32_t max_iter;          /* 0 -> 60                                                          */
     int64_t max_batch;         /* largest batch of one solve call (device I/O staging is sized on it) */
     int32_t pointers_on_device;/* 0: batch arrays are host pointers (calls are synchronous);
@@ -138,6 +140,10 @@ int lbmpc_slots_per_cta(const lbmpc_handle *h);       /* QPs resident per CTA (s
 int64_t lbmpc_kernel_launches(const lbmpc_handle *h); /* kernels launched by this handle so far          */
 /* last solve call: device time of the IPM kernel in ms (CUDA events on the launch stream) */
 float lbmpc_last_kernel_ms(lbmpc_handle *h);
+
+/* roofline denominator: measured FP64-FMA throughput of the device in TFLOP/s (register-resident DFMA
+ * chains, best of 5 after one warm-up; MEASURED_PEAKS.json carries no FP64 entry) */
+int lbmpc_measure_fp64_peak(int device, double *tflops);
 
 void lbmpc_destroy(lbmpc_handle *h);
 const char *lbmpc_last_error(void);                  /* thread-local message of the last failure         */

@@ -380,6 +380,38 @@ float lbmpc_last_kernel_ms(lbmpc_handle* h) {
     return ms;
 }
 
+int lbmpc_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(LBMPC_EINVAL, "tflops is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(LBMPC_ECUDA, "no usable CUDA device");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CU_TRY(dmalloc(&d, 1));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, threads>>>(d, iters, 1.0000001, 1e-9);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * (double)threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return LBMPC_OK;
+}
+
 void lbmpc_destroy(lbmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);

@@ -43,7 +43,7 @@ struct Params {
     double W[kMaxTypes][NV * NV];                                  // stage Hessians, v=[x;theta;u]
     double lo[NVB], hi[NVB];
     double Lref[NZ * NX], Tm[NX * NX];
-    double tol_res, tol_mu, eps_inf, inf_trigger, inv_m;
+    double tol_res, tol_mu, inf_trigger, inf_radius, inv_m;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -835,7 +835,7 @@ struct Core {
         if (!pivots_ok || !(rd == rd) || !(rp == rp) || !(mu == mu) || isinf(rd) || isinf(mu)) return 3;
         const double rd_tol = p.tol_res * (lam > 1.0 ? lam : 1.0);
         if (rd < rd_tol && rp < p.tol_res && mu < p.tol_mu) return 0;
-        if (cert && m[L::M_CERT] <= p.eps_inf * lam && m[L::M_HLAM] < -p.eps_inf * lam) return 2;
+        if (cert && m[L::M_HLAM] < 0.0 && m[L::M_CERT] * p.inf_radius <= -m[L::M_HLAM]) return 2;
         return -1;
     }
 };

@@ -578,4 +578,21 @@ __global__ void loop_init_kernel(LoopState S, const double* __restrict__ x_init,
     S.nd[b] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// FP64-FMA peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
+// 8 independent register-resident DFMA chains per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+            c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+        }
+    }
+    const double s = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
 }  // namespace lbmpc

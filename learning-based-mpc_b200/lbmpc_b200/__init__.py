@@ -6,9 +6,9 @@ include/lbmpc.h); this package only packs arguments, mirrors the reference's fun
 across ranks.  Nothing here computes a solve on the CPU.
 """
 from .capi import (FORM, VARIANT, ST_OPTIMAL, ST_MAXITER, ST_INFEASIBLE, ST_NUMERICAL, LbmpcError, Solver,
-                   load_library, pack_model, make_config)
+                   load_library, pack_model, make_config, measure_fp64_peak)
 from .model import (mgcmDLTI, matOCP, getCONS, getCONSPOLY, moore_greitzer_model, X_WP, U_WP)
 
 __all__ = ["FORM", "VARIANT", "ST_OPTIMAL", "ST_MAXITER", "ST_INFEASIBLE", "ST_NUMERICAL", "LbmpcError", "Solver",
-           "load_library", "pack_model", "make_config", "mgcmDLTI", "matOCP", "getCONS", "getCONSPOLY",
+           "load_library", "pack_model", "make_config", "measure_fp64_peak", "mgcmDLTI", "matOCP", "getCONS", "getCONSPOLY",
            "moore_greitzer_model", "X_WP", "U_WP"]

@@ -35,7 +35,7 @@ class LbmpcModel(C.Structure):
 class LbmpcConfig(C.Structure):
     """struct lbmpc_config (include/lbmpc.h)."""
     _fields_ = [("form", C.c_int32), ("variant", C.c_int32), ("N", C.c_int32), ("delta", C.c_double),
-                ("tol_res", C.c_double), ("tol_mu", C.c_double), ("eps_inf", C.c_double),
+                ("tol_res", C.c_double), ("tol_mu", C.c_double), ("inf_radius", C.c_double),
                 ("max_iter", C.c_int32), ("max_batch", C.c_int64), ("pointers_on_device", C.c_int32)]
 
 
@@ -74,11 +74,11 @@ def pack_model(mdl):
     return m, list(arrs.values())
 
 
-def make_config(form, variant, N, delta=0.01, tol_res=0.0, tol_mu=0.0, eps_inf=0.0, max_iter=0, max_batch=1024,
+def make_config(form, variant, N, delta=0.01, tol_res=0.0, tol_mu=0.0, inf_radius=0.0, max_iter=0, max_batch=1024,
                 pointers_on_device=False):
     c = LbmpcConfig()
     c.form, c.variant, c.N, c.delta = FORM[form], VARIANT[variant], int(N), float(delta)
-    c.tol_res, c.tol_mu, c.eps_inf, c.max_iter = tol_res, tol_mu, eps_inf, int(max_iter)
+    c.tol_res, c.tol_mu, c.inf_radius, c.max_iter = tol_res, tol_mu, inf_radius, int(max_iter)
     c.max_batch, c.pointers_on_device = int(max_batch), int(bool(pointers_on_device))
     return c
 
@@ -112,6 +112,8 @@ def load_library(path=None):
     lib.lbmpc_kernel_launches.restype = C.c_int64
     lib.lbmpc_last_kernel_ms.argtypes = [vp]
     lib.lbmpc_last_kernel_ms.restype = C.c_float
+    lib.lbmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.lbmpc_measure_fp64_peak.restype = C.c_int
     lib.lbmpc_destroy.argtypes = [vp]
     lib.lbmpc_destroy.restype = None
     lib.lbmpc_last_error.restype = C.c_char_p
@@ -123,6 +125,16 @@ def load_library(path=None):
 
 class LbmpcError(RuntimeError):
     pass
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64-FMA peak of the device in TFLOP/s (lbmpc_measure_fp64_peak)."""
+    lib = load_library()
+    v = C.c_double()
+    rc = lib.lbmpc_measure_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise LbmpcError(f"lbmpc_measure_fp64_peak failed ({rc}): {lib.lbmpc_last_error().decode()}")
+    return v.value
 
 
 def _ptr(a):
@@ -145,10 +157,10 @@ class Solver:
     """
 
     def __init__(self, mdl, form, variant, N, delta=0.01, device=0, max_batch=1024, device_pointers=False,
-                 tol_res=0.0, tol_mu=0.0, eps_inf=0.0, max_iter=0, lib=None):
+                 tol_res=0.0, tol_mu=0.0, inf_radius=0.0, max_iter=0, lib=None):
         self.lib = lib or load_library()
         self._model, self._keep = pack_model(mdl)
-        self._cfg = make_config(form, variant, N, delta, tol_res, tol_mu, eps_inf, max_iter, max_batch,
+        self._cfg = make_config(form, variant, N, delta, tol_res, tol_mu, inf_radius, max_iter, max_batch,
                                 device_pointers)
         self.nx, self.nu, self.nt, self.N = self._model.nx, self._model.nu, self._model.nt, int(N)
         self.form, self.variant, self.device, self.device_pointers = form, variant, device, device_pointers

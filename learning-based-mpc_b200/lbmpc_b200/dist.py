@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: one process per GPU, QPs sharded by contiguous index range, no collective
+inside the solve.  torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests) only
+gathers the per-rank results and reduces a handful of statistics."""
+import numpy as np
+
+
+def shard_range(batch, rank, world):
+    """Contiguous range [lo, hi) of rank `rank`: sizes differ by at most one, union = [0, batch)."""
+    base, rem = divmod(int(batch), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local, batch, group=None, dst=None):
+    """All-gather (dst=None) or gather-to-dst of a dict of per-QP arrays sharded with shard_range.
+
+    `local` maps name -> torch tensor whose first dimension is the local shard.  Shards may differ in
+    length by one, so they are padded to the longest before the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    out = {}
+    for name, t in local.items():
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        if dst is None:
+            bufs = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(bufs, pad, group=group)
+        else:
+            bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+            dist.gather(pad, bufs, dst=dst, group=group)
+        if bufs is not None:
+            out[name] = torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+    return out
+
+
+def reduce_stats(status, iters, obj, group=None):
+    """{n_optimal, n_maxiter, n_infeasible, n_numerical, sum_iters, max_iters, sum_obj_optimal} over all ranks."""
+    import torch
+    import torch.distributed as dist
+    st = status.to(torch.int64)
+    sums = torch.stack([(st == k).sum() for k in range(4)] + [iters.to(torch.int64).sum()]).to(torch.float64)
+    sums = torch.cat([sums, torch.where(st == 0, obj, torch.zeros_like(obj)).sum().reshape(1)])
+    mx = iters.max().to(torch.float64).reshape(1) if iters.numel() else torch.zeros(1, dtype=torch.float64, device=obj.device)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    s = sums.tolist()
+    return dict(n_optimal=int(s[0]), n_maxiter=int(s[1]), n_infeasible=int(s[2]), n_numerical=int(s[3]),
+                sum_iters=int(s[4]), max_iters=int(mx.item()), sum_obj_optimal=s[5])
+
+
+def sample_initial_states(batch, seed, lo=(-0.40, -0.45, -0.05, -1.0), hi=(0.10, 0.10, 0.05, 1.0), first=None):
+    """i.i.d. uniform initial conditions of the bench configs; element 0 is the
+    reference's canonical start [-0.35;-0.4;0;0] (LBMPC_RunExample.m:41-44).  Deterministic in the GLOBAL
+    index, so a shard is a slice of the same array regardless of the world size."""
+    rng = np.random.default_rng(seed)
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    x = lo + (hi - lo) * rng.random((int(batch), lo.size))
+    if batch > 0:
+        x[0] = [-0.35, -0.4, 0.0, 0.0] if first is None else first
+    return x

@@ -20,8 +20,9 @@
  *              corrector: r_c = s.lambda + ds_a.dl_a - sigma mu ; alpha = min(1, 0.99 alpha_max)
  *              both Newton systems solved by ONE Riccati factorisation over the augmented state
  *              z = [x;theta] (backward sweep) + two backward/forward substitution sweeps
- *   infeasible when lambda/|lambda|_inf is a Farkas certificate to eps_inf (checked once
- *              |lambda|_inf >= 1e6)
+ *   infeasible when lambda is a Farkas certificate on the ball |[u;theta]|_1 <= R that contains the
+ *              box-feasible set:  h_red'lambda < 0 and |G_red'lambda|_inf R <= -h_red'lambda
+ *              (checked once |lambda|_inf >= 1e2; R = 2 x sum of input bounds, 10 per unbounded var)
  */
 #include "lbmpc_oracle.h"
 
@@ -57,7 +58,7 @@ struct lbo_problem {
     int ng, kg;
     double *G, *hg; /* ng*nz, ng */
     int m_rows;
-    double tol_res, tol_mu, eps_inf, inf_trigger;
+    double tol_res, tol_mu, inf_trigger, inf_radius;
     int max_iter;
 };
 
@@ -142,7 +143,7 @@ static lbo_problem *alloc_problem(int nx, int nu, int nt, int N) {
     p->nx = nx; p->nu = nu; p->nt = nt; p->nz = nx + nt; p->nv = nx + nt + nu; p->nvb = nx + nu;
     p->N = N;
     p->wtype = (int *)calloc((size_t)N + 1, sizeof(int));
-    p->tol_res = 1e-9; p->tol_mu = 1e-10; p->eps_inf = 1e-8; p->inf_trigger = 1e6;
+    p->tol_res = 1e-9; p->tol_mu = 1e-10; p->inf_trigger = 1e2;
     p->max_iter = 60;
     return p;
 }
@@ -184,6 +185,16 @@ static void count_rows(lbo_problem *p) {
             m += isfinite(p->lo[j]) ? 1 : 0;
         }
     p->m_rows = m;
+    /* radius of the Farkas test: twice an upper bound of |[u;theta]|_1 over the feasible set
+     * (box bounds where they exist, 10 per unbounded variable) */
+    double R = 10.0 * p->nt;
+    for (int k = 0; k < p->N; ++k)
+        for (int j = p->nx; j < p->nvb; ++j) {
+            const int in = (k >= p->ku0 && k <= p->ku1);
+            const double b = fmax(fabs(p->lo[j]), fabs(p->hi[j]));
+            R += (in && isfinite(b)) ? b : 10.0;
+        }
+    p->inf_radius = 2.0 * R;
 }
 
 static void set_ref_terms(lbo_problem *p, const double *T, const double *Lam, int kT) {
@@ -309,11 +320,11 @@ void lbo_destroy(lbo_problem *p) {
     free(p->wtype); free(p->G); free(p->hg); free(p);
 }
 
-void lbo_set_options(lbo_problem *p, double tol_res, double tol_mu, int max_iter, double eps_inf) {
+void lbo_set_options(lbo_problem *p, double tol_res, double tol_mu, int max_iter, double inf_radius) {
     if (tol_res > 0) p->tol_res = tol_res;
     if (tol_mu > 0) p->tol_mu = tol_mu;
     if (max_iter > 0) p->max_iter = max_iter;
-    if (eps_inf > 0) p->eps_inf = eps_inf;
+    if (inf_radius > 0) p->inf_radius = inf_radius;
 }
 
 int lbo_num_rows(const lbo_problem *p) { return p->m_rows; }
@@ -768,7 +779,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
             const double rd_tol = p->tol_res * (lam_inf > 1.0 ? lam_inf : 1.0);
             if (rd_inf < rd_tol && rp_inf < p->tol_res && mu < p->tol_mu) { st = LBO_ST_OPTIMAL; break; }
         }
-        if (want_cert && cert[0] <= p->eps_inf * lam_inf && hlam + cert[1] < -p->eps_inf * lam_inf) {
+        if (want_cert && hlam + cert[1] < 0.0 && cert[0] * p->inf_radius <= -(hlam + cert[1])) {
             st = LBO_ST_INFEASIBLE; break;
         }
         forward(p, w);

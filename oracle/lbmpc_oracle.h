@@ -60,7 +60,7 @@ lbo_problem *lbo_create(int form, int variant, int nx, int nu, int nt, int N, do
                         const double *hw, int nFw, const double *Fxd, const double *hxd, int nFxd);
 void lbo_destroy(lbo_problem *p);
 const char *lbo_last_error(void);
-void lbo_set_options(lbo_problem *p, double tol_res, double tol_mu, int max_iter, double eps_inf);
+void lbo_set_options(lbo_problem *p, double tol_res, double tol_mu, int max_iter, double inf_radius);
 /* General custom-shape entry used for the trackingMPC double integrator
  * (trackingMPC/costFunction.m:20-39, constraintsFunction.m:20-38): stage weights and ranges given
  * explicitly.  wq/wr: N entries, kP: stage carrying the P and T terms, x rows on k in [kx0,kx1],

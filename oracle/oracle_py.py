@@ -103,8 +103,8 @@ class OracleProblem:
         self.form = self.variant = "custom"
         return self
 
-    def set_options(self, tol_res=0.0, tol_mu=0.0, max_iter=0, eps_inf=0.0):
-        lib().lbo_set_options(self.h, tol_res, tol_mu, max_iter, eps_inf)
+    def set_options(self, tol_res=0.0, tol_mu=0.0, max_iter=0, inf_radius=0.0):
+        lib().lbo_set_options(self.h, tol_res, tol_mu, max_iter, inf_radius)
 
     @property
     def num_rows(self):

@@ -1,0 +1,60 @@
+"""The product's per-QP arithmetic (learning-based-mpc_b200/csrc/lbmpc_core.cuh + the canonical-form builder
+lbmpc_problem.hpp) compiled for the host and driven in the kernel's phase order, vs the oracle.  This is the
+no-GPU half of the parity gate; the GPU half is tests/test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, sample_ics
+from lbmpc_b200 import capi
+from oracle_py import OracleProblem
+
+
+def emul_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None):
+    m, keep = capi.pack_model(mdl)
+    cfg = capi.make_config(form, variant, N)
+    dx0 = np.ascontiguousarray(dx0, float)
+    nb = dx0.shape[0]
+    nx, nu, nt = m.nx, m.nu, m.nt
+    o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)), xtraj=np.empty((nb, N + 1, nx)), obj=np.empty(nb),
+             iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32))
+    p = capi._ptr
+    c = lambda a: None if a is None else np.ascontiguousarray(a, float)
+    dx_ref, d_off, warm = c(dx_ref), c(d_off), c(warm)
+    rc = lib.emul_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), p(dx0), p(dx_ref), p(d_off), p(warm), p(o["uc"]),
+                              p(o["theta"]), p(o["xtraj"]), p(o["obj"]), p(o["iters"]), p(o["status"]))
+    assert rc == 0, lib.emul_last_error()
+    return o
+
+
+@pytest.mark.parametrize("form", ["F", "C"])
+@pytest.mark.parametrize("variant", ["LMPC", "LBMPC"])
+@pytest.mark.parametrize("N", [3, 20, 50])
+def test_core_matches_oracle(emul_lib, models, form, variant, N):
+    mdl = models[variant]
+    X0 = sample_ics(96, seed=N)
+    got = emul_solve(emul_lib, mdl, form, variant, N, X0)
+    ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, nthreads=4)
+    assert_parity(got, ref)
+
+
+def test_core_inputs_ref_offsets_warm(emul_lib, models):
+    mdl = models["LBMPC"]
+    N, nb = 40, 24
+    rng = np.random.default_rng(11)
+    X0 = sample_ics(nb, seed=2)
+    xref = (mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.1, 0.1, (nb, 1)))
+    doff = 1e-4 * rng.standard_normal((nb, N, 4))
+    warm = np.concatenate([0.05 * rng.standard_normal((nb, N)), 0.01 * rng.standard_normal((nb, 1))], axis=1)
+    got = emul_solve(emul_lib, mdl, "C", "LBMPC", N, X0, xref, doff, warm)
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, xref, doff, warm)
+    assert_parity(got, ref)
+
+
+def test_long_horizon(emul_lib, models):
+    mdl = models["LBMPC"]
+    X0 = sample_ics(8, seed=4)
+    got = emul_solve(emul_lib, mdl, "C", "LBMPC", 200, X0)
+    ref = OracleProblem("C", "LBMPC", mdl, 200).solve_batch(X0)
+    assert_parity(got, ref)

@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/lbmpc.h -> liblbmpc_b200.so), against
+the CPU oracle on the same seeded inputs, against the reference's golden fixtures, and — at BASELINE.json's
+full sizes — through size-independent properties.  Run with `pytest -m gpu` on the B200 box.
+
+Parity rule: identical status, iterations within +-1, 1e-8 relative on u*/c*, theta*, objective
+(FP64).  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from conftest import assert_parity, sample_ics
+from oracle_py import OracleProblem, plant_rk4
+
+pytestmark = pytest.mark.gpu
+
+X_EQ = np.array([0.5, 1.6875, 1.1547, 0.0])
+U_EQ = 1.1547
+X_INIT = np.array([0.15, 1.2875, 1.1547, 0.0])
+DX0 = np.array([-0.35, -0.4, 0.0, 0.0])
+
+
+def solver(mdl, form, variant, N, **kw):
+    import lbmpc_b200
+    return lbmpc_b200.Solver(mdl, form, variant, N, **kw)
+
+
+@pytest.mark.parametrize("form", ["F", "C"])
+@pytest.mark.parametrize("variant", ["LMPC", "LBMPC"])
+@pytest.mark.parametrize("N", [20, 50])
+def test_parity_four_problem_kinds(models, form, variant, N):
+    mdl = models[variant]
+    X0 = sample_ics(512, seed=N + (7 if form == "F" else 0))
+    sol = solver(mdl, form, variant, N, max_batch=512)
+    got = sol.solve_batch(X0)
+    ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, nthreads=8)
+    assert_parity(got, ref)
+    assert sol.kernel_launches == 1
+
+
+def test_config2_batch1024_both_sets(models):
+    """BASELINE.json configs[1]: 1024 initial conditions, N=50, FP64 — LBMPC (24 polytope rows) and the
+    616-row tracking LMPC set."""
+    X0 = sample_ics(1024, seed=0)
+    for variant in ("LBMPC", "LMPC"):
+        got = solver(models[variant], "C", variant, 50, max_batch=1024).solve_batch(X0)
+        ref = OracleProblem("C", variant, models[variant], 50).solve_batch(X0, nthreads=8)
+        assert_parity(got, ref)
+        assert 0 < (ref["status"] == 2).sum() < 0.1 * 1024      # a few percent infeasible, as surveyed
+
+
+@pytest.mark.parametrize("variant,N", [("LMPC", 20), ("LMPC", 40), ("LMPC", 50), ("LBMPC", 40), ("LBMPC", 50),
+                                       ("LBMPC", 60)])
+def test_golden_fform_first_step(fx, models, variant, N):
+    """Reference known answers straight through the GPU: sysH(5,2), art_refH(2) (fmincon runs), 2e-7 abs."""
+    mdl = models[variant]
+    r = solver(mdl, "F", variant, N, max_batch=1).solve_batch(DX0[None, :])
+    assert r["status"][0] == 0
+    du0 = float((mdl["K"] @ DX0).item() + r["uc"][0, 0, 0])
+    assert abs(du0 - fx[f"{variant}_N{N}__sysH"][4, 1]) < 2e-7
+    assert abs(mdl["LAMBDA"][0, 0] * r["theta"][0, 0] - fx[f"{variant}_N{N}__art_refH"][0, 1]) < 2e-7
+
+
+@pytest.mark.parametrize("variant,N,key,tol", [("LMPC", 50, "casadi_DMS_N50_tLMPC__xl", 1e-7),
+                                               ("LBMPC", 50, "casadi_DMS_N50_tLBMPC_q100__xlo", 1e-7),
+                                               ("LBMPC", 100, "casadi_DMS_tLBMPC_q100__xlo", 2e-6)])
+def test_golden_cform_first_step(fx, models, variant, N, key, tol):
+    r = solver(models[variant], "C", variant, N, max_batch=1).solve_batch((X_INIT - X_EQ)[None, :])
+    assert r["status"][0] == 0
+    x1 = plant_rk4(X_INIT, U_EQ + r["uc"][0, 0, 0])
+    assert np.abs(x1 - fx[key][:, 1]).max() < tol
+
+
+@pytest.mark.parametrize("nb", [1, 7, 9, 1025])
+def test_ragged_batches_and_slot_refill(models, nb):
+    """batch sizes that do not divide the slots per CTA / SM count; slots are refilled from the work queue."""
+    mdl = models["LBMPC"]
+    X0 = sample_ics(nb, seed=nb)
+    got = solver(mdl, "C", "LBMPC", 50, max_batch=nb).solve_batch(X0)
+    ref = OracleProblem("C", "LBMPC", mdl, 50).solve_batch(X0, nthreads=8)
+    assert_parity(got, ref)
+
+
+def test_empty_batch_and_argument_errors(models):
+    import lbmpc_b200
+    sol = solver(models["LBMPC"], "C", "LBMPC", 50, max_batch=4)
+    out = sol.solve_batch(np.zeros((0, 4)))
+    assert out["uc"].shape == (0, 50, 1)
+    with pytest.raises(lbmpc_b200.LbmpcError):
+        sol.solve_batch(np.zeros((5, 4)))                     # exceeds max_batch of a host-pointer handle
+    bad = dict(models["LBMPC"])
+    bad["F_x"] = np.ones((8, 4))                               # not a box
+    with pytest.raises(lbmpc_b200.LbmpcError):
+        solver(bad, "C", "LBMPC", 50)
+    with pytest.raises(lbmpc_b200.LbmpcError):
+        solver(models["LBMPC"], "C", "LBMPC", 2)              # horizon too short
+
+
+@pytest.mark.parametrize("N", [3, 200])
+def test_horizon_extremes(models, N):
+    mdl = models["LBMPC"]
+    X0 = sample_ics(64, seed=N)
+    got = solver(mdl, "C", "LBMPC", N, max_batch=64).solve_batch(X0)
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, nthreads=8)
+    assert_parity(got, ref)
+
+
+def test_reference_offsets_and_warm_start(models):
+    """per-QP tracking reference (costLMPC.m:38), oracle offsets d_k and warm starts (opt_var, ocpLBMPC.m:31)."""
+    mdl = models["LBMPC"]
+    N, nb = 50, 96
+    rng = np.random.default_rng(11)
+    X0 = sample_ics(nb, seed=2)
+    xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.1, 0.1, (nb, 1))
+    doff = 1e-4 * rng.standard_normal((nb, N, 4))
+    warm = np.concatenate([0.05 * rng.standard_normal((nb, N)), 0.01 * rng.standard_normal((nb, 1))], axis=1)
+    got = solver(mdl, "C", "LBMPC", N, max_batch=nb).solve_batch(X0, xref, doff, warm)
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, xref, doff, warm, nthreads=8)
+    assert_parity(got, ref)
+
+
+def test_bitwise_determinism_and_permutation_invariance(models):
+    """Each QP's arithmetic is independent of the slot / CTA it lands in: repeated and permuted batches agree
+    bit for bit."""
+    mdl = models["LMPC"]
+    X0 = sample_ics(300, seed=9)
+    sol = solver(mdl, "C", "LMPC", 50, max_batch=300)
+    a = sol.solve_batch(X0)
+    b = sol.solve_batch(X0)
+    perm = np.random.default_rng(1).permutation(300)
+    c = sol.solve_batch(X0[perm])
+    for k in ("uc", "theta", "obj", "iters", "status", "xtraj"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k][perm], c[k]), k
+
+
+def test_device_pointer_mode(models):
+    """Device-resident I/O (torch tensors are only memory + stream plumbing) gives the same bits as host mode."""
+    import torch
+    mdl = models["LBMPC"]
+    X0 = sample_ics(200, seed=4)
+    host = solver(mdl, "C", "LBMPC", 50, max_batch=200).solve_batch(X0)
+    dsol = solver(mdl, "C", "LBMPC", 50, device_pointers=True)
+    out = dsol.solve_batch(torch.from_numpy(X0).cuda())
+    torch.cuda.synchronize()
+    for k in ("uc", "theta", "obj", "iters", "status", "xtraj"):
+        assert np.array_equal(out[k].cpu().numpy(), host[k]), k
+    assert dsol.last_kernel_ms > 0
+
+
+def test_full_size_properties_config3(models):
+    """BASELINE.json configs[2] at full size (tracking LMPC, 616-row terminal set, batch 16384, N=50) through
+    properties that need no oracle run: every optimal solution is primal feasible to 1e-8, reproduces its own
+    trajectory and objective, the first 512 match the oracle, verdict fractions are as surveyed."""
+    mdl = models["LMPC"]
+    nb, N = 16384, 50
+    X0 = sample_ics(nb, seed=1)
+    rng = np.random.default_rng(1)
+    xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.1, 0.1, (nb, 1)) * (rng.random((nb, 1)) < 0.5)
+    got = solver(mdl, "C", "LMPC", N, max_batch=nb).solve_batch(X0, xref)
+    ok = got["status"] == 0
+    assert set(np.unique(got["status"])) <= {0, 2} and 0.9 < ok.mean() < 1.0
+    u, x, th = got["uc"][ok][:, :, 0], got["xtraj"][ok], got["theta"][ok][:, 0]
+    A, B = mdl["A"], mdl["B"][:, 0]
+    xr = np.empty_like(x)
+    xr[:, 0] = X0[ok]
+    for k in range(N):
+        xr[:, k + 1] = xr[:, k] @ A.T + np.outer(u[:, k], B)
+    assert np.abs(xr - x).max() < 1e-9                          # dynamics hold along the returned trajectory
+    assert (np.abs(u) <= mdl["h_u"][0] + 1e-8).all()
+    assert (x[:, 1:, :] <= mdl["h_x"][:4] + 1e-8).all() and (-x[:, 1:, :] <= mdl["h_x"][4:] + 1e-8).all()
+    z = np.concatenate([x[:, N, :], th[:, None]], axis=1)
+    assert (z @ mdl["F_w_N"].T - mdl["h_w_N"]).max() < 1e-8    # terminal set
+    lam, psi, d = mdl["LAMBDA"][:, 0], mdl["PSI"][0, 0], 0.01
+    ex = x - th[:, None, None] * lam
+    J = d * ((ex[:, :N] ** 2).sum((1, 2)) + ((u - psi * th[:, None]) ** 2).sum(1))
+    J += np.einsum("bi,ij,bj->b", ex[:, N], mdl["P"], ex[:, N])
+    et = th[:, None] * lam - xref[ok]
+    J += mdl["T"] * (et ** 2).sum(1)
+    assert (np.abs(J - got["obj"][ok]) / np.maximum(1.0, np.abs(J))).max() < 1e-9
+    ref = OracleProblem("C", "LMPC", mdl, N).solve_batch(X0[:512], xref[:512], nthreads=8)
+    assert_parity({k: v[:512] for k, v in got.items()}, ref)
+
+
+def test_oracle_apply_matches_l2nw(fx, models):
+    """learnedModel.m:25 + oracleL2NW.m / casadiL2NW.m along the horizon, on windows of train_data.mat."""
+    mdl = models["LBMPC"]
+    data = fx["casadi_train_data__data"]
+    nb, N = 40, 50
+    rng = np.random.default_rng(2)
+    X0 = sample_ics(nb, seed=3)
+    du = 0.05 * rng.standard_normal((nb, N, 1))
+    P = OracleProblem("C", "LBMPC", mdl, N)
+    sol = solver(mdl, "C", "LBMPC", N, max_batch=nb)
+    for q, masked in ((100, False), (37, True), (200, False)):
+        offs = rng.integers(0, 500 - q, nb)
+        Xw = np.stack([data[:3, o:o + q].T for o in offs])          # (nb, q, 3): one column per sample
+        Yw = np.stack([data[3:, o:o + q].T for o in offs])
+        V = (rng.random((nb, q)) < 0.7).astype(float) if masked else None
+        got = sol.oracle_apply(X0, du, Xw, Yw, V)
+        for b in range(nb):
+            ref = P.oracle_offsets(X0[b], du[b, :, 0], Xw[b].T, Yw[b].T, None if V is None else V[b])
+            assert np.abs(got[b] - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()) + 1e-16
+
+
+def test_closed_loop_matches_oracle(models):
+    """ocpLBMPC.m:10-47 / LBMPC_casadi.m:160-223 as a batch: solve, RK4 plant, disturbance, data window,
+    oracle offsets, warm-start shift.  Same counter-based disturbance on both sides."""
+    mdl = models["LBMPC"]
+    nb, steps = 12, 25
+    rng = np.random.default_rng(5)
+    x_init = X_EQ + sample_ics(nb, seed=6) * np.array([0.5, 0.5, 0.2, 0.2])
+    x_init[0] = X_INIT
+    wbar = np.array([0.02, 5e-4, 0.0, 0.0])
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb)
+    P = OracleProblem("C", "LBMPC", mdl, 50)
+    for use_oracle, w in ((False, None), (True, wbar)):
+        got = sol.closed_loop(x_init, steps, X_EQ, U_EQ, q=10, use_oracle=use_oracle, wbar=w, seed=42, scenario0=100)
+        for b in range(nb):
+            ref = P.closed_loop(X_EQ, U_EQ, x_init[b], steps, q=10, use_oracle=use_oracle, wbar=w, seed=42,
+                                scenario=100 + b)
+            assert np.array_equal(got["status"][b], ref["status"])
+            assert np.abs(got["iters"][b] - ref["iters"]).max() <= 1
+            if (ref["status"] == 0).all():
+                assert np.abs(got["x"][b] - ref["x"]).max() < 1e-6
+                assert np.abs(got["u"][b] - ref["u"]).max() < 1e-6
