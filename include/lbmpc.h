@@ -80,7 +80,7 @@ typedef struct lbmpc_config {
     int32_t variant;           /* LBMPC_VARIANT_*                                                 */
     int32_t N;                 /* horizon (LBMPC_RunExample.m:22; N_t/delta in the CasADi files)  */
     double delta;              /* C-form stage weight (DMS_tracking_LMPC_casadi.m:84); ignored in F-form */
-    double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1,|lambda|inf)           */
+    double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1, 100 |lambda|inf)      */
     double tol_mu;             /* 0 -> 1e-10  complementarity gap                                  */
     double inf_radius;         /* 0 -> auto   Farkas test radius R: status 2 when h'lambda < 0 and
                                   |G'lambda|inf R <= -h'lambda (reduced space); auto = 2 x (sum of input

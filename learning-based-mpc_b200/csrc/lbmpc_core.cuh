@@ -833,7 +833,7 @@ struct Core {
     static LB_HD int verdict(const P& p, const double* m, bool pivots_ok, bool cert) {
         const double rd = m[L::M_RD], rp = m[L::M_RP], mu = m[L::M_MU], lam = m[L::M_LAM];
         if (!pivots_ok || !(rd == rd) || !(rp == rp) || !(mu == mu) || isinf(rd) || isinf(mu)) return 3;
-        const double rd_tol = p.tol_res * (lam > 1.0 ? lam : 1.0);
+        const double rd_tol = p.tol_res * (100.0 * lam > 1.0 ? 100.0 * lam : 1.0);
         if (rd < rd_tol && rp < p.tol_res && mu < p.tol_mu) return 0;
         if (cert && m[L::M_HLAM] < 0.0 && m[L::M_CERT] * p.inf_radius <= -m[L::M_HLAM]) return 2;
         return -1;

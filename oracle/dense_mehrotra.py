@@ -122,7 +122,7 @@ def mehrotra_dense(H, g, G, h, y0=None, tol=1e-9, tol_mu=1e-10, max_iter=60, ver
         mu = s @ lam / mrow
         if verbose:
             print(it, np.abs(rd).max(), np.abs(rp).max(), mu)
-        if np.abs(rd).max() < tol * max(1.0, lam.max()) and np.abs(rp).max() < tol and mu < tol_mu:
+        if np.abs(rd).max() < tol * max(1.0, 100.0 * lam.max()) and np.abs(rp).max() < tol and mu < tol_mu:
             info = dict(status=0, iters=it)
             break
         w = lam / s

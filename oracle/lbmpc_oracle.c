@@ -14,7 +14,8 @@
  *              polytope block G [x_kg;theta] <= hg)
  *   start      u_k = Kinit x_k + c_k (c = warm start or 0), theta = 0, s = max(h - a v, 1), lambda = 1
  *   iterate    r_p = a v + s - h, mu = s'lambda/m, r_d = reduced gradient of the Lagrangian
- *              (adjoint recursion); stop when |r_d|_inf < tol_res max(1,|lambda|_inf),
+ *              (adjoint recursion); stop when |r_d|_inf < tol_res max(1, 100 |lambda|_inf) (the
+ *              round-off floor of r_d scales with the multipliers),
  *              |r_p|_inf < tol_res and mu < tol_mu
  *              predictor: Newton step with r_c = s.lambda ; alpha_aff ; sigma = (mu_aff/mu)^3
  *              corrector: r_c = s.lambda + ds_a.dl_a - sigma mu ; alpha = min(1, 0.99 alpha_max)
@@ -776,7 +777,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
             st = LBO_ST_NUMERICAL; break;
         }
         {
-            const double rd_tol = p->tol_res * (lam_inf > 1.0 ? lam_inf : 1.0);
+            const double rd_tol = p->tol_res * (100.0 * lam_inf > 1.0 ? 100.0 * lam_inf : 1.0);
             if (rd_inf < rd_tol && rp_inf < p->tol_res && mu < p->tol_mu) { st = LBO_ST_OPTIMAL; break; }
         }
         if (want_cert && hlam + cert[1] < 0.0 && cert[0] * p->inf_radius <= -(hlam + cert[1])) {
@@ -828,7 +829,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
     for (int j = 0; j < nt; ++j) theta[j] = w->th[j];
     if (xtraj) memcpy(xtraj, w->x, sizeof(double) * (size_t)(N + 1) * nx);
     *obj = J; *iters = it; *status = st;
-    if (stats) { stats[0] = rd_inf; stats[1] = rp_inf; stats[2] = mu; stats[3] = w->flops; }
+    if (stats) { stats[0] = rd_inf; stats[1] = rp_inf; stats[2] = mu; stats[3] = w->flops; stats[4] = lam_inf; stats[5] = hlam; }
     return 0;
 }
 

@@ -83,7 +83,7 @@ int lbo_num_rows(const lbo_problem *p);
  *  uc    N*nu    OUT  c (F-form) or du = u - u_wp (C-form)
  *  theta nt      OUT
  *  xtraj (N+1)*nx OUT predicted delta states (NULL to skip)
- *  obj, iters, status  OUT scalars;  stats[4] OUT {|r_d|inf, |r_p|inf, mu, flops} (NULL ok)
+ *  obj, iters, status  OUT scalars;  stats[6] OUT {|r_d|inf, |r_p|inf, mu, flops, |lambda|inf, lambda'slack} (NULL ok)
  */
 int lbo_solve(const lbo_problem *p, const double *dx0, const double *dx_ref, const double *d_off,
               const double *warm, double *uc, double *theta, double *xtraj, double *obj,

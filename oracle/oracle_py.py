@@ -128,10 +128,10 @@ class OracleProblem:
         it = np.empty(nb, np.int32); st = np.empty(nb, np.int32)
         out = dict(uc=uc, theta=th, xtraj=xt, obj=obj, iters=it, status=st)
         if stats and nb == 1:
-            s = np.zeros(4)
+            s = np.zeros(6)
             L.lbo_solve(self.h, _p(dx0), _p(dx_ref), _p(d_off), _p(warm), _p(uc), _p(th), _p(xt), _p(obj),
                         it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), _p(s))
-            out["stats"] = s.reshape(1, 4)
+            out["stats"] = s.reshape(1, 6)
         else:
             L.lbo_solve_batch(self.h, C.c_long(nb), _p(dx0), _p(dx_ref), _p(d_off), _p(warm), _p(uc), _p(th), _p(xt),
                               _p(obj), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), C.c_int(nthreads))
