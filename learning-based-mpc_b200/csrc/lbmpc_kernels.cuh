@@ -97,19 +97,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------
+constexpr int kThreads = 32 * kMaxSlots;  // always 8 warps: warps without a slot still run the helper sweeps
+
 // shared-memory carve-up helper, identical on host and device
 template <int NX, int NT, int NU>
 struct SmemPlan {
     using L = Layout<NX, NT, NU>;
-    int slots, stride, g_off, hg_off, meta_off;  // offsets in doubles
+    static constexpr int kXchPerSlot = 24;  // Coop::kXch + Coop::kXf doubles per QP
+    int slots, stride, xch_off, g_off, hg_off, meta_off;  // offsets in doubles
     size_t bytes;
     __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
         const L l(N, ngp);
         slots = slots_;
         stride = l.stride;
         int o = slots * stride;
-        o = (o + 1) & ~1;  // 16-byte alignment for the bulk copy destination
-        g_off = o;
+        o = (o + 1) & ~1;  // 16-byte alignment
+        xch_off = o;
+        o += kMaxSlots * kXchPerSlot;
+        g_off = o;         // bulk copy destination (16-byte aligned: kXchPerSlot is even)
         if (stage_g) o += (NX + NT) * ngp;
         hg_off = o;
         if (stage_g) o += ngp;
@@ -119,21 +127,20 @@ struct SmemPlan {
     }
 };
 
-// ---------------------------------------------------------------------------------------------
-// the solver
-// ---------------------------------------------------------------------------------------------
 template <int NX, int NT, int NU>
-__global__ void __launch_bounds__(32 * kMaxSlots, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const double* __restrict__ Gglob,
            const double* __restrict__ hgglob, const int slots, const int stage_g) {
     using C = Core<NX, NT, NU>;
     using L = Layout<NX, NT, NU>;
     constexpr int NZ = NX + NT, NH = L::NH, NACC = NH + 2 * NZ;
+    constexpr bool kCoop = (NT == 1 && NU == 1 && NX <= 4);  // 16-lane Riccati factorisation
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const L l(p.N, p.ngp);
     const SmemPlan<NX, NT, NU> plan(p.N, p.ngp, slots, stage_g != 0);
-    double* const slot = smem + warp * l.stride;
+    const bool has_slot = warp < slots;
+    double* const slot = smem + (has_slot ? warp : 0) * l.stride;
     double* const m = slot + l.o_misc;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + plan.meta_off);
     int* const meta = reinterpret_cast<int*>(smem + plan.meta_off + 2);       // [slot][4]
@@ -155,7 +162,18 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         Gs = smem + plan.g_off;
         hgs = smem + plan.hg_off;
     }
-    if (lane == 0) meta[warp * 4 + 0] = SLOT_EMPTY;
+    if (lane == 0 && warp < kMaxSlots) meta[warp * 4 + 0] = SLOT_EMPTY;
+
+    // ---- cooperative factorisation: per-lane coefficient vectors (registers), exchange buffers ----
+    using CP = Coop<kCoop ? NX : 1>;
+    typename CP::Lane ln;
+    const int half = lane >> 4, hl = lane & 15;
+    const int fslot = warp * 2 + half;  // slot factored by this half-warp (warps 0..3)
+    double* const xch = smem + plan.xch_off + (fslot & (kMaxSlots - 1)) * SmemPlan<NX, NT, NU>::kXchPerSlot;
+    double* const xf = xch + CP::kXch;
+    if constexpr (kCoop) {
+        if (warp < kMaxSlots / 2) CP::lane_init(p, hl, ln);
+    }
     if (stage_g) mbar_wait(bar, 0);
     __syncthreads();
 
@@ -165,32 +183,31 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         // phase C: RUN slots: affine step length, sigma, corrector rhs.  DONE slots: write results.
         //          Empty slots: fetch the next QP and load its inputs.
         // =====================================================================================
-        state = meta[warp * 4 + 0];
+        state = has_slot ? meta[warp * 4 + 0] : SLOT_EMPTY;
         if (state == SLOT_RUN) {
             RedStep rs{0.0, 0.0, 0.0, 0.0};
-            for (int k = lane; k <= N; k += 32) C::template step_stage<0>(p, l, slot, k, 0.0, rs);
-            for (int i = lane; i < p.ng; i += 32) C::template step_gen_row<0>(p, l, slot, Gs, hgs, i, 0.0, rs);
+            for (int k = lane; k <= N; k += 32) C::affine_stage(p, l, slot, k, rs);
+            double acc[2 * NZ];
+#pragma unroll
+            for (int a = 0; a < 2 * NZ; ++a) acc[a] = 0.0;
+            for (int i = lane; i < p.ng; i += 32) C::affine_gen_row(p, l, slot, Gs, hgs, i, acc, rs);
             const double ratio = warp_max(rs.ratio);
             const double s0 = warp_sum(rs.s0), s1 = warp_sum(rs.s1), s2 = warp_sum(rs.s2);
+#pragma unroll
+            for (int a = 0; a < 2 * NZ; ++a) acc[a] = warp_sum(acc[a]);
             const double aaff = ratio > 1.0 ? 1.0 / ratio : 1.0;
             const double mu = m[L::M_MU];
             const double mu_aff = (s0 + aaff * s1 + aaff * aaff * s2) * p.inv_m;
             const double sr = mu_aff / mu;
             const double sigmu = sr * sr * sr * mu;
-            for (int k = lane; k <= N; k += 32) C::corrector_stage(p, l, slot, k, sigmu);
-            double dg[NZ];
-#pragma unroll
-            for (int a = 0; a < NZ; ++a) dg[a] = 0.0;
-            for (int i = lane; i < p.ng; i += 32) C::corrector_gen_row(p, l, slot, Gs, hgs, i, sigmu, dg);
-#pragma unroll
-            for (int a = 0; a < NZ; ++a) dg[a] = warp_sum(dg[a]);
+            for (int k = lane; k <= N; k += 32) C::corr_stage(p, l, slot, k, sigmu);
             __syncwarp();
             if (lane == 0) {
                 m[L::M_SIGMU] = sigmu;
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a];
+                for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = acc[a] + sigmu * acc[NZ + a];
             }
-        } else {
+        } else if (has_slot) {
             if (state == SLOT_DONE) {
                 const long long q = qpid[warp];
                 double J = 0.0;
@@ -277,8 +294,8 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             double* const sl = smem + lane * l.stride;
             const int st = meta[lane * 4 + 0];
             if (st == SLOT_RUN) {
-                C::template backward<false>(p, l, sl, false, false);
-                C::forward(p, l, sl, false);
+                C::backward_vec(p, l, sl, false);
+                C::forward_vec(p, l, sl, false);
             } else if (st == SLOT_FRESH) {
                 C::rollout(p, l, sl);
             }
@@ -291,15 +308,15 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         // =====================================================================================
         if (state == SLOT_RUN) {
             const double sigmu = m[L::M_SIGMU];
-            RedStep rs{0.0, 0.0, 0.0, 0.0};
-            for (int k = lane; k <= N; k += 32) C::template step_stage<1>(p, l, slot, k, sigmu, rs);
-            for (int i = lane; i < p.ng; i += 32) C::template step_gen_row<1>(p, l, slot, Gs, hgs, i, sigmu, rs);
-            const double ratio = warp_max(rs.ratio);
+            double ratio = 0.0;
+            for (int k = lane; k <= N; k += 32) ratio = fmax(ratio, C::final_stage(p, l, slot, k, sigmu));
+            for (int i = lane; i < p.ng; i += 32) ratio = fmax(ratio, C::final_gen_row(p, l, slot, Gs, hgs, i, sigmu));
+            ratio = warp_max(ratio);
             double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
             alpha = alpha > 1.0 ? 1.0 : alpha;
             for (int i = lane; i < p.ng; i += 32) C::update_gen_row(p, l, slot, Gs, hgs, i, sigmu, alpha);
             __syncwarp();
-            for (int k = lane; k <= N; k += 32) C::update_stage(p, l, slot, k, sigmu, alpha);
+            for (int k = lane; k <= N; k += 32) C::update_stage(p, l, slot, k, alpha);
             if (lane == 0) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
@@ -340,7 +357,57 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         __syncthreads();
 
         // =====================================================================================
-        // phase B (sweep): Riccati factorisation + adjoint residual, verdict, affine forward sweep
+        // phase B: Riccati factorisation (warps 0..3, 16 lanes per QP) with, on the otherwise
+        //          idle warps, the adjoint recursion (dual residual) and the Farkas recursion
+        // =====================================================================================
+        if constexpr (kCoop) {
+            if (warp < kMaxSlots / 2) {
+                const bool act = fslot < slots && meta[fslot * 4 + 0] == SLOT_RUN && meta[fslot * 4 + 1] < p.max_iter;
+                if (__any_sync(kFull, act)) {
+                    double* const sl = smem + (fslot < slots ? fslot : 0) * l.stride;
+                    CP::terminal(p, l, sl, ln);
+                    int type = C::stage_type(p, N);
+                    for (int k = N - 1; k >= 0; --k) {
+                        const int t = C::stage_type(p, k);
+                        if (t != type) {
+                            type = t;
+                            CP::load_type(p, t, ln);
+                        }
+                        CP::st1(ln, hl, xch);
+                        __syncwarp();
+                        CP::st2(ln, hl, xch, xf);
+                        __syncwarp();
+                        CP::st3(p, l, sl, k, hl, ln, xf, act);
+                    }
+                    CP::finish(l, sl, hl, ln, act);
+                    const unsigned okb = __ballot_sync(kFull, ln.ok);
+                    const unsigned hm = 0xffffu << (16 * half);
+                    if (act && hl == 0) sl[l.o_misc + L::M_PIV] = ((okb & hm) == hm) ? 1.0 : 0.0;
+                }
+            } else if (warp == kMaxSlots / 2) {
+                if (lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter)
+                    C::adjoint_sweep(p, l, smem + lane * l.stride);
+            } else if (warp == kMaxSlots / 2 + 1) {
+                if (lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
+                    double* const sl = smem + lane * l.stride;
+                    if (sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::farkas_sweep(p, l, sl);
+                }
+            }
+        } else {
+            if (warp == 0 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
+                double* const sl = smem + lane * l.stride;
+                C::factor_serial(p, l, sl);
+            } else if (warp == 1 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
+                C::adjoint_sweep(p, l, smem + lane * l.stride);
+            } else if (warp == 2 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
+                double* const sl = smem + lane * l.stride;
+                if (sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::farkas_sweep(p, l, sl);
+            }
+        }
+        __syncthreads();
+
+        // =====================================================================================
+        // phase B2 (sweep): verdict, then the affine backward/forward substitution
         // =====================================================================================
         if (warp == 0 && lane < slots) {
             double* const sl = smem + lane * l.stride;
@@ -350,15 +417,14 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 if (meta[lane * 4 + 1] >= p.max_iter) {
                     v = 1;  // LBMPC_ST_MAXITER
                 } else {
-                    const bool cert = ms[L::M_LAM] >= p.inf_trigger;
-                    const bool ok = C::template backward<true>(p, l, sl, true, cert);
-                    v = C::verdict(p, ms, ok, cert);
+                    v = C::verdict(p, ms, ms[L::M_LAM] >= p.inf_trigger);
                 }
                 if (v >= 0) {
                     meta[lane * 4 + 2] = v;
                     meta[lane * 4 + 0] = SLOT_DONE;
                 } else {
-                    C::forward(p, l, sl, true);
+                    C::backward_vec(p, l, sl, true);
+                    C::forward_vec(p, l, sl, true);
                 }
             }
         }

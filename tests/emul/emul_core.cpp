@@ -47,6 +47,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     for (int i = 0; i < p.ng; ++i) C::init_rows_gen(p, l, s, G, hg, i);
     int it = 0, st = 1;
     for (it = 0; it < p.max_iter; ++it) {
+        // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
         RedAsm ra{0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) C::assemble_stage(p, l, s, k, ra);
         double acc[NH + 2 * NZ];
@@ -55,33 +56,59 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
         for (int a = 0; a < NZ; ++a) { m[L::M_GGL + a] = acc[NH + a]; m[L::M_DG + a] = acc[NH + NZ + a]; }
         m[L::M_RP] = ra.rp; m[L::M_MU] = ra.sl * p.inv_m; m[L::M_LAM] = ra.lam; m[L::M_HLAM] = ra.hl;
+        // ---- phase B: factorisation + adjoint (+ Farkas) recursions ----
         const bool cert = ra.lam >= p.inf_trigger;
-        const bool ok = C::template backward<true>(p, l, s, true, cert);
-        const int v = C::verdict(p, m, ok, cert);
+        if constexpr (NT == 1 && NU == 1 && NX <= 4) {
+            // 16-lane cooperative factorisation, lane-phases run as loops (kernel: __syncwarp between them)
+            using CP = Coop<NX>;
+            typename CP::Lane ln[16];
+            double xch[CP::kXch] = {0}, xf[CP::kXf] = {0};
+            for (int h = 0; h < 16; ++h) { CP::lane_init(p, h, ln[h]); CP::terminal(p, l, s, ln[h]); }
+            int type = C::stage_type(p, N);
+            for (int k = N - 1; k >= 0; --k) {
+                const int t = C::stage_type(p, k);
+                if (t != type) { type = t; for (int h = 0; h < 16; ++h) CP::load_type(p, t, ln[h]); }
+                for (int h = 0; h < 16; ++h) CP::st1(ln[h], h, xch);
+                for (int h = 0; h < 16; ++h) CP::st2(ln[h], h, xch, xf);
+                for (int h = 0; h < 16; ++h) CP::st3(p, l, s, k, h, ln[h], xf, true);
+            }
+            bool ok = true;
+            for (int h = 0; h < 16; ++h) { CP::finish(l, s, h, ln[h], true); ok = ok && ln[h].ok; }
+            m[L::M_PIV] = ok ? 1.0 : 0.0;
+        } else {
+            C::factor_serial(p, l, s);
+        }
+        C::adjoint_sweep(p, l, s);
+        if (cert) C::farkas_sweep(p, l, s);
+        // ---- phase B2: verdict, affine substitution sweeps ----
+        const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
-        C::forward(p, l, s, true);
+        C::backward_vec(p, l, s, true);
+        C::forward_vec(p, l, s, true);
+        // ---- phase C: affine step length, sigma, corrector rhs ----
         RedStep rs{0, 0, 0, 0};
-        for (int k = 0; k <= N; ++k) C::template step_stage<0>(p, l, s, k, 0.0, rs);
-        for (int i = 0; i < p.ng; ++i) C::template step_gen_row<0>(p, l, s, G, hg, i, 0.0, rs);
+        for (int k = 0; k <= N; ++k) C::affine_stage(p, l, s, k, rs);
+        double dg[2 * NZ];
+        std::memset(dg, 0, sizeof dg);
+        for (int i = 0; i < p.ng; ++i) C::affine_gen_row(p, l, s, G, hg, i, dg, rs);
         const double aaff = rs.ratio > 1.0 ? 1.0 / rs.ratio : 1.0;
         const double mu_aff = (rs.s0 + aaff * rs.s1 + aaff * aaff * rs.s2) * p.inv_m;
         const double sr = mu_aff / m[L::M_MU];
         const double sigmu = sr * sr * sr * m[L::M_MU];
         m[L::M_SIGMU] = sigmu;
-        for (int k = 0; k <= N; ++k) C::corrector_stage(p, l, s, k, sigmu);
-        double dg[NZ];
-        std::memset(dg, 0, sizeof dg);
-        for (int i = 0; i < p.ng; ++i) C::corrector_gen_row(p, l, s, G, hg, i, sigmu, dg);
-        for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a];
-        C::template backward<false>(p, l, s, false, false);
-        C::forward(p, l, s, false);
-        RedStep r2{0, 0, 0, 0};
-        for (int k = 0; k <= N; ++k) C::template step_stage<1>(p, l, s, k, sigmu, r2);
-        for (int i = 0; i < p.ng; ++i) C::template step_gen_row<1>(p, l, s, G, hg, i, sigmu, r2);
-        double alpha = r2.ratio > 0.0 ? 0.99 / r2.ratio : 1.0;
+        for (int k = 0; k <= N; ++k) C::corr_stage(p, l, s, k, sigmu);
+        for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a] + sigmu * dg[NZ + a];
+        // ---- phase D: corrector substitution sweeps ----
+        C::backward_vec(p, l, s, false);
+        C::forward_vec(p, l, s, false);
+        // ---- phase E: step length, update ----
+        double ratio = 0.0;
+        for (int k = 0; k <= N; ++k) ratio = lb_max(ratio, C::final_stage(p, l, s, k, sigmu));
+        for (int i = 0; i < p.ng; ++i) ratio = lb_max(ratio, C::final_gen_row(p, l, s, G, hg, i, sigmu));
+        double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
         if (alpha > 1.0) alpha = 1.0;
         for (int i = 0; i < p.ng; ++i) C::update_gen_row(p, l, s, G, hg, i, sigmu, alpha);
-        for (int k = 0; k <= N; ++k) C::update_stage(p, l, s, k, sigmu, alpha);
+        for (int k = 0; k <= N; ++k) C::update_stage(p, l, s, k, alpha);
         for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
     }
     double J = m[L::M_CCONST];
