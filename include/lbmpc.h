@@ -141,6 +141,11 @@ int64_t lbmpc_kernel_launches(const lbmpc_handle *h); /* kernels launched by thi
 /* last solve call: device time of the IPM kernel in ms (CUDA events on the launch stream) */
 float lbmpc_last_kernel_ms(lbmpc_handle *h);
 
+/* diagnostic: SM-cycle counters of CTA 0 per kernel phase, accumulated over the solve calls made while enabled:
+ * out8 = {C: affine step/sigma/refill, D: corrector sweeps, E+A: update+assembly, B: factorisation,
+ * B2: verdict+affine sweeps, lock-step iterations, 0, 0}.  Reads and clears the counters, then sets `enable`. */
+int lbmpc_debug_phase_cycles(lbmpc_handle *h, int enable, uint64_t *out8);
+
 /* roofline denominator: measured FP64-FMA throughput of the device in TFLOP/s (register-resident DFMA
  * chains, best of 5 after one warm-up; MEASURED_PEAKS.json carries no FP64 entry) */
 int lbmpc_measure_fp64_peak(int device, double *tflops);

@@ -49,6 +49,8 @@ struct lbmpc_handle {
     int64_t max_batch = 0;
     double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
     unsigned long long* dqueue = nullptr;
+    unsigned long long* dprof = nullptr;  // 8 counters, enabled by lbmpc_debug_phase_cycles
+    bool prof_on = false;
     // host-pointer staging
     double *s_dx0 = nullptr, *s_ref = nullptr, *s_doff = nullptr, *s_warm = nullptr, *s_uc = nullptr,
            *s_theta = nullptr, *s_x = nullptr, *s_obj = nullptr;
@@ -172,6 +174,8 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(dmalloc(&h->dA, (size_t)hp.nx * hp.nx));
     CU_TRY(dmalloc(&h->dB, (size_t)hp.nx * hp.nu));
     CU_TRY(dmalloc(&h->dqueue, 1));
+    CU_TRY(dmalloc(&h->dprof, 8));
+    CU_TRY(cudaMemset(h->dprof, 0, 8 * sizeof(unsigned long long)));
     CU_TRY(cudaMemcpy(h->dG, hp.G.data(), sizeof(double) * nz * hp.ngp, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->dhg, hp.hg.data(), sizeof(double) * hp.ngp, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->dA, hp.A.data(), sizeof(double) * hp.nx * hp.nx, cudaMemcpyHostToDevice));
@@ -209,6 +213,7 @@ int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const d
     BatchIO io{};
     io.batch = batch;
     io.queue = h->dqueue;
+    io.prof = h->prof_on ? h->dprof : nullptr;
     if (h->dev_ptrs) {
         io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm;
         io.uc = u_or_c; io.theta = theta; io.xtraj = x_traj; io.obj = obj; io.iters = iters; io.status = status;
@@ -347,7 +352,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
             CU_TRY(cudaGetLastError());
         }
         BatchIO io{};
-        io.batch = batch; io.queue = h->dqueue;
+        io.batch = batch; io.queue = h->dqueue; io.prof = nullptr;
         io.dx0 = L.dx0; io.dx_ref = nullptr; io.d_off = (use_oracle && have) ? L.doff : nullptr;
         io.warm = (warm_shift && have) ? L.warm : nullptr;
         io.uc = L.uc; io.theta = L.theta; io.xtraj = nullptr; io.obj = L.obj; io.iters = L.iters; io.status = L.status;
@@ -371,6 +376,16 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
 int lbmpc_num_rows(const lbmpc_handle* h) { return h ? h->hp.m_rows : 0; }
 int lbmpc_slots_per_cta(const lbmpc_handle* h) { return h ? h->max_slots : 0; }
 int64_t lbmpc_kernel_launches(const lbmpc_handle* h) { return h ? h->launches : 0; }
+
+int lbmpc_debug_phase_cycles(lbmpc_handle* h, int enable, uint64_t* out8) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (out8) CU_TRY(cudaMemcpy(out8, h->dprof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemset(h->dprof, 0, 8 * sizeof(unsigned long long)));
+    h->prof_on = enable != 0;
+    return LBMPC_OK;
+}
 
 float lbmpc_last_kernel_ms(lbmpc_handle* h) {
     if (!h || !h->timed) return -1.0f;
@@ -416,7 +431,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     free_loop(h->loop);
-    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue);
+    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_theta); cudaFree(h->s_x); cudaFree(h->s_obj); cudaFree(h->s_it); cudaFree(h->s_st);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -37,6 +37,7 @@ struct BatchIO {
     double *uc, *theta, *xtraj, *obj;
     int *iters, *status;
     unsigned long long* queue;  // global work counter (zeroed before launch)
+    unsigned long long* prof;   // optional (may be null): per-phase SM cycles of CTA 0, see lbmpc_debug_phase_cycles
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -177,6 +178,16 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
     if (stage_g) mbar_wait(bar, 0);
     __syncthreads();
 
+    // optional phase timing (diagnostic): thread 0 of CTA 0 accumulates clock64 deltas per phase
+    const bool prof_on = io.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_prev = prof_on ? clock64() : 0;
+#define LB_PROF(idx)                                           \
+    if (prof_on) {                                             \
+        const long long t_now = clock64();                     \
+        io.prof[idx] += (unsigned long long)(t_now - t_prev);  \
+        t_prev = t_now;                                        \
+    }
+
     int state = SLOT_EMPTY;  // warp-uniform copy of meta[warp].state
     for (;;) {
         // =====================================================================================
@@ -285,6 +296,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             if (lane == 0) meta[warp * 4 + 0] = state;
         }
         const int nactive = __syncthreads_count(lane == 0 && state != SLOT_EMPTY);
+        LB_PROF(0)
         if (nactive == 0) break;
 
         // =====================================================================================
@@ -301,6 +313,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
         }
         __syncthreads();
+        LB_PROF(1)
 
         // =====================================================================================
         // phase E+A: step length + update (RUN) or row initialisation (FRESH); then the
@@ -355,6 +368,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
         }
         __syncthreads();
+        LB_PROF(2)
 
         // =====================================================================================
         // phase B: Riccati factorisation (warps 0..3, 16 lanes per QP) with, on the otherwise
@@ -405,6 +419,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
         }
         __syncthreads();
+        LB_PROF(3)
 
         // =====================================================================================
         // phase B2 (sweep): verdict, then the affine backward/forward substitution
@@ -429,7 +444,10 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
         }
         __syncthreads();
+        LB_PROF(4)
+        if (prof_on) io.prof[5] += 1;
     }
+#undef LB_PROF
 }
 
 // ---------------------------------------------------------------------------------------------

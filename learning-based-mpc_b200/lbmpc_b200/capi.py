@@ -112,6 +112,8 @@ def load_library(path=None):
     lib.lbmpc_kernel_launches.restype = C.c_int64
     lib.lbmpc_last_kernel_ms.argtypes = [vp]
     lib.lbmpc_last_kernel_ms.restype = C.c_float
+    lib.lbmpc_debug_phase_cycles.argtypes = [vp, C.c_int, vp]
+    lib.lbmpc_debug_phase_cycles.restype = C.c_int
     lib.lbmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.lbmpc_measure_fp64_peak.restype = C.c_int
     lib.lbmpc_destroy.argtypes = [vp]
@@ -187,6 +189,14 @@ class Solver:
     @property
     def last_kernel_ms(self):
         return float(self.lib.lbmpc_last_kernel_ms(self.h))
+
+    def phase_cycles(self, enable=True):
+        """Read and clear the per-phase SM-cycle counters of CTA 0 (lbmpc_debug_phase_cycles), then switch the
+        instrumentation on/off for the following solve calls."""
+        out = np.zeros(8, np.uint64)
+        self._check(self.lib.lbmpc_debug_phase_cycles(self.h, int(enable), _ptr(out)), "lbmpc_debug_phase_cycles")
+        names = ("C_affine_step", "D_corrector_sweeps", "EA_update_assemble", "B_factor", "B2_affine_sweeps", "iterations")
+        return dict(zip(names, (int(v) for v in out[:6])))
 
     def _check(self, rc, what):
         if rc != 0:

@@ -12,4 +12,10 @@ dx0 = lo + (hi - lo) * rng.random((nb, 4)); dx0[0] = [-0.35, -0.4, 0, 0]
 sol = lbmpc_b200.Solver(lbmpc_b200.moore_greitzer_model(variant), form, variant, N, max_batch=nb)
 for _ in range(reps):
     out = sol.solve_batch(dx0)
+if os.environ.get("LBMPC_PHASES"):
+    sol.phase_cycles(True)
+    out = sol.solve_batch(dx0)
+    ph = sol.phase_cycles(False)
+    it = max(ph.pop("iterations"), 1)
+    print("phase cycles per lock-step iteration of CTA 0 (", it, "iterations ):", {k: v // it for k, v in ph.items()})
 print(form, variant, N, nb, "kernel_ms", sol.last_kernel_ms, "iters_mean", out["iters"].mean(), "status", np.bincount(out["status"]))
