@@ -53,8 +53,14 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------------
-// slot layout (offsets in doubles).  Arrays are [component][stage] so that lanes striding over
-// stages hit consecutive banks; the slot stride is odd so that lanes striding over slots do too.
+// slot layout (offsets in doubles).  Three arrays of per-stage RECORDS ([stage][field]) so that
+//  - a lane that walks the horizon sequentially (the sweeps) addresses every operand of a stage as
+//    base + compile-time offset (one pointer bump per stage, no index arithmetic), and
+//  - lanes that stride over stages (the row phases) hit different banks: record sizes are odd.
+// The slot stride is odd too, so lanes striding over slots are conflict-free as well.
+//   R1 (iterate)    x[NX] u[NU] s[2 NVB] lambda[2 NVB]
+//   R2 (Newton)     qd[NVB] q[NVB] g[NV] RL[NU NZ] Ri[NU NU] kap[NU]
+//   R3 (directions) dx[NX] du[NU] dxa[NX] dua[NU]
 // ------------------------------------------------------------------------------------------------
 template <int NX, int NT, int NU>
 struct Layout {
@@ -67,35 +73,46 @@ struct Layout {
                          M_RD = M_HLAM + 1, M_ALPHA = M_RD + 1, M_SIGMU = M_ALPHA + 1,
                          M_CCONST = M_SIGMU + 1, M_CERT = M_CCONST + 1, M_OBJ = M_CERT + 1,
                          M_PIV = M_OBJ + 1, M_SIZE = M_PIV + 1;
+    // field offsets inside the records
+    static constexpr int F_X = 0, F_U = NX, F_S = NVB, F_LB = 3 * NVB, RS1 = (5 * NVB) | 1;
+    static constexpr int F_QD = 0, F_Q = NVB, F_G = 2 * NVB, F_RL = F_G + NV, F_RI = F_RL + NU * NZ,
+                         F_KAP = F_RI + NU * NU, RS2 = (F_KAP + NU) | 1;
+    static constexpr int F_DX = 0, F_DU = NX, F_DXA = NVB, F_DUA = NVB + NX, RS3 = (2 * NVB) | 1;
+    static_assert(NV <= RS3, "Farkas scratch does not fit record R3");
     // [qd | q | g | RL] are dead once the corrector sweeps are done: the final step-length pass
     // parks the row directions ds, dl (2 x 2 NVB per stage) there
-    static_assert(NV + NU * NZ >= 2 * NVB, "scratch for the row directions does not fit");
+    static_assert(F_RI >= 4 * NVB, "scratch for the row directions does not fit");
     int Np, ngp;
-    int o_x, o_u, o_sb, o_lb, o_qd, o_q, o_g, o_L, o_Ri, o_kap, o_dx, o_du, o_dxa, o_dua, o_sg,
-        o_lg, o_misc, stride;
+    int o_r1, o_r2, o_r3, o_sg, o_lg, o_misc, stride;
     LB_HD Layout(int N, int ngp_) {
-        Np = (N + 1) | 1;  // odd: lanes striding over components hit different banks too
+        Np = N + 1;
         ngp = ngp_;
         int o = 0;
-        o_x = o;   o += NX * Np;
-        o_u = o;   o += NU * Np;
-        o_sb = o;  o += NVB * 2 * Np;
-        o_lb = o;  o += NVB * 2 * Np;
-        o_qd = o;  o += NVB * Np;      // barrier diagonal
-        o_q = o;   o += NVB * Np;      // Newton rhs on the bounded variables (cost gradient + barrier terms)
-        o_g = o;   o += NV * Np;       // cost gradient + G'lambda (dual residual recursion)
-        o_L = o;   o += NU * NZ * Np;  // RL_k = Ri_k L_k
-        o_Ri = o;  o += NU * NU * Np;
-        o_kap = o; o += NU * Np;
-        o_dx = o;  o += NX * Np;       // (o_dx, o_du) contiguous: scratch of the corrector assembly
-        o_du = o;  o += NU * Np;
-        o_dxa = o; o += NX * Np;
-        o_dua = o; o += NU * Np;
+        o_r1 = o;  o += RS1 * Np;
+        o_r2 = o;  o += RS2 * Np;
+        o_r3 = o;  o += RS3 * Np;
         o_sg = o;  o += ngp;
         o_lg = o;  o += ngp;
         o_misc = o; o += M_SIZE;
         stride = o | 1;  // odd
     }
+    LB_HD int r1(int k) const { return o_r1 + k * RS1; }
+    LB_HD int r2(int k) const { return o_r2 + k * RS2; }
+    LB_HD int r3(int k) const { return o_r3 + k * RS3; }
+    LB_HD int i_x(int j, int k) const { return r1(k) + F_X + j; }
+    LB_HD int i_u(int i, int k) const { return r1(k) + F_U + i; }
+    LB_HD int i_v(int j, int k) const { return r1(k) + j; }            // bounded variable j of [x;u]
+    LB_HD int i_sb(int r, int k) const { return r1(k) + F_S + r; }     // r = 2*j+side
+    LB_HD int i_lb(int r, int k) const { return r1(k) + F_LB + r; }
+    LB_HD int i_qd(int j, int k) const { return r2(k) + F_QD + j; }
+    LB_HD int i_q(int j, int k) const { return r2(k) + F_Q + j; }
+    LB_HD int i_g(int a, int k) const { return r2(k) + F_G + a; }
+    LB_HD int i_L(int j, int k) const { return r2(k) + F_RL + j; }     // RL[i*NZ+b]
+    LB_HD int i_Ri(int j, int k) const { return r2(k) + F_RI + j; }
+    LB_HD int i_kap(int i, int k) const { return r2(k) + F_KAP + i; }
+    LB_HD int i_scr_ds(int r, int k) const { return r2(k) + r; }
+    LB_HD int i_scr_dl(int r, int k) const { return r2(k) + 2 * NVB + r; }
+    LB_HD int i_dv(int j, int k, bool aff) const { return r3(k) + (aff ? NVB : 0) + j; }  // [dx;du] / [dxa;dua]
 };
 
 struct RedAsm {  // reductions of the assembly pass
@@ -147,11 +164,6 @@ struct Core {
         return a * NZ - a * (a - 1) / 2 + (b - a);
     }
     static LB_HD int zidx(int j) { return j < NX ? j : NZ + (j - NX); }  // bounded var -> index in v=[x;theta;u]
-    // value of bounded variable j (x then u) at stage k from arrays ax (NX x Np), au (NU x Np)
-    static LB_HD double bvar(const L& l, const double* s, int ox, int ou, int k, int j) {
-        return j < NX ? s[ox + j * l.Np + k] : s[ou + (j - NX) * l.Np + k];
-    }
-
     // ============================================================================================
     // sweep: initial rollout, in place.  On entry u(:,k) holds the warm-start c_k (or 0) and
     // x(:,k+1) holds the dynamics offset d_k (or 0); x(:,0) = dx0.
@@ -160,25 +172,25 @@ struct Core {
     static LB_HD void rollout(const P& p, const L& l, double* s) {
         double x[NX], u[NU], xn[NX];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) x[j] = s[l.o_x + j * l.Np];
+        for (int j = 0; j < NX; ++j) x[j] = s[l.i_x(j, 0)];
         for (int k = 0; k < p.N; ++k) {
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-                double v = s[l.o_u + i * l.Np + k];
+                double v = s[l.i_u(i, k)];
 #pragma unroll
                 for (int j = 0; j < NX; ++j) v += p.Kinit[i * NX + j] * x[j];
                 u[i] = v;
-                s[l.o_u + i * l.Np + k] = v;
+                s[l.i_u(i, k)] = v;
             }
 #pragma unroll
             for (int a = 0; a < NX; ++a) {
-                double v = s[l.o_x + a * l.Np + k + 1];
+                double v = s[l.i_x(a, k + 1)];
 #pragma unroll
                 for (int j = 0; j < NX; ++j) v += p.A[a * NX + j] * x[j];
 #pragma unroll
                 for (int i = 0; i < NU; ++i) v += p.B[a * NU + i] * u[i];
                 xn[a] = v;
-                s[l.o_x + a * l.Np + k + 1] = v;
+                s[l.i_x(a, k + 1)] = v;
             }
 #pragma unroll
             for (int j = 0; j < NX; ++j) x[j] = xn[j];
@@ -193,14 +205,14 @@ struct Core {
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
             if (!((rows >> (2 * j)) & 3u)) continue;
-            const double v = bvar(l, s, l.o_x, l.o_u, k, j);
+            const double v = s[l.i_v(j, k)];
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!((rows >> (2 * j + side)) & 1u)) continue;
                 const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
-                const int r = (2 * j + side) * l.Np + k;
-                s[l.o_sb + r] = slack > 1.0 ? slack : 1.0;
-                s[l.o_lb + r] = 1.0;
+                const int r = 2 * j + side;
+                s[l.i_sb(r, k)] = slack > 1.0 ? slack : 1.0;
+                s[l.i_lb(r, k)] = 1.0;
             }
         }
     }
@@ -208,7 +220,7 @@ struct Core {
                                   const double* hg, int i) {
         double v = hg[i];
 #pragma unroll
-        for (int a = 0; a < NX; ++a) v -= G[a * p.ngp + i] * s[l.o_x + a * l.Np + p.kg];
+        for (int a = 0; a < NX; ++a) v -= G[a * p.ngp + i] * s[l.i_x(a, p.kg)];
 #pragma unroll
         for (int a = 0; a < NT; ++a) v -= G[(NX + a) * p.ngp + i] * s[l.o_misc + L::M_TH + a];
         return v;
@@ -227,12 +239,12 @@ struct Core {
     static LB_HD void assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red) {
         double v[NV], g[NV];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v[j] = s[l.o_x + j * l.Np + k];
+        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)];
 #pragma unroll
         for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
         const bool last = k >= p.N;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.o_u + j * l.Np + k];
+        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.i_u(j, k)];
         const double* W = p.W[stage_type(p, k)];
 #pragma unroll
         for (int a = 0; a < NV; ++a) {
@@ -253,8 +265,8 @@ struct Core {
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = (2 * j + side) * l.Np + k;
-                const double S = s[l.o_sb + r], Lm = s[l.o_lb + r];
+                const int r = 2 * j + side;
+                const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
                 const double sgn = side == 0 ? 1.0 : -1.0;
                 const double slack = side == 0 ? p.hi[j] - v[a] : v[a] - p.lo[j];
                 const double rp = S - slack;
@@ -267,12 +279,15 @@ struct Core {
                 red.lam = lb_max(red.lam, Lm);
                 red.hl += Lm * slack;
             }
-            s[l.o_qd + j * l.Np + k] = qd;
-            s[l.o_q + j * l.Np + k] = g[a] + gp;
+            s[l.i_qd(j, k)] = qd;
+            s[l.i_q(j, k)] = g[a] + gp;
             g[a] += gl;
+            s[l.r3(k) + a] = gl;  // Farkas input (adjoint_sweep), g-layout
         }
 #pragma unroll
-        for (int a = 0; a < NV; ++a) s[l.o_g + a * l.Np + k] = g[a];
+        for (int t = 0; t < NT; ++t) s[l.r3(k) + NX + t] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NV; ++a) s[l.i_g(a, k)] = g[a];
     }
 
     // row: predictor assembly of polytope row i.  acc = {HG (NH packed), gGl (NZ), dG (NZ)}
@@ -320,7 +335,7 @@ struct Core {
 #pragma unroll
                 for (int b = 0; b < NX; ++b)
                     Pxx[a][b] = W[a * NV + b] + (kg ? m[L::M_HG + (a <= b ? sym(a, b) : sym(b, a))] : 0.0);
-                Pxx[a][a] += s[l.o_qd + a * l.Np + N];
+                Pxx[a][a] += s[l.i_qd(a, N)];
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
                     Pxt[a][t] = W[a * NV + NX + t] + (kg ? m[L::M_HG + sym(a, NX + t)] : 0.0);
@@ -384,7 +399,7 @@ struct Core {
                     Rt[i][j] = v;
                 }
 #pragma unroll
-            for (int i = 0; i < NU; ++i) Rt[i][i] += s[l.o_qd + (NX + i) * l.Np + k];
+            for (int i = 0; i < NU; ++i) Rt[i][i] += s[l.i_qd(NX + i, k)];
             if (NU == 1) {
                 ok = ok && (Rt[0][0] > 0.0);
                 Ri[0][0] = 1.0 / Rt[0][0];
@@ -421,7 +436,7 @@ struct Core {
                     for (int i = 0; i < NU; ++i) v -= Lk[i][a] * RL[i][b];
                     Nxx[a][b] = v;
                 }
-                Nxx[a][a] += s[l.o_qd + a * l.Np + k];
+                Nxx[a][a] += s[l.i_qd(a, k)];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     double v = W[a * NV + NX + t] + (kg ? m[L::M_HG + sym(a, NX + t)] : 0.0);
@@ -456,9 +471,9 @@ struct Core {
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
 #pragma unroll
-                for (int b = 0; b < NZ; ++b) s[l.o_L + (i * NZ + b) * l.Np + k] = RL[i][b];
+                for (int b = 0; b < NZ; ++b) s[l.i_L(i * NZ + b, k)] = RL[i][b];
 #pragma unroll
-                for (int j = 0; j < NU; ++j) s[l.o_Ri + (i * NU + j) * l.Np + k] = Ri[i][j];
+                for (int j = 0; j < NU; ++j) s[l.i_Ri(i * NU + j, k)] = Ri[i][j];
             }
         }
         // theta block of P_0 -> inverse (NT = 1 or 2)
@@ -479,163 +494,201 @@ struct Core {
     }
 
     // ============================================================================================
-    // sweep: adjoint recursion -> |r_d|inf, the reduced gradient of the Lagrangian w.r.t. (u, theta)
+    // The four thread-local recursions below are latency-critical (one lane per QP, in-order issue,
+    // FP64 issue-bound).  Each walks the per-stage records with ONE pointer, fetches every stage's
+    // operands one stage ahead (two register sets, loop unrolled by two: no copies) so the 29-cycle
+    // LDS latency never sits on the recursion's dependency chain, and keeps A, B in registers.
     // ============================================================================================
-    static LB_HD void adjoint_sweep(const P& p, const L& l, double* s) {
+    struct AB {
+        double A[NX * NX], B[NX * NU];
+    };
+    static LB_HD void load_ab(const P& p, AB& c) {
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) c.A[i] = p.A[i];
+#pragma unroll
+        for (int i = 0; i < NX * NU; ++i) c.B[i] = p.B[i];
+    }
+
+    // ---- adjoint recursions.  One instruction stream serves two uses, selected per lane:
+    //   farkas = false: input g (cost gradient + G'lambda, record R2) -> |r_d|inf at M_RD, the reduced
+    //                   gradient of the Lagrangian w.r.t. (u, theta);
+    //   farkas = true : input G'lambda only (parked by assemble_stage in the first NV fields of record
+    //                   R3, free until the affine forward sweep) -> |G_red'lambda|inf at M_CERT and
+    //                   h_red'lambda = lambda'slack + y'(G'lambda)_red accumulated into M_HLAM. ----
+    struct AdjOps {
+        double g[NV], u[NU];
+    };
+    static LB_HD void adj_load(const double* src, const double* r1, AdjOps& o) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) o.g[a] = src[a];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) o.u[i] = r1[L::F_U + i];
+    }
+    static LB_HD void adj_step(const AB& c, const AdjOps& o, double* pi, double& nrm, double& ydot) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            double v = o.g[NZ + i];
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) v += c.B[cc * NU + i] * pi[cc];
+            nrm = lb_nanmax(nrm, lb_abs(v));
+            ydot += v * o.u[i];
+        }
+        double np_[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            double v = o.g[a];
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) v += c.A[cc * NX + a] * pi[cc];
+            np_[a] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < NX; ++a) pi[a] = np_[a];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) pi[NX + t] += o.g[NX + t];
+    }
+    static LB_HD void adjoint_sweep(const P& p, const L& l, double* s, bool farkas) {
         double pi[NZ];
         double* m = s + l.o_misc;
         const int N = p.N;
-        double rdi = 0.0;
+        AB c;
+        load_ab(p, c);
+        double nrm = 0.0, ydot = 0.0;
+        const int step = farkas ? L::RS3 : L::RS2;
+        const double* src = s + (farkas ? l.r3(N) : l.r2(N) + L::F_G);
+        const double* r1 = s + l.r1(N - 1);
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) pi[a] = s[l.o_g + a * l.Np + N] + (p.kg == N ? m[L::M_GGL + a] : 0.0);
-        for (int k = N - 1; k >= 0; --k) {
-            const bool kg = (p.kg == k);
+        for (int a = 0; a < NZ; ++a) pi[a] = src[a] + (p.kg == N ? m[L::M_GGL + a] : 0.0);
+        src -= step;
+        AdjOps o0, o1;
+        adj_load(src, r1, o0);
+        int k = N - 1;
+        for (; k >= 1; k -= 2) {
+            adj_load(src - step, r1 - L::RS1, o1);
+            adj_step(c, o0, pi, nrm, ydot);
+            if (p.kg == k) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                double v = s[l.o_g + (NZ + i) * l.Np + k];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) v += p.B[c * NU + i] * pi[c];
-                rdi = lb_nanmax(rdi, lb_abs(v));
+                for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
             }
-            double np_[NX];
+            src -= 2 * step;
+            r1 -= 2 * L::RS1;
+            adj_load(k >= 2 ? src : src + step, k >= 2 ? r1 : r1 + L::RS1, o0);
+            adj_step(c, o1, pi, nrm, ydot);
+            if (p.kg == k - 1) {
 #pragma unroll
-            for (int a = 0; a < NX; ++a) {
-                double v = s[l.o_g + a * l.Np + k];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) v += p.A[c * NX + a] * pi[c];
-                np_[a] = v;
+                for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
             }
-#pragma unroll
-            for (int a = 0; a < NX; ++a) pi[a] = np_[a] + (kg ? m[L::M_GGL + a] : 0.0);
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-                pi[NX + t] += s[l.o_g + (NX + t) * l.Np + k] + (kg ? m[L::M_GGL + NX + t] : 0.0);
         }
+        if (k == 0) {
+            adj_step(c, o0, pi, nrm, ydot);
+            if (p.kg == 0) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) rdi = lb_nanmax(rdi, lb_abs(pi[NX + t]));
-        m[L::M_RD] = rdi;
-    }
-
-    // ============================================================================================
-    // sweep: Farkas adjoint (same recursion with G'lambda only) -> |G_red'lambda|inf at M_CERT and
-    // h_red'lambda = lambda'slack + y'(G'lambda)_red accumulated into M_HLAM
-    // ============================================================================================
-    static LB_HD void farkas_sweep(const P& p, const L& l, double* s) {
-        double pc[NZ];
-        double* m = s + l.o_misc;
-        const int N = p.N;
-        double ci = 0.0, ydot = 0.0;
-        {
-            const unsigned rows = stage_rows(p, N);
-#pragma unroll
-            for (int a = 0; a < NZ; ++a) pc[a] = (p.kg == N) ? m[L::M_GGL + a] : 0.0;
-#pragma unroll
-            for (int j = 0; j < NX; ++j)
-#pragma unroll
-                for (int side = 0; side < 2; ++side)
-                    if ((rows >> (2 * j + side)) & 1u)
-                        pc[j] += (side == 0 ? 1.0 : -1.0) * s[l.o_lb + (2 * j + side) * l.Np + N];
-        }
-        for (int k = N - 1; k >= 0; --k) {
-            const bool kg = (p.kg == k);
-            const unsigned rows = stage_rows(p, k);
-            double gc[NVB];
-#pragma unroll
-            for (int j = 0; j < NVB; ++j) {
-                double v = 0.0;
-#pragma unroll
-                for (int side = 0; side < 2; ++side)
-                    if ((rows >> (2 * j + side)) & 1u)
-                        v += (side == 0 ? 1.0 : -1.0) * s[l.o_lb + (2 * j + side) * l.Np + k];
-                gc[j] = v;
+                for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
             }
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                double v = gc[NX + i];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) v += p.B[c * NU + i] * pc[c];
-                ci = lb_max(ci, lb_abs(v));
-                ydot += v * s[l.o_u + i * l.Np + k];
-            }
-            double np_[NX];
-#pragma unroll
-            for (int a = 0; a < NX; ++a) {
-                double v = gc[a];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) v += p.A[c * NX + a] * pc[c];
-                np_[a] = v;
-            }
-#pragma unroll
-            for (int a = 0; a < NX; ++a) pc[a] = np_[a] + (kg ? m[L::M_GGL + a] : 0.0);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) pc[NX + t] += (kg ? m[L::M_GGL + NX + t] : 0.0);
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            ci = lb_max(ci, lb_abs(pc[NX + t]));
-            ydot += pc[NX + t] * m[L::M_TH + t];
+            nrm = lb_nanmax(nrm, lb_abs(pi[NX + t]));
+            ydot += pi[NX + t] * m[L::M_TH + t];
         }
-        m[L::M_CERT] = ci;
-        m[L::M_HLAM] += ydot;
+        if (farkas) {
+            m[L::M_CERT] = nrm;
+            m[L::M_HLAM] += ydot;
+        } else {
+            m[L::M_RD] = nrm;
+        }
     }
 
-    // ============================================================================================
-    // sweep: backward substitution (gradient recursion) with the stored factors:
+    // ---- backward substitution (gradient recursion) with the stored factors:
     //   rt = q_u + B'pv ; kap_k = -Ri rt ; pv <- q_z + Abar'pv - RL' rt ; d(theta) = -Ptt^-1 pv_theta
-    // d(theta) goes to M_DTHA (aff) or M_DTH.
-    // ============================================================================================
+    // d(theta) goes to M_DTHA (aff) or M_DTH. ----
+    struct BwdOps {  // shared-memory operands of one stage
+        double q[NVB], gt[NT], RL[NU * NZ], Ri[NU * NU];
+    };
+    static LB_HD void bwd_load(const double* r2, BwdOps& o) {
+#pragma unroll
+        for (int j = 0; j < NVB; ++j) o.q[j] = r2[L::F_Q + j];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) o.gt[t] = r2[L::F_G + NX + t];
+#pragma unroll
+        for (int j = 0; j < NU * NZ; ++j) o.RL[j] = r2[L::F_RL + j];
+#pragma unroll
+        for (int j = 0; j < NU * NU; ++j) o.Ri[j] = r2[L::F_RI + j];
+    }
+    static LB_HD void bwd_step(const AB& c, const BwdOps& o, double* pv, double* r2) {
+        double rt[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            double v0 = o.q[NX + i], v1 = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) {
+                if (cc & 1) v1 += c.B[cc * NU + i] * pv[cc];
+                else v0 += c.B[cc * NU + i] * pv[cc];
+            }
+            rt[i] = v0 + v1;
+        }
+        double np_[NZ];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            double v = o.q[a];
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) v += c.A[cc * NX + a] * pv[cc];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) v -= o.RL[i * NZ + a] * rt[i];
+            np_[a] = v;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            double v = o.gt[t] + pv[NX + t];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) v -= o.RL[i * NZ + NX + t] * rt[i];
+            np_[NX + t] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) v -= o.Ri[i * NU + j] * rt[j];
+            r2[L::F_KAP + i] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) pv[a] = np_[a];
+    }
     static LB_HD void backward_vec(const P& p, const L& l, double* s, bool aff) {
         double pv[NZ];
         double* m = s + l.o_misc;
         const int N = p.N;
+        AB c;
+        load_ab(p, c);
 #pragma unroll
         for (int a = 0; a < NZ; ++a) {
-            const double base = a < NX ? s[l.o_q + a * l.Np + N] : s[l.o_g + a * l.Np + N];
+            const double base = a < NX ? s[l.i_q(a, N)] : s[l.i_g(a, N)];
             pv[a] = base + (p.kg == N ? m[L::M_GGL + a] + m[L::M_DG + a] : 0.0);
         }
-        for (int k = N - 1; k >= 0; --k) {
-            const bool kg = (p.kg == k);
-            double rt[NU];
+        double* r2 = s + l.r2(N - 1);
+        BwdOps o0, o1;
+        bwd_load(r2, o0);
+        int k = N - 1;
+        for (; k >= 1; k -= 2) {
+            bwd_load(r2 - L::RS2, o1);
+            bwd_step(c, o0, pv, r2);
+            if (p.kg == k) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                double v0 = s[l.o_q + (NX + i) * l.Np + k], v1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    if (c & 1) v1 += p.B[c * NU + i] * pv[c];
-                    else v0 += p.B[c * NU + i] * pv[c];
-                }
-                rt[i] = v0 + v1;
+                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
             }
+            r2 -= 2 * L::RS2;
+            bwd_load(k >= 2 ? r2 : r2 + L::RS2, o0);
+            bwd_step(c, o1, pv, r2 + L::RS2);
+            if (p.kg == k - 1) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < NU; ++j) v -= s[l.o_Ri + (i * NU + j) * l.Np + k] * rt[j];
-                s[l.o_kap + i * l.Np + k] = v;
+                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
             }
-            double np_[NZ];
+        }
+        if (k == 0) {
+            bwd_step(c, o0, pv, r2);
+            if (p.kg == 0) {
 #pragma unroll
-            for (int a = 0; a < NX; ++a) {
-                double v0 = s[l.o_q + a * l.Np + k], v1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    if (c & 1) v1 += p.A[c * NX + a] * pv[c];
-                    else v0 += p.A[c * NX + a] * pv[c];
-                }
-                double v = v0 + v1;
-#pragma unroll
-                for (int i = 0; i < NU; ++i) v -= s[l.o_L + (i * NZ + a) * l.Np + k] * rt[i];
-                np_[a] = v;
+                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
             }
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                double v = s[l.o_g + (NX + t) * l.Np + k] + pv[NX + t];
-#pragma unroll
-                for (int i = 0; i < NU; ++i) v -= s[l.o_L + (i * NZ + NX + t) * l.Np + k] * rt[i];
-                np_[NX + t] = v;
-            }
-#pragma unroll
-            for (int a = 0; a < NZ; ++a) pv[a] = np_[a] + (kg ? m[L::M_GGL + a] + m[L::M_DG + a] : 0.0);
         }
 #pragma unroll
         for (int a = 0; a < NT; ++a) {
@@ -646,52 +699,77 @@ struct Core {
         }
     }
 
-    // ============================================================================================
-    // sweep: forward substitution  du_k = kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k
-    // ============================================================================================
+    // ---- forward substitution  du_k = kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k ----
+    struct FwdOps {
+        double RL[NU * NZ], kap[NU];
+    };
+    static LB_HD void fwd_load(const double* r2, FwdOps& o) {
+#pragma unroll
+        for (int j = 0; j < NU * NZ; ++j) o.RL[j] = r2[L::F_RL + j];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) o.kap[i] = r2[L::F_KAP + i];
+    }
+    // r3: record of stage k (du_k is written there, dx_{k+1} to the next record); off: 0 or NVB (affine)
+    static LB_HD void fwd_step(const AB& c, const FwdOps& o, const double* dth, double* dx, double* r3, int off) {
+        double du[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            double v0 = o.kap[i], v1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) v0 -= o.RL[i * NZ + NX + t] * dth[t];
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) {
+                if (cc & 1) v1 -= o.RL[i * NZ + cc] * dx[cc];
+                else v0 -= o.RL[i * NZ + cc] * dx[cc];
+            }
+            du[i] = v0 + v1;
+        }
+        double xn[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NX; ++cc) v += c.A[a * NX + cc] * dx[cc];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) v += c.B[a * NU + i] * du[i];
+            xn[a] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) r3[off + L::F_DU + i] = du[i];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            dx[a] = xn[a];
+            r3[L::RS3 + off + L::F_DX + a] = xn[a];
+        }
+    }
     static LB_HD void forward_vec(const P& p, const L& l, double* s, bool aff) {
-        const int ox = aff ? l.o_dxa : l.o_dx, ou = aff ? l.o_dua : l.o_du;
+        const int off = aff ? NVB : 0;
         const double* m = s + l.o_misc;
-        double dx[NX], dth[NT], du[NU];
+        const int N = p.N;
+        AB c;
+        load_ab(p, c);
+        double dx[NX], dth[NT];
+        double* r3 = s + l.r3(0);
+        const double* r2 = s + l.r2(0);
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
             dx[j] = 0.0;
-            s[ox + j * l.Np] = 0.0;
+            r3[off + L::F_DX + j] = 0.0;
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) dth[t] = m[(aff ? L::M_DTHA : L::M_DTH) + t];
-        for (int k = 0; k < p.N; ++k) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                double v0 = s[l.o_kap + i * l.Np + k], v1 = 0.0;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) v0 -= s[l.o_L + (i * NZ + NX + t) * l.Np + k] * dth[t];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    if (c & 1) v1 -= s[l.o_L + (i * NZ + c) * l.Np + k] * dx[c];
-                    else v0 -= s[l.o_L + (i * NZ + c) * l.Np + k] * dx[c];
-                }
-                du[i] = v0 + v1;
-                s[ou + i * l.Np + k] = du[i];
-            }
-            double xn[NX];
-#pragma unroll
-            for (int a = 0; a < NX; ++a) {
-                double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    if (c & 1) v1 += p.A[a * NX + c] * dx[c];
-                    else v0 += p.A[a * NX + c] * dx[c];
-                }
-                double v = v0 + v1;
-#pragma unroll
-                for (int i = 0; i < NU; ++i) v += p.B[a * NU + i] * du[i];
-                xn[a] = v;
-                s[ox + a * l.Np + k + 1] = v;
-            }
-#pragma unroll
-            for (int a = 0; a < NX; ++a) dx[a] = xn[a];
+        FwdOps o0, o1;
+        fwd_load(r2, o0);
+        int k = 0;
+        for (; k + 1 < N; k += 2) {
+            fwd_load(r2 + L::RS2, o1);
+            fwd_step(c, o0, dth, dx, r3, off);
+            r2 += 2 * L::RS2;
+            fwd_load(k + 2 < N ? r2 : r2 - L::RS2, o0);
+            fwd_step(c, o1, dth, dx, r3 + L::RS3, off);
+            r3 += 2 * L::RS3;
         }
+        if (k < N) fwd_step(c, o0, dth, dx, r3, off);
     }
 
     // ============================================================================================
@@ -708,12 +786,12 @@ struct Core {
             if (j >= NX && k >= p.N) continue;
             double aj = 0.0, bj = 0.0;
             if ((rows >> (2 * j)) & 3u) {
-                const double v = bvar(l, s, l.o_x, l.o_u, k, j), dva = bvar(l, s, l.o_dxa, l.o_dua, k, j);
+                const double v = s[l.i_v(j, k)], dva = s[l.i_dv(j, k, true)];
 #pragma unroll
                 for (int side = 0; side < 2; ++side) {
                     if (!((rows >> (2 * j + side)) & 1u)) continue;
-                    const int r = (2 * j + side) * l.Np + k;
-                    const double S = s[l.o_sb + r], Lm = s[l.o_lb + r];
+                    const int r = 2 * j + side;
+                    const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
                     const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
@@ -727,15 +805,15 @@ struct Core {
                     bj += sgn * is;
                 }
             }
-            s[l.o_q + j * l.Np + k] = s[l.o_g + zidx(j) * l.Np + k] + aj;
-            s[l.o_dx + j * l.Np + k] = bj;
+            s[l.i_q(j, k)] = s[l.i_g(zidx(j), k)] + aj;
+            s[l.i_dv(j, k, false)] = bj;
         }
     }
     static LB_HD void corr_stage(const P& p, const L& l, double* s, int k, double sigmu) {
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
             if (j >= NX && k >= p.N) continue;
-            s[l.o_q + j * l.Np + k] += sigmu * s[l.o_dx + j * l.Np + k];
+            s[l.i_q(j, k)] += sigmu * s[l.i_dv(j, k, false)];
         }
     }
     // polytope row i: acc[0..NZ) += G (t1 - lambda), acc[NZ..2NZ) += G / s   (dG = acc1 + sigmu acc2)
@@ -749,7 +827,7 @@ struct Core {
 #pragma unroll
         for (int a = 0; a < NX; ++a) {
             g[a] = G[a * p.ngp + i];
-            adva += g[a] * s[l.o_dxa + a * l.Np + p.kg];
+            adva += g[a] * s[l.i_dv(a, p.kg, true)];
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -773,21 +851,19 @@ struct Core {
     // stage: final (corrector) row directions of stage k -> parks ds, dl in the scratch block that
     // starts at o_qd, returns the step-length ratio.  update_stage applies the step.
     // ============================================================================================
-    static LB_HD int scr_ds(const L& l, int j, int side, int k) { return l.o_qd + (2 * j + side) * l.Np + k; }
-    static LB_HD int scr_dl(const L& l, int j, int side, int k) { return l.o_qd + (2 * NVB + 2 * j + side) * l.Np + k; }
     static LB_HD double final_stage(const P& p, const L& l, double* s, int k, double sigmu) {
         const unsigned rows = stage_rows(p, k);
         double ratio = 0.0;
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
             if (!((rows >> (2 * j)) & 3u)) continue;
-            const double v = bvar(l, s, l.o_x, l.o_u, k, j), dva = bvar(l, s, l.o_dxa, l.o_dua, k, j),
-                         dv = bvar(l, s, l.o_dx, l.o_du, k, j);
+            const double v = s[l.i_v(j, k)], dva = s[l.i_dv(j, k, true)],
+                         dv = s[l.i_dv(j, k, false)];
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = (2 * j + side) * l.Np + k;
-                const double S = s[l.o_sb + r], Lm = s[l.o_lb + r];
+                const int r = 2 * j + side;
+                const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
                 const double sgn = side == 0 ? 1.0 : -1.0;
                 const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
                 const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
@@ -796,8 +872,8 @@ struct Core {
                 const double rc = S * Lm + dsa * dla - sigmu;
                 const double dl = (-rc - Lm * ds) * is;
                 ratio = lb_max(ratio, lb_max(-ds * is, -dl * lb_rcp(Lm)));
-                s[scr_ds(l, j, side, k)] = ds;
-                s[scr_dl(l, j, side, k)] = dl;
+                s[l.i_scr_ds(2 * j + side, k)] = ds;
+                s[l.i_scr_dl(2 * j + side, k)] = dl;
             }
         }
         return ratio;
@@ -809,16 +885,16 @@ struct Core {
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = (2 * j + side) * l.Np + k;
-                s[l.o_sb + r] += alpha * s[scr_ds(l, j, side, k)];
-                s[l.o_lb + r] += alpha * s[scr_dl(l, j, side, k)];
+                const int r = 2 * j + side;
+                s[l.i_sb(r, k)] += alpha * s[l.i_scr_ds(2 * j + side, k)];
+                s[l.i_lb(r, k)] += alpha * s[l.i_scr_dl(2 * j + side, k)];
             }
         }
 #pragma unroll
-        for (int j = 0; j < NX; ++j) s[l.o_x + j * l.Np + k] += alpha * s[l.o_dx + j * l.Np + k];
+        for (int j = 0; j < NX; ++j) s[l.i_x(j, k)] += alpha * s[l.i_dv(j, k, false)];
         if (k < p.N) {
 #pragma unroll
-            for (int j = 0; j < NU; ++j) s[l.o_u + j * l.Np + k] += alpha * s[l.o_du + j * l.Np + k];
+            for (int j = 0; j < NU; ++j) s[l.i_u(j, k)] += alpha * s[l.i_dv(NX + j, k, false)];
         }
     }
     // polytope row i, final direction (recomputed by final_gen_row and update_gen_row: no scratch)
@@ -835,8 +911,8 @@ struct Core {
 #pragma unroll
         for (int a = 0; a < NX; ++a) {
             const double g = G[a * p.ngp + i];
-            adva += g * s[l.o_dxa + a * l.Np + p.kg];
-            adv += g * s[l.o_dx + a * l.Np + p.kg];
+            adva += g * s[l.i_dv(a, p.kg, true)];
+            adv += g * s[l.i_dv(a, p.kg, false)];
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -867,12 +943,12 @@ struct Core {
     static LB_HD double objective_stage(const P& p, const L& l, const double* s, int k) {
         double v[NV];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v[j] = s[l.o_x + j * l.Np + k];
+        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)];
 #pragma unroll
         for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
         const bool last = k >= p.N;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.o_u + j * l.Np + k];
+        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.i_u(j, k)];
         const double* W = p.W[stage_type(p, k)];
         double J = 0.0;
 #pragma unroll
@@ -908,23 +984,30 @@ struct Core {
 // Lane h < NH owns one unique entry (a,b), a <= b, of the symmetric NZ x NZ cost-to-go matrix, kept
 // SCALED by the pivot of the stage it came from:  Pt = rho P, ir = 1/rho.  One stage is
 //     F    = Abar_e' Pt Abar_e,  Abar_e = [Abar Bbar]        (every entry a fixed linear form in the
-//                                                             NH unique entries of Pt: dot products
+//                                                             unique entries of Pt: dot products
 //                                                             with per-lane coefficient vectors)
 //     Rt   = Wuu + Qd_u + F_uu ir ,  L = Wuz + F_uz ir
 //     Pt'  = Rt (Wzz + Qd + [HG] + F_zz ir) - L'L ,  rho' = Rt
-// which is P' = Wzz + Qd + Abar'P Abar - L'L/Rt multiplied through by Rt: the reciprocal of the
-// pivot is only needed one stage later (and for the stored factors RL = L/Rt, Ri = 1/Rt), so it
-// overlaps the next stage's exchange and dot products instead of sitting on the dependency chain.
-// Lanes 0..NX-1 also produce F_uz[a] (a < NX), lane NX produces F_uu, lane 15 produces F_uz[theta].
-// Two exchanges per stage through a small shared buffer: xch (the NH entries), xf (F_uz, F_uu).
-// The three lane-phases st1/st2/st3 are separated by __syncwarp() in the kernel; tests/emul runs
-// them as loops over the 16 lanes.
+// which is P' = Wzz + Qd + Abar'P Abar - L'L/Rt multiplied through by Rt.  The reciprocal of the
+// pivot is needed only one stage later (and for the stored factors RL = L/Rt, Ri = 1/Rt): its
+// hardware seed is issued as soon as Rt exists and its Newton refinement is interleaved with the
+// next stage's dot products, so it never sits on the stage-to-stage dependency chain.
+//
+// Exchange 1 (shared memory, xch): every lane publishes its entry; entries are ordered
+// [xx block | (a,theta) | (theta,theta) | zero pad] so that each lane reads the 10 values its forms
+// need from a lane-type dependent base (xx lanes: base 0; (a,theta) lanes and lane 15: base NXX;
+// (theta,theta): base NH-1).  Lanes 0..NX-1 also produce F_uz[a], lane NX produces F_uu, lane 15
+// produces F_uz[theta].  Exchange 2 (warp shuffles in the kernel, `pub` in the emulation): each
+// entry lane fetches F_uz[a], F_uz[b], F_uu.
+// The lane-phases st1/st2/st3 are separated by __syncwarp()/shuffles in the kernel; tests/emul
+// runs them as loops over the 16 lanes.
 // ------------------------------------------------------------------------------------------------
 template <int NX>
 struct Coop {
     static constexpr int NT = 1, NU = 1, NZ = NX + 1, NV = NZ + 1, NH = NZ * (NZ + 1) / 2, NXX = NX * (NX + 1) / 2;
-    static constexpr int kLanes = 16, kXch = 16, kXf = 8;
-    static_assert(NH <= 15 && NZ + 1 <= kXf, "shape does not fit the 16-lane mapping");
+    static constexpr int kLanes = 16, kXch = 24;
+    static constexpr int NLD = (NXX + 1) & ~1;  // values each lane reads (even: 16-byte loads)
+    static_assert(NH <= 15 && NX >= 2 && NX + 1 <= NXX && NH - 1 + NLD <= kXch, "shape does not fit the 16-lane mapping");
     using P = Params<NX, 1, 1>;
     using L = Layout<NX, 1, 1>;
     using C = Core<NX, 1, 1>;
@@ -934,22 +1017,35 @@ struct Coop {
         return b < NX ? a * NX - a * (a - 1) / 2 + (b - a) : (a < NX ? NXX + a : NH - 1);
     }
     struct Lane {
-        int a, b;           // entry owned (h < NH)
-        bool isP, diag;
-        double c1[NH];      // F_zz[a][b] (h < NH) or F_uz[theta] (h == 15) as a linear form in the entries
-        double c2[NXX];     // F_uz[h] (h < NX) or F_uu (h == NX) as a linear form in the xx entries
+        int a, b, sa, sb, base;  // entry owned (h < NH), source lanes of F_uz[a], F_uz[b], read base in xch
+        bool isP, diag, dgx;     // dgx: diagonal entry of a bounded state (gets the barrier term)
+        double c1[NLD];          // F_zz[a][b] (h < NH) or F_uz[theta] (h == 15) as a form in xch[base..]
+        double c2[NLD];          // F_uz[h] (h < NX) or F_uu (h == NX) as a form in the xx entries
         double wzz, wa, wb, wuu;
-        double pt, ir, d1;
-        bool ok;
+        double pt, ir, d1, pub;
+        double qdu, qda, hgv;    // stage inputs fetched ahead (Qd_u, Qd_a on the diagonal, HG entry at kg)
+        double rt, y0, la;       // pivot, reciprocal seed and L_a of the previous stage (deferred refinement)
+        bool ok, pend;           // pend: a previous stage's factors are waiting to be stored
     };
-    static LB_HD double abar(const P& p, int c, int a) {  // Abar[c][a]
-        return c < NX ? (a < NX ? p.A[c * NX + a] : 0.0) : (a == NX ? 1.0 : 0.0);
+    static LB_HD double rcp_seed(double x) {
+#ifdef __CUDA_ARCH__
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        return y;
+#else
+        return 1.0 / x;
+#endif
+    }
+    static LB_HD double rcp_refine(double x, double y) {
+        double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+        e = fma(-x, y, 1.0);
+        return fma(y, e, y);
     }
     static LB_HD void lane_init(const P& p, int h, Lane& ln) {
         ln.isP = h < NH;
         ln.a = 0;
         ln.b = 0;
-        // decode (a,b) of entry h
 #pragma unroll
         for (int a = 0; a < NZ; ++a)
 #pragma unroll
@@ -959,36 +1055,49 @@ struct Coop {
                     ln.b = b;
                 }
         ln.diag = ln.isP && ln.a == ln.b;
+        ln.dgx = ln.diag && ln.a < NX;
+        ln.sa = ln.a < NX ? ln.a : 15;
+        ln.sb = ln.b < NX ? ln.b : 15;
+        const bool xx = h < NXX, xt = (h >= NXX && h < NH - 1), tt = (h == NH - 1), ft = (h == 15);
+        ln.base = xx ? 0 : (tt ? NH - 1 : NXX);
 #pragma unroll
-        for (int c = 0; c < NZ; ++c)
-#pragma unroll
-            for (int d = c; d < NZ; ++d) {
-                double v = 0.0;
-                if (ln.isP) {
-                    v = abar(p, c, ln.a) * abar(p, d, ln.b);
-                    if (c != d) v += abar(p, d, ln.a) * abar(p, c, ln.b);
-                } else if (h == 15) {  // F_uz[theta] = sum_c B[c] Pt[c][theta]
-                    v = (c < NX && d == NX) ? p.B[c] : 0.0;
-                }
-                ln.c1[ent(c, d)] = v;
-            }
+        for (int j = 0; j < NLD; ++j) {
+            ln.c1[j] = 0.0;
+            ln.c2[j] = 0.0;
+        }
 #pragma unroll
         for (int c = 0; c < NX; ++c)
 #pragma unroll
             for (int d = c; d < NX; ++d) {
-                double v = 0.0;
-                if (h < NX) {
-                    v = p.A[c * NX + h] * p.B[d];
-                    if (c != d) v += p.A[d * NX + h] * p.B[c];
-                } else if (h == NX) {
-                    v = p.B[c] * p.B[d] * (c != d ? 2.0 : 1.0);
+                const int e = ent(c, d);
+                if (xx) {  // F_zz[a][b], a,b < NX
+                    double v = p.A[c * NX + ln.a] * p.A[d * NX + ln.b];
+                    if (c != d) v += p.A[d * NX + ln.a] * p.A[c * NX + ln.b];
+                    ln.c1[e] = v;
                 }
-                ln.c2[ent(c, d)] = v;
+                double w = 0.0;
+                if (h < NX) {  // F_uz[h]
+                    w = p.A[c * NX + h] * p.B[d];
+                    if (c != d) w += p.A[d * NX + h] * p.B[c];
+                } else if (h == NX) {  // F_uu
+                    w = p.B[c] * p.B[d] * (c != d ? 2.0 : 1.0);
+                }
+                ln.c2[e] = w;
             }
+#pragma unroll
+        for (int c = 0; c < NX; ++c) {
+            if (xt) ln.c1[c] = p.A[c * NX + ln.a];  // F_zz[a][theta] = sum_c A[c][a] Pt[c][theta]
+            if (ft) ln.c1[c] = p.B[c];              // F_uz[theta]    = sum_c B[c] Pt[c][theta]
+        }
+        if (tt) ln.c1[0] = 1.0;                     // F_zz[theta][theta] = Pt[theta][theta]
         ln.ok = true;
+        ln.pend = false;
         ln.pt = 0.0;
         ln.ir = 1.0;
-        ln.d1 = 0.0;
+        ln.d1 = ln.pub = 0.0;
+        ln.qdu = ln.qda = ln.hgv = 0.0;
+        ln.rt = ln.y0 = 1.0;
+        ln.la = 0.0;
         ln.wzz = ln.wa = ln.wb = ln.wuu = 0.0;
     }
     static LB_HD void load_type(const P& p, int t, Lane& ln) {
@@ -998,66 +1107,91 @@ struct Coop {
         ln.wb = W[NZ * NV + ln.b];
         ln.wuu = W[NZ * NV + NZ];
     }
+    // stage inputs of stage k (no dependence on the recursion: fetched before the exchange)
+    static LB_HD void fetch(const P& p, const L& l, const double* s, int k, Lane& ln) {
+        ln.qdu = s[l.i_qd(NX, k)];
+        ln.qda = ln.dgx ? s[l.i_qd(ln.a, k)] : 0.0;
+        ln.hgv = (k == p.kg) ? s[l.o_misc + L::M_HG + C::sym(ln.a, ln.b)] : 0.0;
+    }
     // terminal stage: Pt = Wzz + Qd (+HG), rho = 1
     static LB_HD void terminal(const P& p, const L& l, const double* s, Lane& ln) {
-        const double* m = s + l.o_misc;
         const int N = p.N;
         load_type(p, C::stage_type(p, N), ln);
-        double v = ln.wzz;
-        if (ln.diag && ln.a < NX) v += s[l.o_qd + ln.a * l.Np + N];
-        if (p.kg == N) v += m[L::M_HG + C::sym(ln.a, ln.b)];
-        ln.pt = ln.isP ? v : 0.0;
+        fetch(p, l, s, N, ln);
+        ln.pt = ln.isP ? ln.wzz + ln.qda + ln.hgv : 0.0;
         ln.ir = 1.0;
+        ln.rt = ln.y0 = 1.0;
         ln.ok = true;
+        ln.pend = false;
     }
-    static LB_HD void st1(const Lane& ln, int h, double* xch) {
+    // zero the pad of the exchange buffer once (entries beyond NH are read with zero coefficients)
+    static LB_HD void xch_init(int h, double* xch) {
+        for (int j = h; j < kXch; j += kLanes) xch[j] = 0.0;
+    }
+    static LB_HD void st1(const P& p, const L& l, const double* s, int k, int h, Lane& ln, double* xch) {
         if (h < NH) xch[h] = ln.pt;
+        fetch(p, l, s, k, ln);
     }
-    static LB_HD void st2(Lane& ln, int h, const double* xch, double* xf) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0;
+    // dot products + deferred refinement / store of the previous stage's reciprocal pivot
+    //   kprev = k + 1 (stage whose factors are pending), act = the half-warp owns a running QP
+    static LB_HD void st2(const L& l, double* s, int kprev, int h, Lane& ln, const double* xch, bool act) {
+        double v[NLD];
+#ifdef __CUDA_ARCH__
+        const double2* src = reinterpret_cast<const double2*>(xch + ln.base);
 #pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const double v = xch[j];
-            if (j % 3 == 0) a0 += ln.c1[j] * v;
-            else if (j % 3 == 1) a1 += ln.c1[j] * v;
-            else a2 += ln.c1[j] * v;
-            if (j < NXX) {
-                if (j & 1) b1 += ln.c2[j] * v;
-                else b0 += ln.c2[j] * v;
+        for (int j = 0; j < NLD / 2; ++j) {
+            const double2 t = src[j];
+            v[2 * j] = t.x;
+            v[2 * j + 1] = t.y;
+        }
+#else
+        for (int j = 0; j < NLD; ++j) v[j] = xch[ln.base + j];
+#endif
+        const double irn = rcp_refine(ln.rt, ln.y0);  // 1/rho of the matrix being read
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            if (j & 1) {
+                a1 += ln.c1[j] * v[j];
+                b1 += ln.c2[j] * v[j];
+            } else {
+                a0 += ln.c1[j] * v[j];
+                b0 += ln.c2[j] * v[j];
             }
         }
-        ln.d1 = (a0 + a1) + a2;
-        const double d2 = b0 + b1;
-        if (h < NX) xf[h] = d2;            // F_uz[h]
-        else if (h == NX) xf[NZ] = d2;     // F_uu
-        else if (h == 15) xf[NX] = ln.d1;  // F_uz[theta]
-    }
-    // act = false: the half-warp has no running QP (nothing is stored)
-    static LB_HD void st3(const P& p, const L& l, double* s, int k, int h, Lane& ln, const double* xf, bool act) {
-        if (!ln.isP) return;
-        const double fa = xf[ln.a], fb = xf[ln.b], fuu = xf[NZ];
-        const double ir = ln.ir;
-        const double Rt = (ln.wuu + s[l.o_qd + NX * l.Np + k]) + fuu * ir;
-        const double La = ln.wa + fa * ir, Lb = ln.wb + fb * ir;
-        double hz = ln.wzz + ln.d1 * ir;
-        if (ln.diag && ln.a < NX) hz += s[l.o_qd + ln.a * l.Np + k];
-        if (k == p.kg) hz += s[l.o_misc + L::M_HG + C::sym(ln.a, ln.b)];
-        ln.pt = Rt * hz - La * Lb;
-        ln.ok = ln.ok && (Rt > 0.0);
-        const double irn = lb_rcp(Rt);
+        ln.d1 = a0 + a1;
+        ln.pub = (h == 15) ? ln.d1 : (b0 + b1);
         ln.ir = irn;
-        if (act) {
-            if (ln.diag) s[l.o_L + ln.a * l.Np + k] = La * irn;  // RL_k[a]
-            if (h == 0) s[l.o_Ri + k] = irn;
+        if (ln.pend && act) {
+            if (ln.diag) s[l.i_L(ln.a, kprev)] = ln.la * irn;  // RL[a] of stage kprev
+            if (h == 0) s[l.i_Ri(0, kprev)] = irn;
         }
     }
-    // after stage 0: inverse of the theta block of P_0 (lane of the (theta,theta) entry)
+    static LB_HD void st3(Lane& ln, double fa, double fb, double fuu) {
+        const double ir = ln.ir;
+        const double Rt = (ln.wuu + ln.qdu) + fuu * ir;
+        const double La = ln.wa + fa * ir, Lb = ln.wb + fb * ir;
+        const double hz = (ln.wzz + ln.qda + ln.hgv) + ln.d1 * ir;
+        ln.pt = Rt * hz - La * Lb;
+        ln.ok = ln.ok && (Rt > 0.0);
+        ln.rt = Rt;
+        ln.y0 = rcp_seed(Rt);
+        ln.la = La;
+        ln.pend = true;
+    }
+    // after stage 0: store its factors, inverse of the theta block of P_0 (lane of the (theta,theta) entry)
     static LB_HD void finish(const L& l, double* s, int h, Lane& ln, bool act) {
+        const double irn = rcp_refine(ln.rt, ln.y0);
+        if (ln.pend && act) {
+            if (ln.diag) s[l.i_L(ln.a, 0)] = ln.la * irn;
+            if (h == 0) s[l.i_Ri(0, 0)] = irn;
+        }
         if (h == NH - 1) {
-            const double ptt = ln.pt * ln.ir;
+            const double ptt = ln.pt * irn;
             ln.ok = ln.ok && (ptt > 0.0);
             if (act) s[l.o_misc + L::M_PTT] = 1.0 / ptt;
         }
+        if (!ln.isP) ln.ok = true;
     }
 };
 

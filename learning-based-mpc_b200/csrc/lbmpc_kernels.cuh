@@ -135,7 +135,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
     using C = Core<NX, NT, NU>;
     using L = Layout<NX, NT, NU>;
     constexpr int NZ = NX + NT, NH = L::NH, NACC = NH + 2 * NZ;
-    constexpr bool kCoop = (NT == 1 && NU == 1 && NX <= 4);  // 16-lane Riccati factorisation
+    constexpr bool kCoop = (NT == 1 && NU == 1 && NX >= 2 && NX <= 4);  // 16-lane Riccati factorisation
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const L l(p.N, p.ngp);
@@ -166,14 +166,16 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
     if (lane == 0 && warp < kMaxSlots) meta[warp * 4 + 0] = SLOT_EMPTY;
 
     // ---- cooperative factorisation: per-lane coefficient vectors (registers), exchange buffers ----
-    using CP = Coop<kCoop ? NX : 1>;
+    using CP = Coop<kCoop ? NX : 2>;
     typename CP::Lane ln;
     const int half = lane >> 4, hl = lane & 15;
     const int fslot = warp * 2 + half;  // slot factored by this half-warp (warps 0..3)
     double* const xch = smem + plan.xch_off + (fslot & (kMaxSlots - 1)) * SmemPlan<NX, NT, NU>::kXchPerSlot;
-    double* const xf = xch + CP::kXch;
     if constexpr (kCoop) {
-        if (warp < kMaxSlots / 2) CP::lane_init(p, hl, ln);
+        if (warp < kMaxSlots / 2) {
+            CP::lane_init(p, hl, ln);
+            CP::xch_init(hl, xch);
+        }
     }
     if (stage_g) mbar_wait(bar, 0);
     __syncthreads();
@@ -227,16 +229,16 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 for (int k = lane; k < N; k += 32) {
 #pragma unroll
                     for (int i = 0; i < NU; ++i) {
-                        double v = slot[l.o_u + i * l.Np + k];
+                        double v = slot[l.i_u(i, k)];
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * slot[l.o_x + j * l.Np + k];
+                        for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * slot[l.i_x(j, k)];
                         io.uc[(q * N + k) * NU + i] = v;
                     }
                 }
                 if (io.xtraj) {
                     for (int k = lane; k <= N; k += 32)
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = slot[l.o_x + j * l.Np + k];
+                        for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = slot[l.i_x(j, k)];
                 }
                 if (lane == 0) {
 #pragma unroll
@@ -255,14 +257,14 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
             q = __shfl_sync(kFull, q, 0);
             if (q >= 0) {
-                if (lane < NX) slot[l.o_x + lane * l.Np] = io.dx0[q * NX + lane];
+                if (lane < NX) slot[l.i_x(lane, 0)] = io.dx0[q * NX + lane];
                 for (int k = lane; k < N; k += 32) {
 #pragma unroll
                     for (int i = 0; i < NU; ++i)
-                        slot[l.o_u + i * l.Np + k] = io.warm ? io.warm[q * (NU * N + NT) + k * NU + i] : 0.0;
+                        slot[l.i_u(i, k)] = io.warm ? io.warm[q * (NU * N + NT) + k * NU + i] : 0.0;
 #pragma unroll
                     for (int j = 0; j < NX; ++j)
-                        slot[l.o_x + j * l.Np + k + 1] = io.d_off ? io.d_off[(q * N + k) * NX + j] : 0.0;
+                        slot[l.i_x(j, k + 1)] = io.d_off ? io.d_off[(q * N + k) * NX + j] : 0.0;
                 }
                 if (lane == 0) {
 #pragma unroll
@@ -374,24 +376,30 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         // phase B: Riccati factorisation (warps 0..3, 16 lanes per QP) with, on the otherwise
         //          idle warps, the adjoint recursion (dual residual) and the Farkas recursion
         // =====================================================================================
+        const bool prof_w = io.prof != nullptr && blockIdx.x == 0 && lane == 0;
+        const long long tb0 = prof_w ? clock64() : 0;
         if constexpr (kCoop) {
             if (warp < kMaxSlots / 2) {
                 const bool act = fslot < slots && meta[fslot * 4 + 0] == SLOT_RUN && meta[fslot * 4 + 1] < p.max_iter;
                 if (__any_sync(kFull, act)) {
                     double* const sl = smem + (fslot < slots ? fslot : 0) * l.stride;
+                    const int hb = lane & 16;
                     CP::terminal(p, l, sl, ln);
-                    int type = C::stage_type(p, N);
+                    int type = C::stage_type(p, N), kseg = p.tseg[type];
                     for (int k = N - 1; k >= 0; --k) {
-                        const int t = C::stage_type(p, k);
-                        if (t != type) {
-                            type = t;
-                            CP::load_type(p, t, ln);
+                        if (k < kseg) {  // crossed into the previous cost segment
+                            type = C::stage_type(p, k);
+                            kseg = p.tseg[type];
+                            CP::load_type(p, type, ln);
                         }
-                        CP::st1(ln, hl, xch);
+                        CP::st1(p, l, sl, k, hl, ln, xch);
                         __syncwarp();
-                        CP::st2(ln, hl, xch, xf);
-                        __syncwarp();
-                        CP::st3(p, l, sl, k, hl, ln, xf, act);
+                        CP::st2(l, sl, k + 1, hl, ln, xch, act);
+                        const double fa = __shfl_sync(kFull, ln.pub, hb | ln.sa);
+                        const double fb = __shfl_sync(kFull, ln.pub, hb | ln.sb);
+                        const double fuu = __shfl_sync(kFull, ln.pub, hb | NX);
+                        CP::st3(ln, fa, fb, fuu);
+                        __syncwarp();  // xch is rewritten by the next stage's st1
                     }
                     CP::finish(l, sl, hl, ln, act);
                     const unsigned okb = __ballot_sync(kFull, ln.ok);
@@ -399,25 +407,28 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     if (act && hl == 0) sl[l.o_misc + L::M_PIV] = ((okb & hm) == hm) ? 1.0 : 0.0;
                 }
             } else if (warp == kMaxSlots / 2) {
-                if (lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter)
-                    C::adjoint_sweep(p, l, smem + lane * l.stride);
-            } else if (warp == kMaxSlots / 2 + 1) {
-                if (lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
-                    double* const sl = smem + lane * l.stride;
-                    if (sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::farkas_sweep(p, l, sl);
+                // lanes 0..7: dual residual of slot `lane`; lanes 8..15: Farkas recursion of slot `lane - 8`
+                const int sl_i = lane & (kMaxSlots - 1);
+                const bool fk = lane >= kMaxSlots;
+                if (lane < 2 * kMaxSlots && sl_i < slots && meta[sl_i * 4 + 0] == SLOT_RUN && meta[sl_i * 4 + 1] < p.max_iter) {
+                    double* const sl = smem + sl_i * l.stride;
+                    if (!fk || sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::adjoint_sweep(p, l, sl, fk);
                 }
             }
         } else {
             if (warp == 0 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
-                double* const sl = smem + lane * l.stride;
-                C::factor_serial(p, l, sl);
-            } else if (warp == 1 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
-                C::adjoint_sweep(p, l, smem + lane * l.stride);
-            } else if (warp == 2 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
-                double* const sl = smem + lane * l.stride;
-                if (sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::farkas_sweep(p, l, sl);
+                C::factor_serial(p, l, smem + lane * l.stride);
+            } else if (warp == 1) {
+                const int sl_i = lane & (kMaxSlots - 1);
+                const bool fk = lane >= kMaxSlots;
+                if (lane < 2 * kMaxSlots && sl_i < slots && meta[sl_i * 4 + 0] == SLOT_RUN && meta[sl_i * 4 + 1] < p.max_iter) {
+                    double* const sl = smem + sl_i * l.stride;
+                    if (!fk || sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::adjoint_sweep(p, l, sl, fk);
+                }
             }
         }
+        if (prof_w && warp == 0) io.prof[6] += (unsigned long long)(clock64() - tb0);
+        if (prof_w && warp == kMaxSlots / 2) io.prof[7] += (unsigned long long)(clock64() - tb0);
         __syncthreads();
         LB_PROF(3)
 

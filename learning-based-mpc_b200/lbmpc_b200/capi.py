@@ -195,8 +195,9 @@ class Solver:
         instrumentation on/off for the following solve calls."""
         out = np.zeros(8, np.uint64)
         self._check(self.lib.lbmpc_debug_phase_cycles(self.h, int(enable), _ptr(out)), "lbmpc_debug_phase_cycles")
-        names = ("C_affine_step", "D_corrector_sweeps", "EA_update_assemble", "B_factor", "B2_affine_sweeps", "iterations")
-        return dict(zip(names, (int(v) for v in out[:6])))
+        names = ("C_affine_step", "D_corrector_sweeps", "EA_update_assemble", "B_factor", "B2_affine_sweeps", "iterations",
+                 "B_warp0_factor", "B_warp4_adjoint")
+        return dict(zip(names, (int(v) for v in out[:8])))
 
     def _check(self, rc, what):
         if rc != 0:

@@ -25,10 +25,10 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     const double *G = hp.G.data(), *hg = hp.hg.data();
     const int N = p.N;
     // ---- load (kernel: warp-parallel) ----
-    for (int j = 0; j < NX; ++j) s[l.o_x + j * l.Np] = dx0[j];
+    for (int j = 0; j < NX; ++j) s[l.i_x(j, 0)] = dx0[j];
     for (int k = 0; k < N; ++k) {
-        for (int i = 0; i < NU; ++i) s[l.o_u + i * l.Np + k] = warm ? warm[k * NU + i] : 0.0;
-        for (int j = 0; j < NX; ++j) s[l.o_x + j * l.Np + k + 1] = d_off ? d_off[k * NX + j] : 0.0;
+        for (int i = 0; i < NU; ++i) s[l.i_u(i, k)] = warm ? warm[k * NU + i] : 0.0;
+        for (int j = 0; j < NX; ++j) s[l.i_x(j, k + 1)] = d_off ? d_off[k * NX + j] : 0.0;
     }
     for (int t = 0; t < NT; ++t) m[L::M_TH + t] = warm ? warm[N * NU + t] : 0.0;
     double cconst = 0.0;
@@ -62,15 +62,16 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
             // 16-lane cooperative factorisation, lane-phases run as loops (kernel: __syncwarp between them)
             using CP = Coop<NX>;
             typename CP::Lane ln[16];
-            double xch[CP::kXch] = {0}, xf[CP::kXf] = {0};
-            for (int h = 0; h < 16; ++h) { CP::lane_init(p, h, ln[h]); CP::terminal(p, l, s, ln[h]); }
+            double xch[CP::kXch];
+            for (int h = 0; h < 16; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::terminal(p, l, s, ln[h]); }
             int type = C::stage_type(p, N);
             for (int k = N - 1; k >= 0; --k) {
                 const int t = C::stage_type(p, k);
                 if (t != type) { type = t; for (int h = 0; h < 16; ++h) CP::load_type(p, t, ln[h]); }
-                for (int h = 0; h < 16; ++h) CP::st1(ln[h], h, xch);
-                for (int h = 0; h < 16; ++h) CP::st2(ln[h], h, xch, xf);
-                for (int h = 0; h < 16; ++h) CP::st3(p, l, s, k, h, ln[h], xf, true);
+                for (int h = 0; h < 16; ++h) CP::st1(p, l, s, k, h, ln[h], xch);
+                for (int h = 0; h < 16; ++h) CP::st2(l, s, k + 1, h, ln[h], xch, true);
+                for (int h = 0; h < 16; ++h)          // kernel: three warp shuffles
+                    if (ln[h].isP) CP::st3(ln[h], ln[ln[h].sa].pub, ln[ln[h].sb].pub, ln[NX].pub);
             }
             bool ok = true;
             for (int h = 0; h < 16; ++h) { CP::finish(l, s, h, ln[h], true); ok = ok && ln[h].ok; }
@@ -78,8 +79,8 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         } else {
             C::factor_serial(p, l, s);
         }
-        C::adjoint_sweep(p, l, s);
-        if (cert) C::farkas_sweep(p, l, s);
+        C::adjoint_sweep(p, l, s, false);
+        if (cert) C::adjoint_sweep(p, l, s, true);
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
@@ -115,14 +116,14 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k);
     for (int k = 0; k < N; ++k)
         for (int i = 0; i < NU; ++i) {
-            double v = s[l.o_u + i * l.Np + k];
-            for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * s[l.o_x + j * l.Np + k];
+            double v = s[l.i_u(i, k)];
+            for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * s[l.i_x(j, k)];
             uc[k * NU + i] = v;
         }
     for (int t = 0; t < NT; ++t) theta[t] = m[L::M_TH + t];
     if (xtraj)
         for (int k = 0; k <= N; ++k)
-            for (int j = 0; j < NX; ++j) xtraj[k * NX + j] = s[l.o_x + j * l.Np + k];
+            for (int j = 0; j < NX; ++j) xtraj[k * NX + j] = s[l.i_x(j, k)];
     *obj = J; *iters = it; *status = st;
     return 0;
 }
