@@ -143,7 +143,7 @@ float lbmpc_last_kernel_ms(lbmpc_handle *h);
 
 /* diagnostic: SM-cycle counters of CTA 0 per kernel phase, accumulated over the solve calls made while enabled:
  * out8 = {C: affine step/sigma/refill, D: corrector sweeps, E+A: update+assembly, B: factorisation,
- * B2: verdict+affine sweeps, lock-step iterations, 0, 0}.  Reads and clears the counters, then sets `enable`. */
+ * B2: verdict+affine sweeps, lock-step iterations, factor warp, adjoint warp, 8 spare}; out8 holds 16 values.  Reads and clears the counters, then sets `enable`. */
 int lbmpc_debug_phase_cycles(lbmpc_handle *h, int enable, uint64_t *out8);
 
 /* roofline denominator: measured FP64-FMA throughput of the device in TFLOP/s (register-resident DFMA

@@ -174,8 +174,8 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(dmalloc(&h->dA, (size_t)hp.nx * hp.nx));
     CU_TRY(dmalloc(&h->dB, (size_t)hp.nx * hp.nu));
     CU_TRY(dmalloc(&h->dqueue, 1));
-    CU_TRY(dmalloc(&h->dprof, 8));
-    CU_TRY(cudaMemset(h->dprof, 0, 8 * sizeof(unsigned long long)));
+    CU_TRY(dmalloc(&h->dprof, 16));
+    CU_TRY(cudaMemset(h->dprof, 0, 16 * sizeof(unsigned long long)));
     CU_TRY(cudaMemcpy(h->dG, hp.G.data(), sizeof(double) * nz * hp.ngp, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->dhg, hp.hg.data(), sizeof(double) * hp.ngp, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->dA, hp.A.data(), sizeof(double) * hp.nx * hp.nx, cudaMemcpyHostToDevice));
@@ -381,8 +381,8 @@ int lbmpc_debug_phase_cycles(lbmpc_handle* h, int enable, uint64_t* out8) {
     if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());
-    if (out8) CU_TRY(cudaMemcpy(out8, h->dprof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemset(h->dprof, 0, 8 * sizeof(unsigned long long)));
+    if (out8) CU_TRY(cudaMemcpy(out8, h->dprof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemset(h->dprof, 0, 16 * sizeof(unsigned long long)));
     h->prof_on = enable != 0;
     return LBMPC_OK;
 }

@@ -198,22 +198,22 @@ struct Core {
     }
 
     // ============================================================================================
-    // stage/row: initial slacks and multipliers  s = max(h - a v, 1), lambda = 1
+    // Row phases.  The box rows of a stage are processed WITHOUT branches: rows that do not exist at
+    // a stage (stage_rows mask) are replaced by the neutral pair s = 1, lambda = 0 through selects,
+    // so the ten rows of a stage form one basic block and their dependency chains (reciprocal,
+    // directions, ratios) interleave instead of running one after the other.
     // ============================================================================================
-    static LB_HD void init_rows_stage(const P& p, const L& l, double* s, int k) {
-        const unsigned rows = stage_rows(p, k);
+    struct StageRows {  // iterate of one stage in registers
+        double v[NVB], S[2 * NVB], Lm[2 * NVB];
+    };
+    static LB_HD void load_rows(const L& l, const double* s, int k, StageRows& r) {
+        const double* r1 = s + l.r1(k);
 #pragma unroll
-        for (int j = 0; j < NVB; ++j) {
-            if (!((rows >> (2 * j)) & 3u)) continue;
-            const double v = s[l.i_v(j, k)];
+        for (int j = 0; j < NVB; ++j) r.v[j] = r1[j];
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
-                const int r = 2 * j + side;
-                s[l.i_sb(r, k)] = slack > 1.0 ? slack : 1.0;
-                s[l.i_lb(r, k)] = 1.0;
-            }
+        for (int q = 0; q < 2 * NVB; ++q) {
+            r.S[q] = r1[L::F_S + q];
+            r.Lm[q] = r1[L::F_LB + q];
         }
     }
     static LB_HD double gen_slack(const P& p, const L& l, const double* s, const double* G,
@@ -233,61 +233,115 @@ struct Core {
     }
 
     // ============================================================================================
-    // stage: predictor assembly.  Writes Qd (barrier diagonal), g (cost gradient + G'lambda) and
-    // q (Newton rhs on the bounded variables) of stage k; accumulates reductions.
+    // stage: predictor assembly from the register copy r of stage k.  Writes Qd (barrier diagonal),
+    // g (cost gradient + G'lambda), q (Newton rhs on the bounded variables) and the Farkas input
+    // (G'lambda of the box rows, g-layout, first NV fields of record R3); accumulates reductions.
     // ============================================================================================
-    static LB_HD void assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red) {
+    static LB_HD void asm_core(const P& p, const L& l, double* s, int k, unsigned rows, const StageRows& r, RedAsm& red) {
         double v[NV], g[NV];
-#pragma unroll
-        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
         const bool last = k >= p.N;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.i_u(j, k)];
+        for (int j = 0; j < NX; ++j) v[j] = r.v[j];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : r.v[NX + j];
         const double* W = p.W[stage_type(p, k)];
 #pragma unroll
         for (int a = 0; a < NV; ++a) {
-            double acc = 0.0;
+            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int b = 0; b < NV; ++b) acc += W[a * NV + b] * v[b];
-            g[a] = (last && a >= NZ) ? 0.0 : acc;
+            for (int b = 0; b < NV; ++b) {
+                if (b & 1) a1 += W[a * NV + b] * v[b];
+                else a0 += W[a * NV + b] * v[b];
+            }
+            g[a] = (last && a >= NZ) ? 0.0 : a0 + a1;
         }
         if (k == p.kT) {
 #pragma unroll
             for (int a = 0; a < NZ; ++a) g[a] += s[l.o_misc + L::M_LIN + a];
         }
-        const unsigned rows = stage_rows(p, k);
+        double* r2 = s + l.r2(k);
+        double* r3 = s + l.r3(k);
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
             double qd = 0.0, gl = 0.0, gp = 0.0;
             const int a = zidx(j);
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = 2 * j + side;
-                const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
+                const int q = 2 * j + side;
+                const bool act = (rows >> q) & 1u;
+                const double S = act ? r.S[q] : 1.0, Lm = act ? r.Lm[q] : 0.0;
                 const double sgn = side == 0 ? 1.0 : -1.0;
                 const double slack = side == 0 ? p.hi[j] - v[a] : v[a] - p.lo[j];
-                const double rp = S - slack;
+                const double rp = act ? S - slack : 0.0;
                 const double w = Lm * lb_rcp(S);
                 qd += w;
                 gl += sgn * Lm;
                 gp += sgn * (w * rp);
-                red.rp = lb_nanmax(red.rp, lb_abs(rp));
+                red.rp = lb_max(red.rp, lb_abs(rp));
                 red.sl += S * Lm;
                 red.lam = lb_max(red.lam, Lm);
                 red.hl += Lm * slack;
             }
-            s[l.i_qd(j, k)] = qd;
-            s[l.i_q(j, k)] = g[a] + gp;
+            r2[L::F_QD + j] = qd;
+            r2[L::F_Q + j] = g[a] + gp;
             g[a] += gl;
-            s[l.r3(k) + a] = gl;  // Farkas input (adjoint_sweep), g-layout
+            r3[a] = gl;
         }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) s[l.r3(k) + NX + t] = 0.0;
+        for (int t = 0; t < NT; ++t) r3[NX + t] = 0.0;
 #pragma unroll
-        for (int a = 0; a < NV; ++a) s[l.i_g(a, k)] = g[a];
+        for (int a = 0; a < NV; ++a) r2[L::F_G + a] = g[a];
+    }
+    // fresh QP: initial slacks and multipliers s = max(h - a v, 1), lambda = 1, then the assembly
+    static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red) {
+        const unsigned rows = stage_rows(p, k);
+        StageRows r;
+        double* r1 = s + l.r1(k);
+#pragma unroll
+        for (int j = 0; j < NVB; ++j) r.v[j] = r1[j];
+#pragma unroll
+        for (int j = 0; j < NVB; ++j) {
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int q = 2 * j + side;
+                const double slack = side == 0 ? p.hi[j] - r.v[j] : r.v[j] - p.lo[j];
+                r.S[q] = slack > 1.0 ? slack : 1.0;
+                r.Lm[q] = 1.0;
+                if ((rows >> q) & 1u) {
+                    r1[L::F_S + q] = r.S[q];
+                    r1[L::F_LB + q] = 1.0;
+                }
+            }
+        }
+        asm_core(p, l, s, k, rows, r, red);
+    }
+    // running QP: apply the step parked by final_stage (ds, dl in the scratch block; dx, du), then the assembly
+    static LB_HD void update_assemble_stage(const P& p, const L& l, double* s, int k, double alpha, RedAsm& red) {
+        const unsigned rows = stage_rows(p, k);
+        StageRows r;
+        load_rows(l, s, k, r);
+        double* r1 = s + l.r1(k);
+        const double* r2 = s + l.r2(k);
+        const double* r3 = s + l.r3(k);
+#pragma unroll
+        for (int q = 0; q < 2 * NVB; ++q) {
+            r.S[q] += alpha * r2[q];
+            r.Lm[q] += alpha * r2[2 * NVB + q];
+            if ((rows >> q) & 1u) {
+                r1[L::F_S + q] = r.S[q];
+                r1[L::F_LB + q] = r.Lm[q];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NVB; ++j) {
+            if (j < NX || k < p.N) {
+                r.v[j] += alpha * r3[j];
+                r1[j] = r.v[j];
+            }
+        }
+        asm_core(p, l, s, k, rows, r, red);
     }
 
     // row: predictor assembly of polytope row i.  acc = {HG (NH packed), gGl (NZ), dG (NZ)}
@@ -781,32 +835,34 @@ struct Core {
     // ============================================================================================
     static LB_HD void affine_stage(const P& p, const L& l, double* s, int k, RedStep& red) {
         const unsigned rows = stage_rows(p, k);
+        const double* r1 = s + l.r1(k);
+        double* r2 = s + l.r2(k);
+        double* r3 = s + l.r3(k);
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
-            if (j >= NX && k >= p.N) continue;
             double aj = 0.0, bj = 0.0;
-            if ((rows >> (2 * j)) & 3u) {
-                const double v = s[l.i_v(j, k)], dva = s[l.i_dv(j, k, true)];
+            const double v = r1[j], dva = r3[NVB + j];
 #pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    if (!((rows >> (2 * j + side)) & 1u)) continue;
-                    const int r = 2 * j + side;
-                    const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
-                    const double sgn = side == 0 ? 1.0 : -1.0;
-                    const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
-                    const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
-                    const double dsa = -rp - sgn * dva, dla = -Lm - w * dsa;
-                    const double rr = dsa * is;
-                    red.ratio = lb_max(red.ratio, lb_max(-rr, 1.0 + rr));
-                    red.s0 += S * Lm;
-                    red.s1 += S * dla + Lm * dsa;
-                    red.s2 += dsa * dla;
-                    aj += sgn * (w * rp - dsa * dla * is - Lm);
-                    bj += sgn * is;
-                }
+            for (int side = 0; side < 2; ++side) {
+                const int q = 2 * j + side;
+                const bool act = (rows >> q) & 1u;
+                const double S = act ? r1[L::F_S + q] : 1.0, Lm = act ? r1[L::F_LB + q] : 0.0;
+                const double sgn = side == 0 ? 1.0 : -1.0;
+                const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
+                const double rp = act ? S - slack : 0.0, is = lb_rcp(S), w = Lm * is;
+                const double dsa = act ? -rp - sgn * dva : 0.0, dla = -Lm - w * dsa;
+                const double rr = dsa * is;
+                red.ratio = lb_max(red.ratio, act ? lb_max(-rr, 1.0 + rr) : 0.0);
+                red.s0 += S * Lm;
+                red.s1 += S * dla + Lm * dsa;
+                red.s2 += dsa * dla;
+                aj += sgn * (w * rp - dsa * dla * is - Lm);
+                bj += act ? sgn * is : 0.0;
             }
-            s[l.i_q(j, k)] = s[l.i_g(zidx(j), k)] + aj;
-            s[l.i_dv(j, k, false)] = bj;
+            if (j < NX || k < p.N) {
+                r2[L::F_Q + j] = r2[L::F_G + zidx(j)] + aj;
+                r3[j] = bj;
+            }
         }
     }
     static LB_HD void corr_stage(const P& p, const L& l, double* s, int k, double sigmu) {
@@ -848,22 +904,23 @@ struct Core {
     }
 
     // ============================================================================================
-    // stage: final (corrector) row directions of stage k -> parks ds, dl in the scratch block that
-    // starts at o_qd, returns the step-length ratio.  update_stage applies the step.
+    // stage: final (corrector) row directions of stage k -> parks ds, dl in the scratch block at the
+    // start of record R2, returns the step-length ratio.  update_assemble_stage applies the step.
     // ============================================================================================
     static LB_HD double final_stage(const P& p, const L& l, double* s, int k, double sigmu) {
         const unsigned rows = stage_rows(p, k);
+        const double* r1 = s + l.r1(k);
+        double* r2 = s + l.r2(k);
+        const double* r3 = s + l.r3(k);
         double ratio = 0.0;
 #pragma unroll
         for (int j = 0; j < NVB; ++j) {
-            if (!((rows >> (2 * j)) & 3u)) continue;
-            const double v = s[l.i_v(j, k)], dva = s[l.i_dv(j, k, true)],
-                         dv = s[l.i_dv(j, k, false)];
+            const double v = r1[j], dva = r3[NVB + j], dv = r3[j];
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = 2 * j + side;
-                const double S = s[l.i_sb(r, k)], Lm = s[l.i_lb(r, k)];
+                const int q = 2 * j + side;
+                const bool act = (rows >> q) & 1u;
+                const double S = act ? r1[L::F_S + q] : 1.0, Lm = act ? r1[L::F_LB + q] : 1.0;
                 const double sgn = side == 0 ? 1.0 : -1.0;
                 const double slack = side == 0 ? p.hi[j] - v : v - p.lo[j];
                 const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
@@ -871,31 +928,12 @@ struct Core {
                 const double ds = -rp - sgn * dv;
                 const double rc = S * Lm + dsa * dla - sigmu;
                 const double dl = (-rc - Lm * ds) * is;
-                ratio = lb_max(ratio, lb_max(-ds * is, -dl * lb_rcp(Lm)));
-                s[l.i_scr_ds(2 * j + side, k)] = ds;
-                s[l.i_scr_dl(2 * j + side, k)] = dl;
+                ratio = lb_max(ratio, act ? lb_max(-ds * is, -dl * lb_rcp(Lm)) : 0.0);
+                r2[q] = act ? ds : 0.0;
+                r2[2 * NVB + q] = act ? dl : 0.0;
             }
         }
         return ratio;
-    }
-    static LB_HD void update_stage(const P& p, const L& l, double* s, int k, double alpha) {
-        const unsigned rows = stage_rows(p, k);
-#pragma unroll
-        for (int j = 0; j < NVB; ++j) {
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                if (!((rows >> (2 * j + side)) & 1u)) continue;
-                const int r = 2 * j + side;
-                s[l.i_sb(r, k)] += alpha * s[l.i_scr_ds(2 * j + side, k)];
-                s[l.i_lb(r, k)] += alpha * s[l.i_scr_dl(2 * j + side, k)];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NX; ++j) s[l.i_x(j, k)] += alpha * s[l.i_dv(j, k, false)];
-        if (k < p.N) {
-#pragma unroll
-            for (int j = 0; j < NU; ++j) s[l.i_u(j, k)] += alpha * s[l.i_dv(NX + j, k, false)];
-        }
     }
     // polytope row i, final direction (recomputed by final_gen_row and update_gen_row: no scratch)
     static LB_HD void gen_final_dir(const P& p, const L& l, const double* s, const double* G, const double* hg,

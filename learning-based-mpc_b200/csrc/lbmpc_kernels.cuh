@@ -321,40 +321,51 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         // phase E+A: step length + update (RUN) or row initialisation (FRESH); then the
         //            predictor assembly of the next iteration
         // =====================================================================================
-        if (state == SLOT_RUN) {
-            const double sigmu = m[L::M_SIGMU];
-            double ratio = 0.0;
-            for (int k = lane; k <= N; k += 32) ratio = fmax(ratio, C::final_stage(p, l, slot, k, sigmu));
-            for (int i = lane; i < p.ng; i += 32) ratio = fmax(ratio, C::final_gen_row(p, l, slot, Gs, hgs, i, sigmu));
-            ratio = warp_max(ratio);
-            double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
-            alpha = alpha > 1.0 ? 1.0 : alpha;
-            for (int i = lane; i < p.ng; i += 32) C::update_gen_row(p, l, slot, Gs, hgs, i, sigmu, alpha);
-            __syncwarp();
-            for (int k = lane; k <= N; k += 32) C::update_stage(p, l, slot, k, alpha);
-            if (lane == 0) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
-                meta[warp * 4 + 1] += 1;
-            }
-            __syncwarp();
-        } else if (state == SLOT_FRESH) {
-            for (int k = lane; k <= N; k += 32) C::init_rows_stage(p, l, slot, k);
-            for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
-            state = SLOT_RUN;
-            if (lane == 0) meta[warp * 4 + 0] = SLOT_RUN;
-            __syncwarp();
-        }
-        if (state == SLOT_RUN) {
+#ifdef LBMPC_SUBPROF
+        long long ts_prev = clock64();
+#define LB_SUB(idx) if (io.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long tn = clock64(); io.prof[idx] += (unsigned long long)(tn - ts_prev); ts_prev = tn; }
+#else
+#define LB_SUB(idx)
+#endif
+        if (state == SLOT_RUN || state == SLOT_FRESH) {
             RedAsm ra{0.0, 0.0, 0.0, 0.0};
-            for (int k = lane; k <= N; k += 32) C::assemble_stage(p, l, slot, k, ra);
+            if (state == SLOT_RUN) {
+                const double sigmu = m[L::M_SIGMU];
+                double ratio = 0.0;
+                for (int k = lane; k <= N; k += 32) ratio = fmax(ratio, C::final_stage(p, l, slot, k, sigmu));
+                LB_SUB(8)
+                for (int i = lane; i < p.ng; i += 32) ratio = fmax(ratio, C::final_gen_row(p, l, slot, Gs, hgs, i, sigmu));
+                ratio = warp_max(ratio);
+                LB_SUB(9)
+                double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
+                alpha = alpha > 1.0 ? 1.0 : alpha;
+                for (int i = lane; i < p.ng; i += 32) C::update_gen_row(p, l, slot, Gs, hgs, i, sigmu, alpha);
+                __syncwarp();  // the polytope rows read x_kg, theta of the old iterate
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
+                    meta[warp * 4 + 1] += 1;
+                }
+                __syncwarp();
+                LB_SUB(10)
+                for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra);
+                LB_SUB(11)
+            } else {
+                for (int k = lane; k <= N; k += 32) C::init_assemble_stage(p, l, slot, k, ra);
+                for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
+                state = SLOT_RUN;
+                if (lane == 0) meta[warp * 4 + 0] = SLOT_RUN;
+            }
+            __syncwarp();  // x_kg of the new iterate is read by the polytope rows
             double acc[NACC];
 #pragma unroll
             for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
             for (int i = lane; i < p.ng; i += 32) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
+            LB_SUB(12)
 #pragma unroll
             for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
-            const double rp = warp_max_nan(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
+            const double rp = warp_max(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
+            LB_SUB(13)
             if (lane == 0) {
 #pragma unroll
                 for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];

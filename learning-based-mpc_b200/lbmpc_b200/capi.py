@@ -193,11 +193,11 @@ class Solver:
     def phase_cycles(self, enable=True):
         """Read and clear the per-phase SM-cycle counters of CTA 0 (lbmpc_debug_phase_cycles), then switch the
         instrumentation on/off for the following solve calls."""
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(16, np.uint64)
         self._check(self.lib.lbmpc_debug_phase_cycles(self.h, int(enable), _ptr(out)), "lbmpc_debug_phase_cycles")
         names = ("C_affine_step", "D_corrector_sweeps", "EA_update_assemble", "B_factor", "B2_affine_sweeps", "iterations",
-                 "B_warp0_factor", "B_warp4_adjoint")
-        return dict(zip(names, (int(v) for v in out[:8])))
+                 "B_warp0_factor", "B_warp4_adjoint", "sub8", "sub9", "sub10", "sub11", "sub12", "sub13")
+        return dict(zip(names, (int(v) for v in out[:14])))
 
     def _check(self, rc, what):
         if rc != 0:

@@ -43,13 +43,16 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
             for (int j = 0; j < NX; ++j) cconst += dx_ref[i] * p.Tm[i * NX + j] * dx_ref[j];
     m[L::M_CCONST] = cconst;
     C::rollout(p, l, s);
-    for (int k = 0; k <= N; ++k) C::init_rows_stage(p, l, s, k);
     for (int i = 0; i < p.ng; ++i) C::init_rows_gen(p, l, s, G, hg, i);
+    double alpha = 0.0;
     int it = 0, st = 1;
     for (it = 0; it < p.max_iter; ++it) {
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
         RedAsm ra{0, 0, 0, 0};
-        for (int k = 0; k <= N; ++k) C::assemble_stage(p, l, s, k, ra);
+        for (int k = 0; k <= N; ++k) {
+            if (it == 0) C::init_assemble_stage(p, l, s, k, ra);
+            else C::update_assemble_stage(p, l, s, k, alpha, ra);
+        }
         double acc[NH + 2 * NZ];
         std::memset(acc, 0, sizeof acc);
         for (int i = 0; i < p.ng; ++i) C::assemble_gen_row(p, l, s, G, hg, i, acc, ra);
@@ -106,12 +109,14 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         double ratio = 0.0;
         for (int k = 0; k <= N; ++k) ratio = lb_max(ratio, C::final_stage(p, l, s, k, sigmu));
         for (int i = 0; i < p.ng; ++i) ratio = lb_max(ratio, C::final_gen_row(p, l, s, G, hg, i, sigmu));
-        double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
+        alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
         if (alpha > 1.0) alpha = 1.0;
         for (int i = 0; i < p.ng; ++i) C::update_gen_row(p, l, s, G, hg, i, sigmu, alpha);
-        for (int k = 0; k <= N; ++k) C::update_stage(p, l, s, k, alpha);
         for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
+        // the box rows / x / u step is applied at the top of the next pass (update_assemble_stage)
     }
+    if (it == p.max_iter)  // ran out of iterations: apply the last step so that the outputs are the last iterate
+        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra); }
     double J = m[L::M_CCONST];
     for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k);
     for (int k = 0; k < N; ++k)
