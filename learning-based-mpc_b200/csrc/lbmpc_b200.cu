@@ -92,7 +92,7 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io, cudaStream_t s
     const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
     cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    ipm_kernel<NX, NT, NU><<<grid, kThreads, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
+    ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
     h->launches += 1;
     return cudaGetLastError();
 }

@@ -1017,35 +1017,45 @@ struct Core {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Cooperative Riccati factorisation for NT = NU = 1 (the Moore-Greitzer shape): 16 lanes per QP.
+// Cooperative Riccati factorisation for NT = NU = 1 (the Moore-Greitzer shape): ONE WARP per QP,
+// one dot product per lane per stage, with the adjoint (dual-residual) recursion riding on spare
+// lanes of the same instruction stream.
 //
-// Lane h < NH owns one unique entry (a,b), a <= b, of the symmetric NZ x NZ cost-to-go matrix, kept
-// SCALED by the pivot of the stage it came from:  Pt = rho P, ir = 1/rho.  One stage is
-//     F    = Abar_e' Pt Abar_e,  Abar_e = [Abar Bbar]        (every entry a fixed linear form in the
-//                                                             unique entries of Pt: dot products
-//                                                             with per-lane coefficient vectors)
-//     Rt   = Wuu + Qd_u + F_uu ir ,  L = Wuz + F_uz ir
-//     Pt'  = Rt (Wzz + Qd + [HG] + F_zz ir) - L'L ,  rho' = Rt
+// A single warp issues at most one instruction every ~2 cycles on sm_100a (measured,
+// tools/microbench), so the stage time is  2.2 x (instructions per stage) + exposed latencies: the
+// design minimises instructions on the one stream and keeps latencies off the dependency chain.
+//
+// Lane roles (NX = 4: NH = 15 unique entries of the symmetric NZ x NZ cost-to-go matrix):
+//   0..NH-1        entry (a,b), a <= b, kept SCALED by the pivot of the stage it came from:
+//                  Pt = rho P, ir = 1/rho
+//   NH..NH+NZ-1    F_uz[c] = (Abar' Pt Bbar)[c]            NH+NZ   F_uu = Bbar' Pt Bbar
+//   NH+NZ+1 ..+NZ  adjoint pi[a]                            +NZ+1   r_d lane: g_u + B'pi
+// One stage:  F = Abar_e' Pt Abar_e with Abar_e = [Abar Bbar]: every entry is a fixed linear form in
+// the unique entries of Pt, i.e. a dot product with a per-lane coefficient vector over NLD values
+// read from a lane-type dependent base of the exchange buffer; then
+//     Rt  = Wuu + Qd_u + F_uu ir ,  L = Wuz + F_uz ir
+//     Pt' = Rt (Wzz + Qd + [HG] + F_zz ir) - L'L ,  rho' = Rt
 // which is P' = Wzz + Qd + Abar'P Abar - L'L/Rt multiplied through by Rt.  The reciprocal of the
 // pivot is needed only one stage later (and for the stored factors RL = L/Rt, Ri = 1/Rt): its
 // hardware seed is issued as soon as Rt exists and its Newton refinement is interleaved with the
 // next stage's dot products, so it never sits on the stage-to-stage dependency chain.
+// The adjoint lanes compute pi' = g + Abar'pi and |g_u + B'pi| with the SAME dot instruction
+// (coefficients = columns of Abar / B, operands = the published pi).
 //
-// Exchange 1 (shared memory, xch): every lane publishes its entry; entries are ordered
-// [xx block | (a,theta) | (theta,theta) | zero pad] so that each lane reads the 10 values its forms
-// need from a lane-type dependent base (xx lanes: base 0; (a,theta) lanes and lane 15: base NXX;
-// (theta,theta): base NH-1).  Lanes 0..NX-1 also produce F_uz[a], lane NX produces F_uu, lane 15
-// produces F_uz[theta].  Exchange 2 (warp shuffles in the kernel, `pub` in the emulation): each
-// entry lane fetches F_uz[a], F_uz[b], F_uu.
+// Exchange 1 (shared memory, xch): entry lanes publish Pt, adjoint lanes publish pi; layout
+// [xx block | (a,theta) | (theta,theta) | zero pad | pi | zero pad].  Exchange 2 (warp shuffles in
+// the kernel, `pub` in the emulation): entry lanes fetch F_uz[a], F_uz[b], F_uu.
 // The lane-phases st1/st2/st3 are separated by __syncwarp()/shuffles in the kernel; tests/emul
-// runs them as loops over the 16 lanes.
+// runs them as loops over the 32 lanes.
 // ------------------------------------------------------------------------------------------------
 template <int NX>
 struct Coop {
     static constexpr int NT = 1, NU = 1, NZ = NX + 1, NV = NZ + 1, NH = NZ * (NZ + 1) / 2, NXX = NX * (NX + 1) / 2;
-    static constexpr int kLanes = 16, kXch = 24;
-    static constexpr int NLD = (NXX + 1) & ~1;  // values each lane reads (even: 16-byte loads)
-    static_assert(NH <= 15 && NX >= 2 && NX + 1 <= NXX && NH - 1 + NLD <= kXch, "shape does not fit the 16-lane mapping");
+    static constexpr int NLD = (NXX + 1) & ~1;            // values each lane reads (even: 16-byte loads)
+    static constexpr int kFz = NH, kFu = NH + NZ, kPi = NH + NZ + 1, kRd = kPi + NZ;  // first lane of each role
+    static constexpr int kXpi = (NH - 1 + NLD + 1) & ~1;  // pi block of the exchange buffer
+    static constexpr int kXch = (kXpi + NLD + 1) & ~1;
+    static_assert(kRd < 32 && NX >= 2 && NZ <= NLD, "shape does not fit the one-warp mapping");
     using P = Params<NX, 1, 1>;
     using L = Layout<NX, 1, 1>;
     using C = Core<NX, 1, 1>;
@@ -1055,13 +1065,12 @@ struct Coop {
         return b < NX ? a * NX - a * (a - 1) / 2 + (b - a) : (a < NX ? NXX + a : NH - 1);
     }
     struct Lane {
-        int a, b, sa, sb, base;  // entry owned (h < NH), source lanes of F_uz[a], F_uz[b], read base in xch
-        bool isP, diag, dgx;     // dgx: diagonal entry of a bounded state (gets the barrier term)
-        double c1[NLD];          // F_zz[a][b] (h < NH) or F_uz[theta] (h == 15) as a form in xch[base..]
-        double c2[NLD];          // F_uz[h] (h < NX) or F_uu (h == NX) as a form in the xx entries
+        int a, b, base, in_off;  // entry owned / adjoint component a; read base in xch; stage-input offset in R2
+        bool isP, isPi, isRd, has_in;
+        double c1[NLD];          // the lane's linear form over xch[base..base+NLD)
         double wzz, wa, wb, wuu;
-        double pt, ir, d1, pub;
-        double qdu, qda, hgv;    // stage inputs fetched ahead (Qd_u, Qd_a on the diagonal, HG entry at kg)
+        double val, ir, d1, pub; // val: Pt entry / pi component / running |r_d|
+        double qdu, in, hgv;     // stage inputs fetched ahead: Qd_u; Qd_a (diagonal x entries) or g[a]; HG / GGL at kg
         double rt, y0, la;       // pivot, reciprocal seed and L_a of the previous stage (deferred refinement)
         bool ok, pend;           // pend: a previous stage's factors are waiting to be stored
     };
@@ -1082,6 +1091,8 @@ struct Coop {
     }
     static LB_HD void lane_init(const P& p, int h, Lane& ln) {
         ln.isP = h < NH;
+        ln.isPi = h >= kPi && h < kPi + NZ;
+        ln.isRd = h == kRd;
         ln.a = 0;
         ln.b = 0;
 #pragma unroll
@@ -1092,48 +1103,47 @@ struct Coop {
                     ln.a = a;
                     ln.b = b;
                 }
-        ln.diag = ln.isP && ln.a == ln.b;
-        ln.dgx = ln.diag && ln.a < NX;
-        ln.sa = ln.a < NX ? ln.a : 15;
-        ln.sb = ln.b < NX ? ln.b : 15;
-        const bool xx = h < NXX, xt = (h >= NXX && h < NH - 1), tt = (h == NH - 1), ft = (h == 15);
-        ln.base = xx ? 0 : (tt ? NH - 1 : NXX);
+        if (ln.isPi) ln.a = ln.b = h - kPi;
+        const bool xx = h < NXX, xt = (h >= NXX && h < NH - 1), tt = (h == NH - 1);
+        const int fz = h - kFz;  // F_uz component for lanes kFz..kFz+NZ-1
+        const bool fzx = (fz >= 0 && fz < NX), fzt = (fz == NX), fu = (h == kFu);
+        ln.base = (xt || fzt) ? NXX : (tt ? NH - 1 : ((ln.isPi || ln.isRd) ? kXpi : 0));
+        const bool dgx = ln.isP && ln.a == ln.b && ln.a < NX;
+        ln.has_in = dgx || ln.isPi || ln.isRd;
+        ln.in_off = dgx ? L::F_QD + ln.a : (ln.isPi ? L::F_G + ln.a : L::F_G + NZ);
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            ln.c1[j] = 0.0;
-            ln.c2[j] = 0.0;
-        }
+        for (int j = 0; j < NLD; ++j) ln.c1[j] = 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c)
 #pragma unroll
             for (int d = c; d < NX; ++d) {
-                const int e = ent(c, d);
+                double v = 0.0;
                 if (xx) {  // F_zz[a][b], a,b < NX
-                    double v = p.A[c * NX + ln.a] * p.A[d * NX + ln.b];
+                    v = p.A[c * NX + ln.a] * p.A[d * NX + ln.b];
                     if (c != d) v += p.A[d * NX + ln.a] * p.A[c * NX + ln.b];
-                    ln.c1[e] = v;
+                } else if (fzx) {  // F_uz[fz]
+                    v = p.A[c * NX + fz] * p.B[d];
+                    if (c != d) v += p.A[d * NX + fz] * p.B[c];
+                } else if (fu) {  // F_uu
+                    v = p.B[c] * p.B[d] * (c != d ? 2.0 : 1.0);
                 }
-                double w = 0.0;
-                if (h < NX) {  // F_uz[h]
-                    w = p.A[c * NX + h] * p.B[d];
-                    if (c != d) w += p.A[d * NX + h] * p.B[c];
-                } else if (h == NX) {  // F_uu
-                    w = p.B[c] * p.B[d] * (c != d ? 2.0 : 1.0);
-                }
-                ln.c2[e] = w;
+                if (xx || fzx || fu) ln.c1[ent(c, d)] = v;
             }
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            if (xt) ln.c1[c] = p.A[c * NX + ln.a];  // F_zz[a][theta] = sum_c A[c][a] Pt[c][theta]
-            if (ft) ln.c1[c] = p.B[c];              // F_uz[theta]    = sum_c B[c] Pt[c][theta]
+            if (xt) ln.c1[c] = p.A[c * NX + ln.a];                      // F_zz[a][theta] = sum_c A[c][a] Pt[c][theta]
+            if (fzt) ln.c1[c] = p.B[c];                                 // F_uz[theta]    = sum_c B[c] Pt[c][theta]
+            if (ln.isPi && ln.a < NX) ln.c1[c] = p.A[c * NX + ln.a];    // (Abar'pi)[a]
+            if (ln.isRd) ln.c1[c] = p.B[c];                             // B'pi
         }
-        if (tt) ln.c1[0] = 1.0;                     // F_zz[theta][theta] = Pt[theta][theta]
+        if (tt) ln.c1[0] = 1.0;                                         // F_zz[theta][theta] = Pt[theta][theta]
+        if (ln.isPi && ln.a == NX) ln.c1[NX] = 1.0;                     // (Abar'pi)[theta] = pi[theta]
         ln.ok = true;
         ln.pend = false;
-        ln.pt = 0.0;
+        ln.val = 0.0;
         ln.ir = 1.0;
         ln.d1 = ln.pub = 0.0;
-        ln.qdu = ln.qda = ln.hgv = 0.0;
+        ln.qdu = ln.in = ln.hgv = 0.0;
         ln.rt = ln.y0 = 1.0;
         ln.la = 0.0;
         ln.wzz = ln.wa = ln.wb = ln.wuu = 0.0;
@@ -1147,32 +1157,39 @@ struct Coop {
     }
     // stage inputs of stage k (no dependence on the recursion: fetched before the exchange)
     static LB_HD void fetch(const P& p, const L& l, const double* s, int k, Lane& ln) {
-        ln.qdu = s[l.i_qd(NX, k)];
-        ln.qda = ln.dgx ? s[l.i_qd(ln.a, k)] : 0.0;
-        ln.hgv = (k == p.kg) ? s[l.o_misc + L::M_HG + C::sym(ln.a, ln.b)] : 0.0;
+        const double* r2 = s + l.r2(k);
+        ln.qdu = r2[L::F_QD + NX];
+        ln.in = ln.has_in ? r2[ln.in_off] : 0.0;
+        double hv = 0.0;
+        if (k == p.kg) {
+            if (ln.isP) hv = s[l.o_misc + L::M_HG + C::sym(ln.a, ln.b)];
+            else if (ln.isPi) hv = s[l.o_misc + L::M_GGL + ln.a];
+        }
+        ln.hgv = hv;
     }
-    // terminal stage: Pt = Wzz + Qd (+HG), rho = 1
+    // terminal stage: Pt = Wzz + Qd (+HG), rho = 1 ; pi = g (+GGL)
     static LB_HD void terminal(const P& p, const L& l, const double* s, Lane& ln) {
         const int N = p.N;
         load_type(p, C::stage_type(p, N), ln);
         fetch(p, l, s, N, ln);
-        ln.pt = ln.isP ? ln.wzz + ln.qda + ln.hgv : 0.0;
+        ln.val = ln.isP ? ln.wzz + ln.in + ln.hgv : (ln.isPi ? ln.in + ln.hgv : 0.0);
         ln.ir = 1.0;
         ln.rt = ln.y0 = 1.0;
         ln.ok = true;
         ln.pend = false;
     }
-    // zero the pad of the exchange buffer once (entries beyond NH are read with zero coefficients)
+    // zero the pads of the exchange buffer once (read with zero coefficients)
     static LB_HD void xch_init(int h, double* xch) {
-        for (int j = h; j < kXch; j += kLanes) xch[j] = 0.0;
+        for (int j = h; j < kXch; j += 32) xch[j] = 0.0;
     }
     static LB_HD void st1(const P& p, const L& l, const double* s, int k, int h, Lane& ln, double* xch) {
-        if (h < NH) xch[h] = ln.pt;
+        if (ln.isP) xch[h] = ln.val;
+        if (ln.isPi) xch[kXpi + ln.a] = ln.val;
         fetch(p, l, s, k, ln);
     }
-    // dot products + deferred refinement / store of the previous stage's reciprocal pivot
-    //   kprev = k + 1 (stage whose factors are pending), act = the half-warp owns a running QP
-    static LB_HD void st2(const L& l, double* s, int kprev, int h, Lane& ln, const double* xch, bool act) {
+    // dot product + deferred refinement / store of the previous stage's reciprocal pivot
+    //   kprev = k + 1 (stage whose factors are pending)
+    static LB_HD void st2(const L& l, double* s, int kprev, int h, Lane& ln, const double* xch) {
         double v[NLD];
 #ifdef __CUDA_ARCH__
         const double2* src = reinterpret_cast<const double2*>(xch + ln.base);
@@ -1186,48 +1203,48 @@ struct Coop {
         for (int j = 0; j < NLD; ++j) v[j] = xch[ln.base + j];
 #endif
         const double irn = rcp_refine(ln.rt, ln.y0);  // 1/rho of the matrix being read
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int j = 0; j < NLD; ++j) {
-            if (j & 1) {
-                a1 += ln.c1[j] * v[j];
-                b1 += ln.c2[j] * v[j];
-            } else {
-                a0 += ln.c1[j] * v[j];
-                b0 += ln.c2[j] * v[j];
-            }
+            if (j & 1) a1 += ln.c1[j] * v[j];
+            else a0 += ln.c1[j] * v[j];
         }
         ln.d1 = a0 + a1;
-        ln.pub = (h == 15) ? ln.d1 : (b0 + b1);
+        ln.pub = ln.d1;
         ln.ir = irn;
-        if (ln.pend && act) {
-            if (ln.diag) s[l.i_L(ln.a, kprev)] = ln.la * irn;  // RL[a] of stage kprev
+        if (ln.pend) {
+            if (ln.isP && ln.a == ln.b) s[l.i_L(ln.a, kprev)] = ln.la * irn;  // RL[a] of stage kprev
             if (h == 0) s[l.i_Ri(0, kprev)] = irn;
         }
     }
+    // fa, fb, fuu: F_uz[a], F_uz[b], F_uu (lanes kFz + a, kFz + b, kFu)
     static LB_HD void st3(Lane& ln, double fa, double fb, double fuu) {
         const double ir = ln.ir;
         const double Rt = (ln.wuu + ln.qdu) + fuu * ir;
         const double La = ln.wa + fa * ir, Lb = ln.wb + fb * ir;
-        const double hz = (ln.wzz + ln.qda + ln.hgv) + ln.d1 * ir;
-        ln.pt = Rt * hz - La * Lb;
+        const double hz = (ln.wzz + ln.in + ln.hgv) + ln.d1 * ir;
+        const double pnew = Rt * hz - La * Lb;         // entry lanes
+        const double anew = (ln.in + ln.hgv) + ln.d1;  // adjoint lanes: pi' = g + Abar'pi (+GGL at kg)
+        const double av = lb_abs(ln.in + ln.d1);       // r_d lane: |g_u + B'pi|
+        ln.val = ln.isP ? pnew : (ln.isPi ? anew : (ln.isRd ? lb_nanmax(ln.val, av) : 0.0));
         ln.ok = ln.ok && (Rt > 0.0);
         ln.rt = Rt;
         ln.y0 = rcp_seed(Rt);
         ln.la = La;
         ln.pend = true;
     }
-    // after stage 0: store its factors, inverse of the theta block of P_0 (lane of the (theta,theta) entry)
-    static LB_HD void finish(const L& l, double* s, int h, Lane& ln, bool act) {
+    // after stage 0: store its factors and the inverse of the theta block of P_0; the caller combines the r_d
+    // pieces (lane kRd: running max over the stages; lane kPi + NX: |pi_theta| at stage 0)
+    static LB_HD void finish(const L& l, double* s, int h, Lane& ln) {
         const double irn = rcp_refine(ln.rt, ln.y0);
-        if (ln.pend && act) {
-            if (ln.diag) s[l.i_L(ln.a, 0)] = ln.la * irn;
+        if (ln.pend) {
+            if (ln.isP && ln.a == ln.b) s[l.i_L(ln.a, 0)] = ln.la * irn;
             if (h == 0) s[l.i_Ri(0, 0)] = irn;
         }
         if (h == NH - 1) {
-            const double ptt = ln.pt * irn;
+            const double ptt = ln.val * irn;
             ln.ok = ln.ok && (ptt > 0.0);
-            if (act) s[l.o_misc + L::M_PTT] = 1.0 / ptt;
+            s[l.o_misc + L::M_PTT] = 1.0 / ptt;
         }
         if (!ln.isP) ln.ok = true;
     }

@@ -101,13 +101,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------
 // the solver
 // ---------------------------------------------------------------------------------------------
-constexpr int kThreads = 32 * kMaxSlots;  // always 8 warps: warps without a slot still run the helper sweeps
-
 // shared-memory carve-up helper, identical on host and device
 template <int NX, int NT, int NU>
 struct SmemPlan {
     using L = Layout<NX, NT, NU>;
-    static constexpr int kXchPerSlot = 24;  // Coop::kXch + Coop::kXf doubles per QP
+    static constexpr int kXchPerSlot = 40;  // >= Coop::kXch doubles per QP (even)
     int slots, stride, xch_off, g_off, hg_off, meta_off;  // offsets in doubles
     size_t bytes;
     __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
@@ -117,35 +115,37 @@ struct SmemPlan {
         int o = slots * stride;
         o = (o + 1) & ~1;  // 16-byte alignment
         xch_off = o;
-        o += kMaxSlots * kXchPerSlot;
+        o += slots * kXchPerSlot;
         g_off = o;         // bulk copy destination (16-byte aligned: kXchPerSlot is even)
         if (stage_g) o += (NX + NT) * ngp;
         hg_off = o;
         if (stage_g) o += ngp;
         meta_off = o;
-        o += 2 + kMaxSlots * 4;  // mbarrier (8 B) + pad, then per-slot {state, iters, status, -} ints + qp ids
+        o += 2;  // mbarrier (8 B) + pad
         bytes = (size_t)o * sizeof(double);
     }
 };
 
+// One warp per resident QP ("slot"), `slots` warps per CTA, no CTA-level synchronisation inside the
+// solve: a warp fetches a QP from the global work queue, iterates it to its verdict with every phase
+// mapped onto its 32 lanes, writes the result and fetches the next one.  The phases of different
+// warps interleave freely on the SM sub-partitions (a single warp can issue only every other cycle,
+// so two resident warps per scheduler is what saturates issue).
 template <int NX, int NT, int NU>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(32 * kMaxSlots, 1)
 ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const double* __restrict__ Gglob,
            const double* __restrict__ hgglob, const int slots, const int stage_g) {
     using C = Core<NX, NT, NU>;
     using L = Layout<NX, NT, NU>;
     constexpr int NZ = NX + NT, NH = L::NH, NACC = NH + 2 * NZ;
-    constexpr bool kCoop = (NT == 1 && NU == 1 && NX >= 2 && NX <= 4);  // 16-lane Riccati factorisation
+    constexpr bool kCoop = (NT == 1 && NU == 1 && NX >= 2 && NX <= 4);  // one-warp Riccati factorisation
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const L l(p.N, p.ngp);
     const SmemPlan<NX, NT, NU> plan(p.N, p.ngp, slots, stage_g != 0);
-    const bool has_slot = warp < slots;
-    double* const slot = smem + (has_slot ? warp : 0) * l.stride;
+    double* const slot = smem + warp * l.stride;
     double* const m = slot + l.o_misc;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + plan.meta_off);
-    int* const meta = reinterpret_cast<int*>(smem + plan.meta_off + 2);       // [slot][4]
-    long long* const qpid = reinterpret_cast<long long*>(meta + kMaxSlots * 4);  // [slot]
     const double* Gs = Gglob;
     const double* hgs = hgglob;
     const int N = p.N;
@@ -163,24 +163,18 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         Gs = smem + plan.g_off;
         hgs = smem + plan.hg_off;
     }
-    if (lane == 0 && warp < kMaxSlots) meta[warp * 4 + 0] = SLOT_EMPTY;
-
-    // ---- cooperative factorisation: per-lane coefficient vectors (registers), exchange buffers ----
+    // ---- cooperative factorisation: per-lane coefficient vector (registers), exchange buffer ----
     using CP = Coop<kCoop ? NX : 2>;
     typename CP::Lane ln;
-    const int half = lane >> 4, hl = lane & 15;
-    const int fslot = warp * 2 + half;  // slot factored by this half-warp (warps 0..3)
-    double* const xch = smem + plan.xch_off + (fslot & (kMaxSlots - 1)) * SmemPlan<NX, NT, NU>::kXchPerSlot;
+    double* const xch = smem + plan.xch_off + warp * SmemPlan<NX, NT, NU>::kXchPerSlot;
     if constexpr (kCoop) {
-        if (warp < kMaxSlots / 2) {
-            CP::lane_init(p, hl, ln);
-            CP::xch_init(hl, xch);
-        }
+        CP::lane_init(p, lane, ln);
+        CP::xch_init(lane, xch);
     }
     if (stage_g) mbar_wait(bar, 0);
     __syncthreads();
 
-    // optional phase timing (diagnostic): thread 0 of CTA 0 accumulates clock64 deltas per phase
+    // optional phase timing (diagnostic): lane 0 of warp 0 of CTA 0 accumulates clock64 deltas per phase
     const bool prof_on = io.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_prev = prof_on ? clock64() : 0;
 #define LB_PROF(idx)                                           \
@@ -190,284 +184,236 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         t_prev = t_now;                                        \
     }
 
-    int state = SLOT_EMPTY;  // warp-uniform copy of meta[warp].state
     for (;;) {
-        // =====================================================================================
-        // phase C: RUN slots: affine step length, sigma, corrector rhs.  DONE slots: write results.
-        //          Empty slots: fetch the next QP and load its inputs.
-        // =====================================================================================
-        state = has_slot ? meta[warp * 4 + 0] : SLOT_EMPTY;
-        if (state == SLOT_RUN) {
-            RedStep rs{0.0, 0.0, 0.0, 0.0};
-            for (int k = lane; k <= N; k += 32) C::affine_stage(p, l, slot, k, rs);
-            double acc[2 * NZ];
+        // ---- fetch the next QP and load its inputs ----
+        long long q = -1;
+        if (lane == 0) {
+            const unsigned long long t = atomicAdd(io.queue, 1ULL);
+            q = t < (unsigned long long)io.batch ? (long long)t : -1;
+        }
+        q = __shfl_sync(kFull, q, 0);
+        if (q < 0) break;
+        if (lane < NX) slot[l.i_x(lane, 0)] = io.dx0[q * NX + lane];
+        for (int k = lane; k < N; k += 32) {
 #pragma unroll
-            for (int a = 0; a < 2 * NZ; ++a) acc[a] = 0.0;
-            for (int i = lane; i < p.ng; i += 32) C::affine_gen_row(p, l, slot, Gs, hgs, i, acc, rs);
-            const double ratio = warp_max(rs.ratio);
-            const double s0 = warp_sum(rs.s0), s1 = warp_sum(rs.s1), s2 = warp_sum(rs.s2);
+            for (int i = 0; i < NU; ++i) slot[l.i_u(i, k)] = io.warm ? io.warm[q * (NU * N + NT) + k * NU + i] : 0.0;
 #pragma unroll
-            for (int a = 0; a < 2 * NZ; ++a) acc[a] = warp_sum(acc[a]);
-            const double aaff = ratio > 1.0 ? 1.0 / ratio : 1.0;
-            const double mu = m[L::M_MU];
-            const double mu_aff = (s0 + aaff * s1 + aaff * aaff * s2) * p.inv_m;
-            const double sr = mu_aff / mu;
-            const double sigmu = sr * sr * sr * mu;
-            for (int k = lane; k <= N; k += 32) C::corr_stage(p, l, slot, k, sigmu);
-            __syncwarp();
-            if (lane == 0) {
-                m[L::M_SIGMU] = sigmu;
+            for (int j = 0; j < NX; ++j) slot[l.i_x(j, k + 1)] = io.d_off ? io.d_off[(q * N + k) * NX + j] : 0.0;
+        }
+        if (lane == 0) {
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = acc[a] + sigmu * acc[NZ + a];
+            for (int t = 0; t < NT; ++t) m[L::M_TH + t] = io.warm ? io.warm[q * (NU * N + NT) + N * NU + t] : 0.0;
+            double cconst = 0.0;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) {
+                double v = 0.0;
+                if (io.dx_ref) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v += p.Lref[a * NX + j] * io.dx_ref[q * NX + j];
+                }
+                m[L::M_LIN + a] = v;
             }
-        } else if (has_slot) {
-            if (state == SLOT_DONE) {
-                const long long q = qpid[warp];
-                double J = 0.0;
-                for (int k = lane; k <= N; k += 32) J += C::objective_stage(p, l, slot, k);
-                J = warp_sum(J);
-                for (int k = lane; k < N; k += 32) {
+            if (io.dx_ref) {
 #pragma unroll
-                    for (int i = 0; i < NU; ++i) {
-                        double v = slot[l.i_u(i, k)];
+                for (int i = 0; i < NX; ++i)
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * slot[l.i_x(j, k)];
-                        io.uc[(q * N + k) * NU + i] = v;
-                    }
+                    for (int j = 0; j < NX; ++j) cconst += io.dx_ref[q * NX + i] * p.Tm[i * NX + j] * io.dx_ref[q * NX + j];
+            }
+            m[L::M_CCONST] = cconst;
+        }
+        __syncwarp();
+        if (lane == 0) C::rollout(p, l, slot);
+        __syncwarp();
+
+        int iters = 0, status = 1;  // LBMPC_ST_MAXITER unless a verdict is reached
+        double alpha = 0.0;
+        LB_PROF(0)
+        for (;;) {
+            // =================================================================================
+            // phase E+A: apply the step of the previous iteration (or initialise the rows of a fresh
+            //            QP) fused with the predictor assembly of this iteration
+            // =================================================================================
+            {
+                RedAsm ra{0.0, 0.0, 0.0, 0.0};
+                if (iters > 0) {
+                    for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra);
+                } else {
+                    for (int k = lane; k <= N; k += 32) C::init_assemble_stage(p, l, slot, k, ra);
+                    for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
                 }
-                if (io.xtraj) {
-                    for (int k = lane; k <= N; k += 32)
+                __syncwarp();  // x_kg of the new iterate is read by the polytope rows
+                double acc[NACC];
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = slot[l.i_x(j, k)];
-                }
+                for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+                for (int i = lane; i < p.ng; i += 32) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
+                const double rp = warp_max(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
                 if (lane == 0) {
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) io.theta[q * NT + t] = m[L::M_TH + t];
-                    io.obj[q] = J + m[L::M_CCONST];
-                    io.iters[q] = meta[warp * 4 + 1];
-                    io.status[q] = meta[warp * 4 + 2];
+                    for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) {
+                        m[L::M_GGL + a] = acc[NH + a];
+                        m[L::M_DG + a] = acc[NH + NZ + a];
+                    }
+                    m[L::M_RP] = rp;
+                    m[L::M_MU] = sl * p.inv_m;
+                    m[L::M_LAM] = lam;
+                    m[L::M_HLAM] = hl;
                 }
                 __syncwarp();
             }
-            // fetch the next QP
-            long long q = -1;
-            if (lane == 0) {
-                const unsigned long long t = atomicAdd(io.queue, 1ULL);
-                q = t < (unsigned long long)io.batch ? (long long)t : -1;
-            }
-            q = __shfl_sync(kFull, q, 0);
-            if (q >= 0) {
-                if (lane < NX) slot[l.i_x(lane, 0)] = io.dx0[q * NX + lane];
-                for (int k = lane; k < N; k += 32) {
-#pragma unroll
-                    for (int i = 0; i < NU; ++i)
-                        slot[l.i_u(i, k)] = io.warm ? io.warm[q * (NU * N + NT) + k * NU + i] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < NX; ++j)
-                        slot[l.i_x(j, k + 1)] = io.d_off ? io.d_off[(q * N + k) * NX + j] : 0.0;
+            LB_PROF(1)
+            if (iters >= p.max_iter) break;
+
+            // =================================================================================
+            // phase B: Riccati factorisation + dual residual (one warp, one dot product per lane and
+            //          stage); Farkas recursion when the multipliers are large
+            // =================================================================================
+            const bool cert = m[L::M_LAM] >= p.inf_trigger;
+            if constexpr (kCoop) {
+                CP::terminal(p, l, slot, ln);
+                int type = C::stage_type(p, N), kseg = p.tseg[type];
+                for (int k = N - 1; k >= 0; --k) {
+                    if (k < kseg) {  // crossed into the previous cost segment
+                        type = C::stage_type(p, k);
+                        kseg = p.tseg[type];
+                        CP::load_type(p, type, ln);
+                    }
+                    CP::st1(p, l, slot, k, lane, ln, xch);
+                    __syncwarp();
+                    CP::st2(l, slot, k + 1, lane, ln, xch);
+                    const double fa = __shfl_sync(kFull, ln.pub, CP::kFz + ln.a);
+                    const double fb = __shfl_sync(kFull, ln.pub, CP::kFz + ln.b);
+                    const double fuu = __shfl_sync(kFull, ln.pub, CP::kFu);
+                    CP::st3(ln, fa, fb, fuu);
+                    __syncwarp();  // xch is rewritten by the next stage's st1
                 }
+                CP::finish(l, slot, lane, ln);
+                const bool okall = __all_sync(kFull, ln.ok);
+                const double rdm = __shfl_sync(kFull, ln.val, CP::kRd);
+                const double pth = __shfl_sync(kFull, ln.val, CP::kPi + NX);
+                if (lane == 0) {
+                    m[L::M_PIV] = okall ? 1.0 : 0.0;
+                    m[L::M_RD] = lb_nanmax(rdm, lb_abs(pth));
+                }
+                if (cert && lane == 0) C::adjoint_sweep(p, l, slot, true);
+            } else {
+                if (lane == 0) C::factor_serial(p, l, slot);
+                else if (lane == 1) C::adjoint_sweep(p, l, slot, false);
+                else if (lane == 2 && cert) C::adjoint_sweep(p, l, slot, true);
+            }
+            __syncwarp();
+            LB_PROF(2)
+
+            // =================================================================================
+            // phase B2: verdict, then the affine backward/forward substitution
+            // =================================================================================
+            const int v = C::verdict(p, m, cert);
+            if (v >= 0) {
+                status = v;
+                break;
+            }
+            if (lane == 0) {
+                C::backward_vec(p, l, slot, true);
+                C::forward_vec(p, l, slot, true);
+            }
+            __syncwarp();
+            LB_PROF(3)
+
+            // =================================================================================
+            // phase C: affine step length, sigma, corrector rhs
+            // =================================================================================
+            double sigmu;
+            {
+                RedStep rs{0.0, 0.0, 0.0, 0.0};
+                for (int k = lane; k <= N; k += 32) C::affine_stage(p, l, slot, k, rs);
+                double acc[2 * NZ];
+#pragma unroll
+                for (int a = 0; a < 2 * NZ; ++a) acc[a] = 0.0;
+                for (int i = lane; i < p.ng; i += 32) C::affine_gen_row(p, l, slot, Gs, hgs, i, acc, rs);
+                const double ratio = warp_max(rs.ratio);
+                const double s0 = warp_sum(rs.s0), s1 = warp_sum(rs.s1), s2 = warp_sum(rs.s2);
+#pragma unroll
+                for (int a = 0; a < 2 * NZ; ++a) acc[a] = warp_sum(acc[a]);
+                const double aaff = ratio > 1.0 ? 1.0 / ratio : 1.0;
+                const double mu = m[L::M_MU];
+                const double mu_aff = (s0 + aaff * s1 + aaff * aaff * s2) * p.inv_m;
+                const double sr = mu_aff / mu;
+                sigmu = sr * sr * sr * mu;
+                for (int k = lane; k <= N; k += 32) C::corr_stage(p, l, slot, k, sigmu);
+                __syncwarp();
                 if (lane == 0) {
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) m[L::M_TH + t] = io.warm ? io.warm[q * (NU * N + NT) + N * NU + t] : 0.0;
-                    double cconst = 0.0;
-#pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        double v = 0.0;
-                        if (io.dx_ref) {
-#pragma unroll
-                            for (int j = 0; j < NX; ++j) v += p.Lref[a * NX + j] * io.dx_ref[q * NX + j];
-                        }
-                        m[L::M_LIN + a] = v;
-                    }
-                    if (io.dx_ref) {
-#pragma unroll
-                        for (int i = 0; i < NX; ++i)
-#pragma unroll
-                            for (int j = 0; j < NX; ++j)
-                                cconst += io.dx_ref[q * NX + i] * p.Tm[i * NX + j] * io.dx_ref[q * NX + j];
-                    }
-                    m[L::M_CCONST] = cconst;
-                    qpid[warp] = q;
-                    meta[warp * 4 + 1] = 0;
-                    meta[warp * 4 + 2] = 0;
+                    for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = acc[a] + sigmu * acc[NZ + a];
                 }
-                state = SLOT_FRESH;
-            } else {
-                state = SLOT_EMPTY;
+                __syncwarp();
             }
-            if (lane == 0) meta[warp * 4 + 0] = state;
-        }
-        const int nactive = __syncthreads_count(lane == 0 && state != SLOT_EMPTY);
-        LB_PROF(0)
-        if (nactive == 0) break;
+            LB_PROF(4)
 
-        // =====================================================================================
-        // phase D (sweep): corrector backward/forward substitution; initial rollout of fresh slots
-        // =====================================================================================
-        if (warp == 0 && lane < slots) {
-            double* const sl = smem + lane * l.stride;
-            const int st = meta[lane * 4 + 0];
-            if (st == SLOT_RUN) {
-                C::backward_vec(p, l, sl, false);
-                C::forward_vec(p, l, sl, false);
-            } else if (st == SLOT_FRESH) {
-                C::rollout(p, l, sl);
+            // =================================================================================
+            // phase D: corrector backward/forward substitution
+            // =================================================================================
+            if (lane == 0) {
+                C::backward_vec(p, l, slot, false);
+                C::forward_vec(p, l, slot, false);
             }
-        }
-        __syncthreads();
-        LB_PROF(1)
+            __syncwarp();
+            LB_PROF(5)
 
-        // =====================================================================================
-        // phase E+A: step length + update (RUN) or row initialisation (FRESH); then the
-        //            predictor assembly of the next iteration
-        // =====================================================================================
-#ifdef LBMPC_SUBPROF
-        long long ts_prev = clock64();
-#define LB_SUB(idx) if (io.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long tn = clock64(); io.prof[idx] += (unsigned long long)(tn - ts_prev); ts_prev = tn; }
-#else
-#define LB_SUB(idx)
-#endif
-        if (state == SLOT_RUN || state == SLOT_FRESH) {
-            RedAsm ra{0.0, 0.0, 0.0, 0.0};
-            if (state == SLOT_RUN) {
-                const double sigmu = m[L::M_SIGMU];
+            // =================================================================================
+            // phase E (first half): final directions of the rows, step length, polytope rows and theta
+            // =================================================================================
+            {
                 double ratio = 0.0;
                 for (int k = lane; k <= N; k += 32) ratio = fmax(ratio, C::final_stage(p, l, slot, k, sigmu));
-                LB_SUB(8)
                 for (int i = lane; i < p.ng; i += 32) ratio = fmax(ratio, C::final_gen_row(p, l, slot, Gs, hgs, i, sigmu));
                 ratio = warp_max(ratio);
-                LB_SUB(9)
-                double alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
+                alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
                 alpha = alpha > 1.0 ? 1.0 : alpha;
                 for (int i = lane; i < p.ng; i += 32) C::update_gen_row(p, l, slot, Gs, hgs, i, sigmu, alpha);
                 __syncwarp();  // the polytope rows read x_kg, theta of the old iterate
                 if (lane == 0) {
 #pragma unroll
                     for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
-                    meta[warp * 4 + 1] += 1;
                 }
                 __syncwarp();
-                LB_SUB(10)
-                for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra);
-                LB_SUB(11)
-            } else {
-                for (int k = lane; k <= N; k += 32) C::init_assemble_stage(p, l, slot, k, ra);
-                for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
-                state = SLOT_RUN;
-                if (lane == 0) meta[warp * 4 + 0] = SLOT_RUN;
             }
-            __syncwarp();  // x_kg of the new iterate is read by the polytope rows
-            double acc[NACC];
+            iters += 1;
+            LB_PROF(6)
+            if (prof_on) io.prof[7] += 1;
+        }
+
+        // ---- results ----
+        {
+            double J = 0.0;
+            for (int k = lane; k <= N; k += 32) J += C::objective_stage(p, l, slot, k);
+            J = warp_sum(J);
+            for (int k = lane; k < N; k += 32) {
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-            for (int i = lane; i < p.ng; i += 32) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
-            LB_SUB(12)
+                for (int i = 0; i < NU; ++i) {
+                    double v = slot[l.i_u(i, k)];
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
-            const double rp = warp_max(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
-            LB_SUB(13)
+                    for (int j = 0; j < NX; ++j) v -= p.Kout[i * NX + j] * slot[l.i_x(j, k)];
+                    io.uc[(q * N + k) * NU + i] = v;
+                }
+            }
+            if (io.xtraj) {
+                for (int k = lane; k <= N; k += 32)
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = slot[l.i_x(j, k)];
+            }
             if (lane == 0) {
 #pragma unroll
-                for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
-#pragma unroll
-                for (int a = 0; a < NZ; ++a) {
-                    m[L::M_GGL + a] = acc[NH + a];
-                    m[L::M_DG + a] = acc[NH + NZ + a];
-                }
-                m[L::M_RP] = rp;
-                m[L::M_MU] = sl * p.inv_m;
-                m[L::M_LAM] = lam;
-                m[L::M_HLAM] = hl;
+                for (int t = 0; t < NT; ++t) io.theta[q * NT + t] = m[L::M_TH + t];
+                io.obj[q] = J + m[L::M_CCONST];
+                io.iters[q] = iters;
+                io.status[q] = status;
             }
+            __syncwarp();
         }
-        __syncthreads();
-        LB_PROF(2)
-
-        // =====================================================================================
-        // phase B: Riccati factorisation (warps 0..3, 16 lanes per QP) with, on the otherwise
-        //          idle warps, the adjoint recursion (dual residual) and the Farkas recursion
-        // =====================================================================================
-        const bool prof_w = io.prof != nullptr && blockIdx.x == 0 && lane == 0;
-        const long long tb0 = prof_w ? clock64() : 0;
-        if constexpr (kCoop) {
-            if (warp < kMaxSlots / 2) {
-                const bool act = fslot < slots && meta[fslot * 4 + 0] == SLOT_RUN && meta[fslot * 4 + 1] < p.max_iter;
-                if (__any_sync(kFull, act)) {
-                    double* const sl = smem + (fslot < slots ? fslot : 0) * l.stride;
-                    const int hb = lane & 16;
-                    CP::terminal(p, l, sl, ln);
-                    int type = C::stage_type(p, N), kseg = p.tseg[type];
-                    for (int k = N - 1; k >= 0; --k) {
-                        if (k < kseg) {  // crossed into the previous cost segment
-                            type = C::stage_type(p, k);
-                            kseg = p.tseg[type];
-                            CP::load_type(p, type, ln);
-                        }
-                        CP::st1(p, l, sl, k, hl, ln, xch);
-                        __syncwarp();
-                        CP::st2(l, sl, k + 1, hl, ln, xch, act);
-                        const double fa = __shfl_sync(kFull, ln.pub, hb | ln.sa);
-                        const double fb = __shfl_sync(kFull, ln.pub, hb | ln.sb);
-                        const double fuu = __shfl_sync(kFull, ln.pub, hb | NX);
-                        CP::st3(ln, fa, fb, fuu);
-                        __syncwarp();  // xch is rewritten by the next stage's st1
-                    }
-                    CP::finish(l, sl, hl, ln, act);
-                    const unsigned okb = __ballot_sync(kFull, ln.ok);
-                    const unsigned hm = 0xffffu << (16 * half);
-                    if (act && hl == 0) sl[l.o_misc + L::M_PIV] = ((okb & hm) == hm) ? 1.0 : 0.0;
-                }
-            } else if (warp == kMaxSlots / 2) {
-                // lanes 0..7: dual residual of slot `lane`; lanes 8..15: Farkas recursion of slot `lane - 8`
-                const int sl_i = lane & (kMaxSlots - 1);
-                const bool fk = lane >= kMaxSlots;
-                if (lane < 2 * kMaxSlots && sl_i < slots && meta[sl_i * 4 + 0] == SLOT_RUN && meta[sl_i * 4 + 1] < p.max_iter) {
-                    double* const sl = smem + sl_i * l.stride;
-                    if (!fk || sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::adjoint_sweep(p, l, sl, fk);
-                }
-            }
-        } else {
-            if (warp == 0 && lane < slots && meta[lane * 4 + 0] == SLOT_RUN && meta[lane * 4 + 1] < p.max_iter) {
-                C::factor_serial(p, l, smem + lane * l.stride);
-            } else if (warp == 1) {
-                const int sl_i = lane & (kMaxSlots - 1);
-                const bool fk = lane >= kMaxSlots;
-                if (lane < 2 * kMaxSlots && sl_i < slots && meta[sl_i * 4 + 0] == SLOT_RUN && meta[sl_i * 4 + 1] < p.max_iter) {
-                    double* const sl = smem + sl_i * l.stride;
-                    if (!fk || sl[l.o_misc + L::M_LAM] >= p.inf_trigger) C::adjoint_sweep(p, l, sl, fk);
-                }
-            }
-        }
-        if (prof_w && warp == 0) io.prof[6] += (unsigned long long)(clock64() - tb0);
-        if (prof_w && warp == kMaxSlots / 2) io.prof[7] += (unsigned long long)(clock64() - tb0);
-        __syncthreads();
-        LB_PROF(3)
-
-        // =====================================================================================
-        // phase B2 (sweep): verdict, then the affine backward/forward substitution
-        // =====================================================================================
-        if (warp == 0 && lane < slots) {
-            double* const sl = smem + lane * l.stride;
-            if (meta[lane * 4 + 0] == SLOT_RUN) {
-                double* const ms = sl + l.o_misc;
-                int v;
-                if (meta[lane * 4 + 1] >= p.max_iter) {
-                    v = 1;  // LBMPC_ST_MAXITER
-                } else {
-                    v = C::verdict(p, ms, ms[L::M_LAM] >= p.inf_trigger);
-                }
-                if (v >= 0) {
-                    meta[lane * 4 + 2] = v;
-                    meta[lane * 4 + 0] = SLOT_DONE;
-                } else {
-                    C::backward_vec(p, l, sl, true);
-                    C::forward_vec(p, l, sl, true);
-                }
-            }
-        }
-        __syncthreads();
-        LB_PROF(4)
-        if (prof_on) io.prof[5] += 1;
+        LB_PROF(8)
     }
 #undef LB_PROF
 }

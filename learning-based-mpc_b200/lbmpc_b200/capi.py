@@ -195,9 +195,9 @@ class Solver:
         instrumentation on/off for the following solve calls."""
         out = np.zeros(16, np.uint64)
         self._check(self.lib.lbmpc_debug_phase_cycles(self.h, int(enable), _ptr(out)), "lbmpc_debug_phase_cycles")
-        names = ("C_affine_step", "D_corrector_sweeps", "EA_update_assemble", "B_factor", "B2_affine_sweeps", "iterations",
-                 "B_warp0_factor", "B_warp4_adjoint", "sub8", "sub9", "sub10", "sub11", "sub12", "sub13")
-        return dict(zip(names, (int(v) for v in out[:14])))
+        names = ("load_rollout", "EA_update_assemble", "B_factor_adjoint", "B2_affine_sweeps", "C_affine_step",
+                 "D_corrector_sweeps", "E_final_step", "iterations", "store")
+        return dict(zip(names, (int(v) for v in out[:9])))
 
     def _check(self, rc, what):
         if rc != 0:

@@ -64,25 +64,26 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         if constexpr (NT == 1 && NU == 1 && NX <= 4) {
             // 16-lane cooperative factorisation, lane-phases run as loops (kernel: __syncwarp between them)
             using CP = Coop<NX>;
-            typename CP::Lane ln[16];
+            typename CP::Lane ln[32];
             double xch[CP::kXch];
-            for (int h = 0; h < 16; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::terminal(p, l, s, ln[h]); }
+            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::terminal(p, l, s, ln[h]); }
             int type = C::stage_type(p, N);
             for (int k = N - 1; k >= 0; --k) {
                 const int t = C::stage_type(p, k);
-                if (t != type) { type = t; for (int h = 0; h < 16; ++h) CP::load_type(p, t, ln[h]); }
-                for (int h = 0; h < 16; ++h) CP::st1(p, l, s, k, h, ln[h], xch);
-                for (int h = 0; h < 16; ++h) CP::st2(l, s, k + 1, h, ln[h], xch, true);
-                for (int h = 0; h < 16; ++h)          // kernel: three warp shuffles
-                    if (ln[h].isP) CP::st3(ln[h], ln[ln[h].sa].pub, ln[ln[h].sb].pub, ln[NX].pub);
+                if (t != type) { type = t; for (int h = 0; h < 32; ++h) CP::load_type(p, t, ln[h]); }
+                for (int h = 0; h < 32; ++h) CP::st1(p, l, s, k, h, ln[h], xch);
+                for (int h = 0; h < 32; ++h) CP::st2(l, s, k + 1, h, ln[h], xch);
+                for (int h = 0; h < 32; ++h)          // kernel: three warp shuffles
+                    CP::st3(ln[h], ln[CP::kFz + ln[h].a].pub, ln[CP::kFz + ln[h].b].pub, ln[CP::kFu].pub);
             }
             bool ok = true;
-            for (int h = 0; h < 16; ++h) { CP::finish(l, s, h, ln[h], true); ok = ok && ln[h].ok; }
+            for (int h = 0; h < 32; ++h) { CP::finish(l, s, h, ln[h]); ok = ok && ln[h].ok; }
             m[L::M_PIV] = ok ? 1.0 : 0.0;
+            m[L::M_RD] = lb_nanmax(ln[CP::kRd].val, lb_abs(ln[CP::kPi + NX].val));
         } else {
             C::factor_serial(p, l, s);
+            C::adjoint_sweep(p, l, s, false);
         }
-        C::adjoint_sweep(p, l, s, false);
         if (cert) C::adjoint_sweep(p, l, s, true);
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
