@@ -82,15 +82,27 @@ struct Layout {
     // [qd | q | g | RL] are dead once the corrector sweeps are done: the final step-length pass
     // parks the row directions ds, dl (2 x 2 NVB per stage) there
     static_assert(F_RI >= 4 * NVB, "scratch for the row directions does not fit");
-    int Np, ngp;
-    int o_r1, o_r2, o_r3, o_sg, o_lg, o_misc, stride;
+    // blocked substitution sweeps: per block of bm stages the NX columns of the block transfer matrix
+    // ([Tx; t_theta], NZ values each) and one NZ-vector (local result / incoming state)
+    static constexpr int TS = NX * NZ, BS = (TS + NZ) | 1;
+    int Np, ngp, bm, nb;
+    int o_r1, o_r2, o_r3, o_blk, o_sg, o_lg, o_misc, stride;
+    static LB_HD int block_len(int N) {  // ~0.6 sqrt(N), at least N/32 (one lane per block)
+        int m = 1;
+        while (25 * m * m < 9 * N) ++m;
+        const int mmin = (N + 31) / 32;
+        return m > mmin ? m : mmin;
+    }
     LB_HD Layout(int N, int ngp_) {
         Np = N + 1;
         ngp = ngp_;
+        bm = block_len(N);
+        nb = (N + bm - 1) / bm;
         int o = 0;
         o_r1 = o;  o += RS1 * Np;
         o_r2 = o;  o += RS2 * Np;
         o_r3 = o;  o += RS3 * Np;
+        o_blk = o; o += BS * nb;
         o_sg = o;  o += ngp;
         o_lg = o;  o += ngp;
         o_misc = o; o += M_SIZE;
@@ -99,6 +111,7 @@ struct Layout {
     LB_HD int r1(int k) const { return o_r1 + k * RS1; }
     LB_HD int r2(int k) const { return o_r2 + k * RS2; }
     LB_HD int r3(int k) const { return o_r3 + k * RS3; }
+    LB_HD int blk(int b) const { return o_blk + b * BS; }
     LB_HD int i_x(int j, int k) const { return r1(k) + F_X + j; }
     LB_HD int i_u(int i, int k) const { return r1(k) + F_U + i; }
     LB_HD int i_v(int j, int k) const { return r1(k) + j; }            // bounded variable j of [x;u]
@@ -652,23 +665,32 @@ struct Core {
         }
     }
 
-    // ---- backward substitution (gradient recursion) with the stored factors:
-    //   rt = q_u + B'pv ; kap_k = -Ri rt ; pv <- q_z + Abar'pv - RL' rt ; d(theta) = -Ptt^-1 pv_theta
-    // d(theta) goes to M_DTHA (aff) or M_DTH. ----
+    // ---- backward / forward substitution with the stored factors, BLOCKED over the horizon ----
+    //   backward (gradient recursion): rt = q_u + B'pv ; kap_k = -Ri rt ; pv <- q_z + Abar'pv - RL' rt
+    //   forward                      : du_k = kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k
+    // Both recursions are affine in their state, so the horizon is cut into nb blocks of bm stages and
+    // one LANE per block runs them concurrently (one instruction stream for the whole warp instead of
+    // one per stage chain):
+    //   P1  every block from a zero state -> local result r_b; once per factorisation also the NX unit
+    //       states through the homogeneous recursion -> block transfer matrix T_b (lanes = block x vector;
+    //       the forward recursion uses the transposed x-block of the same matrices)
+    //   P2  one lane chains the blocks: state_in(b) = T_b state_in(b+1) + r_b   (nb small mat-vecs)
+    //   P3  every block again from its true incoming state, storing kap (backward) / du, dx (forward).
+    // The homogeneous runs read their affine inputs from an all-zero record (pointer step 0).
     struct BwdOps {  // shared-memory operands of one stage
         double q[NVB], gt[NT], RL[NU * NZ], Ri[NU * NU];
     };
-    static LB_HD void bwd_load(const double* r2, BwdOps& o) {
+    static LB_HD void bwd_load(const double* r2, const double* qrec, BwdOps& o) {
 #pragma unroll
-        for (int j = 0; j < NVB; ++j) o.q[j] = r2[L::F_Q + j];
+        for (int j = 0; j < NVB; ++j) o.q[j] = qrec[L::F_Q + j];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) o.gt[t] = r2[L::F_G + NX + t];
+        for (int t = 0; t < NT; ++t) o.gt[t] = qrec[L::F_G + NX + t];
 #pragma unroll
         for (int j = 0; j < NU * NZ; ++j) o.RL[j] = r2[L::F_RL + j];
 #pragma unroll
         for (int j = 0; j < NU * NU; ++j) o.Ri[j] = r2[L::F_RI + j];
     }
-    static LB_HD void bwd_step(const AB& c, const BwdOps& o, double* pv, double* r2) {
+    static LB_HD void bwd_step(const AB& c, const BwdOps& o, double* pv, double* r2, bool store) {
         double rt[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -697,63 +719,119 @@ struct Core {
             for (int i = 0; i < NU; ++i) v -= o.RL[i * NZ + NX + t] * rt[i];
             np_[NX + t] = v;
         }
+        if (store) {
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            double v = 0.0;
+            for (int i = 0; i < NU; ++i) {
+                double v = 0.0;
 #pragma unroll
-            for (int j = 0; j < NU; ++j) v -= o.Ri[i * NU + j] * rt[j];
-            r2[L::F_KAP + i] = v;
+                for (int j = 0; j < NU; ++j) v -= o.Ri[i * NU + j] * rt[j];
+                r2[L::F_KAP + i] = v;
+            }
         }
 #pragma unroll
         for (int a = 0; a < NZ; ++a) pv[a] = np_[a];
     }
-    static LB_HD void backward_vec(const P& p, const L& l, double* s, bool aff) {
-        double pv[NZ];
-        double* m = s + l.o_misc;
+    static LB_HD void bwd_kg(const double* m, double* pv) {
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
+    }
+    // costate at stage N (start of the recursion)
+    static LB_HD void bwd_terminal(const P& p, const L& l, const double* s, double* pv) {
+        const double* m = s + l.o_misc;
         const int N = p.N;
-        AB c;
-        load_ab(p, c);
 #pragma unroll
         for (int a = 0; a < NZ; ++a) {
             const double base = a < NX ? s[l.i_q(a, N)] : s[l.i_g(a, N)];
             pv[a] = base + (p.kg == N ? m[L::M_GGL + a] + m[L::M_DG + a] : 0.0);
         }
-        double* r2 = s + l.r2(N - 1);
+    }
+    // stages hi-1 .. lo from the costate pv (in/out).  qrec: record with q / g_theta of stage hi-1, stepping by
+    // qstep per stage (the slot's R2, or an all-zero record with qstep = 0 for the homogeneous recursion);
+    // kgl: stage after which the polytope terms are added (-1: never); store: write kap_k
+    static LB_HD void bwd_range(const AB& c, const L& l, double* s, int lo, int hi, double* pv, const double* qrec,
+                                int qstep, int kgl, bool store) {
+        const double* m = s + l.o_misc;
+        double* r2 = s + l.r2(hi - 1);
         BwdOps o0, o1;
-        bwd_load(r2, o0);
-        int k = N - 1;
-        for (; k >= 1; k -= 2) {
-            bwd_load(r2 - L::RS2, o1);
-            bwd_step(c, o0, pv, r2);
-            if (p.kg == k) {
-#pragma unroll
-                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
-            }
+        bwd_load(r2, qrec, o0);
+        int k = hi - 1;
+        for (; k >= lo + 1; k -= 2) {
+            bwd_load(r2 - L::RS2, qrec - qstep, o1);
+            bwd_step(c, o0, pv, r2, store);
+            if (kgl == k) bwd_kg(m, pv);
             r2 -= 2 * L::RS2;
-            bwd_load(k >= 2 ? r2 : r2 + L::RS2, o0);
-            bwd_step(c, o1, pv, r2 + L::RS2);
-            if (p.kg == k - 1) {
-#pragma unroll
-                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
-            }
+            qrec -= 2 * qstep;
+            const bool more = k >= lo + 2;
+            bwd_load(more ? r2 : r2 + L::RS2, more ? qrec : qrec + qstep, o0);
+            bwd_step(c, o1, pv, r2 + L::RS2, store);
+            if (kgl == k - 1) bwd_kg(m, pv);
         }
-        if (k == 0) {
-            bwd_step(c, o0, pv, r2);
-            if (p.kg == 0) {
+        if (k == lo) {
+            bwd_step(c, o0, pv, r2, store);
+            if (kgl == lo) bwd_kg(m, pv);
+        }
+    }
+    // P1 task t of the backward solve (with_T: tasks = block x (1 + NX) vectors, else one task per block)
+    static LB_HD void bwd_p1(const P& p, const L& l, double* s, const double* zero_rec, int t, bool with_T) {
+        AB c;
+        load_ab(p, c);
+        const int b = with_T ? t / (NX + 1) : t, vec = with_T ? t % (NX + 1) : 0;
+        const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
+        double pv[NZ];
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) pv[a] += m[L::M_GGL + a] + m[L::M_DG + a];
+        for (int a = 0; a < NZ; ++a) pv[a] = (vec > 0 && a == vec - 1) ? 1.0 : 0.0;
+        if (vec == 0 && b == l.nb - 1) bwd_terminal(p, l, s, pv);
+        const bool part = vec == 0;
+        bwd_range(c, l, s, lo, hi, pv, part ? s + l.r2(hi - 1) : zero_rec, part ? L::RS2 : 0, part ? p.kg : -1, false);
+        double* dst = s + l.blk(b) + (part ? L::TS : (vec - 1) * NZ);
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) dst[a] = pv[a];
+    }
+    // P2 of the backward solve (one lane): chain the blocks top-down, leave the incoming costate of block b in the
+    // vector slot of block b+1, finish with d(theta) = -Ptt^-1 pv_theta(0) -> M_DTHA (aff) or M_DTH
+    static LB_HD void bwd_p2(const L& l, double* s, bool aff) {
+        double* m = s + l.o_misc;
+        double out[NZ];
+        {
+            const double* v = s + l.blk(l.nb - 1) + L::TS;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) out[a] = v[a];
+        }
+        for (int b = l.nb - 2; b >= 0; --b) {
+            double* vin = s + l.blk(b + 1) + L::TS;  // consumed: now holds the incoming costate of block b
+            const double* T = s + l.blk(b);
+            double nv[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) nv[a] = T[L::TS + a] + (a >= NX ? out[a] : 0.0);
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) nv[a] += T[j * NZ + a] * out[j];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) {
+                vin[a] = out[a];
+                out[a] = nv[a];
             }
         }
 #pragma unroll
         for (int a = 0; a < NT; ++a) {
             double v = 0.0;
 #pragma unroll
-            for (int b = 0; b < NT; ++b) v -= m[L::M_PTT + a * NT + b] * pv[NX + b];
+            for (int bb = 0; bb < NT; ++bb) v -= m[L::M_PTT + a * NT + bb] * out[NX + bb];
             m[(aff ? L::M_DTHA : L::M_DTH) + a] = v;
         }
     }
+    // incoming costate of block b for P3 (read by every block lane BEFORE any lane overwrites the slots)
+    static LB_HD void bwd_p3_in(const P& p, const L& l, const double* s, int b, double* pv) {
+        if (b == l.nb - 1) {
+            bwd_terminal(p, l, s, pv);
+        } else {
+            const double* v = s + l.blk(b + 1) + L::TS;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) pv[a] = v[a];
+        }
+    }
 
-    // ---- forward substitution  du_k = kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k ----
     struct FwdOps {
         double RL[NU * NZ], kap[NU];
     };
@@ -764,7 +842,7 @@ struct Core {
         for (int i = 0; i < NU; ++i) o.kap[i] = r2[L::F_KAP + i];
     }
     // r3: record of stage k (du_k is written there, dx_{k+1} to the next record); off: 0 or NVB (affine)
-    static LB_HD void fwd_step(const AB& c, const FwdOps& o, const double* dth, double* dx, double* r3, int off) {
+    static LB_HD void fwd_step(const AB& c, const FwdOps& o, const double* dth, double* dx, double* r3, int off, bool store) {
         double du[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -788,42 +866,92 @@ struct Core {
             for (int i = 0; i < NU; ++i) v += c.B[a * NU + i] * du[i];
             xn[a] = v;
         }
+        if (store) {
 #pragma unroll
-        for (int i = 0; i < NU; ++i) r3[off + L::F_DU + i] = du[i];
+            for (int i = 0; i < NU; ++i) r3[off + L::F_DU + i] = du[i];
+        }
 #pragma unroll
         for (int a = 0; a < NX; ++a) {
             dx[a] = xn[a];
-            r3[L::RS3 + off + L::F_DX + a] = xn[a];
+            if (store) r3[L::RS3 + off + L::F_DX + a] = xn[a];
         }
     }
-    static LB_HD void forward_vec(const P& p, const L& l, double* s, bool aff) {
-        const int off = aff ? NVB : 0;
-        const double* m = s + l.o_misc;
-        const int N = p.N;
-        AB c;
-        load_ab(p, c);
-        double dx[NX], dth[NT];
-        double* r3 = s + l.r3(0);
-        const double* r2 = s + l.r2(0);
-#pragma unroll
-        for (int j = 0; j < NX; ++j) {
-            dx[j] = 0.0;
-            r3[off + L::F_DX + j] = 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) dth[t] = m[(aff ? L::M_DTHA : L::M_DTH) + t];
+    // stages lo .. hi-1 from the state dx (in/out)
+    static LB_HD void fwd_range(const AB& c, const L& l, double* s, int lo, int hi, double* dx, const double* dth,
+                                int off, bool store) {
+        double* r3 = s + l.r3(lo);
+        const double* r2 = s + l.r2(lo);
         FwdOps o0, o1;
         fwd_load(r2, o0);
-        int k = 0;
-        for (; k + 1 < N; k += 2) {
+        int k = lo;
+        for (; k + 1 < hi; k += 2) {
             fwd_load(r2 + L::RS2, o1);
-            fwd_step(c, o0, dth, dx, r3, off);
+            fwd_step(c, o0, dth, dx, r3, off, store);
             r2 += 2 * L::RS2;
-            fwd_load(k + 2 < N ? r2 : r2 - L::RS2, o0);
-            fwd_step(c, o1, dth, dx, r3 + L::RS3, off);
+            fwd_load(k + 2 < hi ? r2 : r2 - L::RS2, o0);
+            fwd_step(c, o1, dth, dx, r3 + L::RS3, off, store);
             r3 += 2 * L::RS3;
         }
-        if (k < N) fwd_step(c, o0, dth, dx, r3, off);
+        if (k < hi) fwd_step(c, o0, dth, dx, r3, off, store);
+    }
+    // backward P3 (true incoming costate pv, stores kap) fused with forward P1 (zero state -> local result in
+    // the vector slot of block b) for block b
+    static LB_HD void bwd_p3_fwd_p1(const P& p, const L& l, double* s, int b, double* pv, bool aff) {
+        AB c;
+        load_ab(p, c);
+        const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
+        bwd_range(c, l, s, lo, hi, pv, s + l.r2(hi - 1), L::RS2, p.kg, true);
+        const double* m = s + l.o_misc;
+        double dx[NX], dth[NT];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) dx[j] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) dth[t] = m[(aff ? L::M_DTHA : L::M_DTH) + t];
+        fwd_range(c, l, s, lo, hi, dx, dth, aff ? NVB : 0, false);
+        double* v = s + l.blk(b) + L::TS;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v[j] = dx[j];
+    }
+    // forward P2 (one lane): dx_in(b+1) = Tx_b' dx_in(b) + local(b), left in the vector slot of block b
+    static LB_HD void fwd_p2(const L& l, double* s) {
+        double din[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) din[j] = 0.0;
+        for (int b = 0; b + 1 < l.nb; ++b) {
+            double* v = s + l.blk(b) + L::TS;
+            const double* T = s + l.blk(b);
+            double nv[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                double a0 = v[i];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a0 += T[i * NZ + j] * din[j];
+                nv[i] = a0;
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                din[i] = nv[i];
+                v[i] = nv[i];
+            }
+        }
+    }
+    // forward P3 for block b: from the true incoming state, storing du_k, dx_{k+1}
+    static LB_HD void fwd_p3(const P& p, const L& l, double* s, int b, bool aff) {
+        AB c;
+        load_ab(p, c);
+        const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
+        const double* m = s + l.o_misc;
+        const int off = aff ? NVB : 0;
+        double dx[NX], dth[NT];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) dx[j] = b > 0 ? s[l.blk(b - 1) + L::TS + j] : 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) dth[t] = m[(aff ? L::M_DTHA : L::M_DTH) + t];
+        if (b == 0) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) s[l.r3(0) + off + L::F_DX + j] = 0.0;
+        }
+        fwd_range(c, l, s, lo, hi, dx, dth, off, true);
     }
 
     // ============================================================================================

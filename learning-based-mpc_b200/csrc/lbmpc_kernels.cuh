@@ -106,7 +106,7 @@ template <int NX, int NT, int NU>
 struct SmemPlan {
     using L = Layout<NX, NT, NU>;
     static constexpr int kXchPerSlot = 40;  // >= Coop::kXch doubles per QP (even)
-    int slots, stride, xch_off, g_off, hg_off, meta_off;  // offsets in doubles
+    int slots, stride, xch_off, zero_off, g_off, hg_off, meta_off;  // offsets in doubles
     size_t bytes;
     __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
         const L l(N, ngp);
@@ -116,7 +116,9 @@ struct SmemPlan {
         o = (o + 1) & ~1;  // 16-byte alignment
         xch_off = o;
         o += slots * kXchPerSlot;
-        g_off = o;         // bulk copy destination (16-byte aligned: kXchPerSlot is even)
+        zero_off = o;      // all-zero record read by the homogeneous block recursions
+        o += (L::RS2 + 1) & ~1;
+        g_off = o;         // bulk copy destination (16-byte aligned)
         if (stage_g) o += (NX + NT) * ngp;
         hg_off = o;
         if (stage_g) o += ngp;
@@ -125,6 +127,28 @@ struct SmemPlan {
         bytes = (size_t)o * sizeof(double);
     }
 };
+
+// blocked backward + forward substitution of one QP by its warp (lanes = blocks / block x vector tasks)
+template <int NX, int NT, int NU>
+__device__ __forceinline__ void solve_sweeps(const Params<NX, NT, NU>& p, const Layout<NX, NT, NU>& l, double* slot,
+                                             const double* zero_rec, int lane, bool aff, bool with_T) {
+    using C = Core<NX, NT, NU>;
+    constexpr int NZ = NX + NT;
+    const int ntask = l.nb * (with_T ? NX + 1 : 1);
+    for (int t = lane; t < ntask; t += 32) C::bwd_p1(p, l, slot, zero_rec, t, with_T);
+    __syncwarp();
+    if (lane == 0) C::bwd_p2(l, slot, aff);
+    __syncwarp();
+    double pv[NZ];
+    if (lane < l.nb) C::bwd_p3_in(p, l, slot, lane, pv);
+    __syncwarp();
+    if (lane < l.nb) C::bwd_p3_fwd_p1(p, l, slot, lane, pv, aff);
+    __syncwarp();
+    if (lane == 0) C::fwd_p2(l, slot);
+    __syncwarp();
+    if (lane < l.nb) C::fwd_p3(p, l, slot, lane, aff);
+    __syncwarp();
+}
 
 // One warp per resident QP ("slot"), `slots` warps per CTA, no CTA-level synchronisation inside the
 // solve: a warp fetches a QP from the global work queue, iterates it to its verdict with every phase
@@ -171,6 +195,8 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         CP::lane_init(p, lane, ln);
         CP::xch_init(lane, xch);
     }
+    const double* const zero_rec = smem + plan.zero_off;
+    for (int i = threadIdx.x; i < L::RS2; i += blockDim.x) smem[plan.zero_off + i] = 0.0;
     if (stage_g) mbar_wait(bar, 0);
     __syncthreads();
 
@@ -315,11 +341,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 status = v;
                 break;
             }
-            if (lane == 0) {
-                C::backward_vec(p, l, slot, true);
-                C::forward_vec(p, l, slot, true);
-            }
-            __syncwarp();
+            solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, true, true);
             LB_PROF(3)
 
             // =================================================================================
@@ -355,11 +377,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             // =================================================================================
             // phase D: corrector backward/forward substitution
             // =================================================================================
-            if (lane == 0) {
-                C::backward_vec(p, l, slot, false);
-                C::forward_vec(p, l, slot, false);
-            }
-            __syncwarp();
+            solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, false, false);
             LB_PROF(5)
 
             // =================================================================================

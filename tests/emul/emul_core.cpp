@@ -45,6 +45,18 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     C::rollout(p, l, s);
     for (int i = 0; i < p.ng; ++i) C::init_rows_gen(p, l, s, G, hg, i);
     double alpha = 0.0;
+    std::vector<double> zero_rec(L::RS2, 0.0);
+    // blocked substitution sweeps: lane-phases as loops (kernel: lanes of the QP's warp, __syncwarp between phases)
+    auto solve_sweeps = [&](bool aff, bool with_T) {
+        const int ntask = l.nb * (with_T ? NX + 1 : 1);
+        for (int t = 0; t < ntask; ++t) C::bwd_p1(p, l, s, zero_rec.data(), t, with_T);
+        C::bwd_p2(l, s, aff);
+        std::vector<double> pin((size_t)l.nb * NZ);
+        for (int b = 0; b < l.nb; ++b) C::bwd_p3_in(p, l, s, b, pin.data() + (size_t)b * NZ);
+        for (int b = 0; b < l.nb; ++b) C::bwd_p3_fwd_p1(p, l, s, b, pin.data() + (size_t)b * NZ, aff);
+        C::fwd_p2(l, s);
+        for (int b = l.nb - 1; b >= 0; --b) C::fwd_p3(p, l, s, b, aff);
+    };
     int it = 0, st = 1;
     for (it = 0; it < p.max_iter; ++it) {
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
@@ -88,8 +100,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
-        C::backward_vec(p, l, s, true);
-        C::forward_vec(p, l, s, true);
+        solve_sweeps(true, true);
         // ---- phase C: affine step length, sigma, corrector rhs ----
         RedStep rs{0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) C::affine_stage(p, l, s, k, rs);
@@ -104,8 +115,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         for (int k = 0; k <= N; ++k) C::corr_stage(p, l, s, k, sigmu);
         for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a] + sigmu * dg[NZ + a];
         // ---- phase D: corrector substitution sweeps ----
-        C::backward_vec(p, l, s, false);
-        C::forward_vec(p, l, s, false);
+        solve_sweeps(false, false);
         // ---- phase E: step length, update ----
         double ratio = 0.0;
         for (int k = 0; k <= N; ++k) ratio = lb_max(ratio, C::final_stage(p, l, s, k, sigmu));

@@ -1,5 +1,5 @@
-// Isolated timing of the 16-lane cooperative Riccati stage (Coop<4>) — one warp, variants that drop
-// one ingredient at a time, to see what the per-stage dependency chain really costs on sm_100a.
+// Isolated timing of the one-warp cooperative Riccati stage (Coop<4>) for 1..8 resident warps per SM:
+// what the per-stage dependency chain costs on sm_100a and how warps sharing a scheduler interact.
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../learning-based-mpc_b200/csrc/lbmpc_core.cuh"
@@ -8,49 +8,45 @@ using CP = Coop<4>;
 using P4 = Params<4, 1, 1>;
 using L4 = Layout<4, 1, 1>;
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef REPS
+#define REPS 20
+#endif
 
 template <int MODE>
 __global__ void k_factor(const __grid_constant__ P4 p, long long* cyc, double* out, int reps) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const L4 l(p.N, p.ngp);
-    double* sl = smem + half * l.stride;
-    double* xch = smem + 2 * l.stride + 2 + half * 24;
-    for (int i = lane; i < 2 * l.stride + 64; i += 32) smem[i] = 0.01 * (i % 7) + 0.5;
-    __syncwarp();
+    double* sl = smem;  // all warps read the same slot (stores suppressed in MODE 1)
+    double* xch = smem + ((l.stride + 3) & ~1) + warp * 40;
+    for (int i = threadIdx.x; i < l.stride + 2; i += blockDim.x) smem[i] = 0.01 * (i % 7) + 0.5;
+    __syncthreads();
     typename CP::Lane ln;
-    CP::lane_init(p, hl, ln);
-    CP::xch_init(hl, xch);
-    __syncwarp();
-    const int N = p.N, hb = lane & 16;
+    CP::lane_init(p, lane, ln);
+    CP::xch_init(lane, xch);
+    __syncthreads();
+    const int N = p.N;
     long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
         CP::terminal(p, l, sl, ln);
         for (int k = N - 1; k >= 0; --k) {
-            CP::st1(p, l, sl, k, hl, ln, xch);
+            CP::st1(p, l, sl, k, lane, ln, xch);
             __syncwarp();
-            CP::st2(l, sl, k + 1, hl, ln, xch, MODE != 1);
-            double fa, fb, fuu;
-            if (MODE == 2) { fa = ln.pub; fb = ln.pub * 0.5; fuu = ln.pub * 0.25; }
-            else {
-                fa = __shfl_sync(kFull, ln.pub, hb | ln.sa);
-                fb = __shfl_sync(kFull, ln.pub, hb | ln.sb);
-                fuu = __shfl_sync(kFull, ln.pub, hb | 4);
-            }
+            CP::st2(l, sl, k + 1, lane, ln, xch);
+            const double fa = __shfl_sync(kFull, ln.pub, CP::kFz + ln.a);
+            const double fb = __shfl_sync(kFull, ln.pub, CP::kFz + ln.b);
+            const double fuu = __shfl_sync(kFull, ln.pub, CP::kFu);
             CP::st3(ln, fa, fb, fuu);
-            if (MODE == 3) ln.pt = ln.pt * 1e-3 + 1.0;  // keep values tame
+            if (MODE == 1) ln.val = ln.val * 1e-3 + 1.0;  // keep values tame
             __syncwarp();
         }
-        CP::finish(l, sl, hl, ln, true);
+        CP::finish(l, sl, lane, ln);
     }
     long long t1 = clock64();
-    if (lane == 0) cyc[0] = t1 - t0;
-    out[threadIdx.x] = ln.pt;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    out[threadIdx.x] = ln.val;
 }
 
-#ifndef REPS
-#define REPS 20
-#endif
 int main() {
     P4 p{};
     p.N = 50; p.ng = 24; p.ngp = 24; p.kg = 1; p.kT = 50; p.kx0 = 1; p.kx1 = 50; p.ku0 = 0; p.ku1 = 49; p.ntypes = 2;
@@ -59,15 +55,16 @@ int main() {
     for (int i = 0; i < 4; ++i) p.B[i] = 0.1 * (i + 1);
     for (int t = 0; t < 4; ++t) for (int i = 0; i < 36; ++i) p.W[t][i] = (i % 7 == 0) ? 2.0 : 0.01;
     long long* cyc; double* out;
-    cudaMalloc(&cyc, 8); cudaMalloc(&out, 32 * 8);
+    cudaMalloc(&cyc, 8); cudaMalloc(&out, 256 * 8);
     const L4 l(p.N, p.ngp);
-    size_t smem = (2 * l.stride + 128) * 8;
-    const char* names[4] = {"full stage", "no factor stores", "no shuffles (local values)", "full + damping"};
-    for (int rep = 0; rep < 2; ++rep) {
-#define RUN(M) { cudaFuncSetAttribute(k_factor<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_factor<M><<<1, 32, smem>>>(p, cyc, out, REPS); long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
-        printf("%-30s %8.1f cycles/stage  (%s)\n", names[M], (double)h / ((double)REPS * 50), cudaGetErrorString(cudaGetLastError())); }
-        RUN(0) RUN(1) RUN(2) RUN(3)
-    }
+    size_t smem = (l.stride + 8 * 40 + 16) * 8;
+    cudaFuncSetAttribute(k_factor<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_factor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; ++rep)
+        for (int warps = 1; warps <= 8; warps *= 2) {
+            k_factor<0><<<1, 32 * warps, smem>>>(p, cyc, out, REPS);
+            long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+            printf("one-warp stage, %d warps/CTA : %8.1f cycles/stage  (%s)\n", warps, (double)h / ((double)REPS * 50), cudaGetErrorString(cudaGetLastError()));
+        }
     return 0;
 }
