@@ -72,7 +72,7 @@ struct Layout {
                          M_RP = M_PTT + NT * NT, M_MU = M_RP + 1, M_LAM = M_MU + 1, M_HLAM = M_LAM + 1,
                          M_RD = M_HLAM + 1, M_ALPHA = M_RD + 1, M_SIGMU = M_ALPHA + 1,
                          M_CCONST = M_SIGMU + 1, M_CERT = M_CCONST + 1, M_OBJ = M_CERT + 1,
-                         M_PIV = M_OBJ + 1, M_SIZE = M_PIV + 1;
+                         M_PIV = M_OBJ + 1, M_GTH = M_PIV + 1, M_SIZE = M_GTH + 1;
     // field offsets inside the records
     static constexpr int F_X = 0, F_U = NX, F_S = NVB, F_LB = 3 * NVB, RS1 = (5 * NVB) | 1;
     static constexpr int F_QD = 0, F_Q = NVB, F_G = 2 * NVB, F_RL = F_G + NV, F_RI = F_RL + NU * NZ,
@@ -130,6 +130,7 @@ struct Layout {
 
 struct RedAsm {  // reductions of the assembly pass
     double rp, sl, lam, hl;  // max |r_p|, sum s*lambda, max lambda, sum lambda*slack
+    double gth;              // sum over the stages of g_theta (NT = 1): theta component of the dual residual
 };
 struct RedStep {  // reductions of a step-length pass
     double ratio, s0, s1, s2;  // max(-ds/s, -dl/l), sum s l, sum (s dl + l ds), sum ds dl
@@ -306,6 +307,7 @@ struct Core {
         for (int t = 0; t < NT; ++t) r3[NX + t] = 0.0;
 #pragma unroll
         for (int a = 0; a < NV; ++a) r2[L::F_G + a] = g[a];
+        red.gth += g[NX];
     }
     // fresh QP: initial slacks and multipliers s = max(h - a v, 1), lambda = 1, then the assembly
     static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red) {
@@ -773,9 +775,16 @@ struct Core {
     }
     // P1 task t of the backward solve (with_T: tasks = block x (1 + NX) vectors, else one task per block)
     static LB_HD void bwd_p1(const P& p, const L& l, double* s, const double* zero_rec, int t, bool with_T) {
+        bwd_p1_task(p, l, s, zero_rec, with_T ? t / (NX + 1) : t, with_T ? t % (NX + 1) : 0);
+    }
+    // homogeneous tasks only (block transfer matrices): t = block x unit vector
+    static LB_HD void bwd_p1_T(const P& p, const L& l, double* s, const double* zero_rec, int t) {
+        bwd_p1_task(p, l, s, zero_rec, t / NX, 1 + t % NX);
+    }
+    // vec = 0: particular solution of block b (local result); vec = j+1: unit costate e_j through the homogeneous recursion
+    static LB_HD void bwd_p1_task(const P& p, const L& l, double* s, const double* zero_rec, int b, int vec) {
         AB c;
         load_ab(p, c);
-        const int b = with_T ? t / (NX + 1) : t, vec = with_T ? t % (NX + 1) : 0;
         const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
         double pv[NZ];
 #pragma unroll
@@ -901,6 +910,16 @@ struct Core {
         load_ab(p, c);
         const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
         bwd_range(c, l, s, lo, hi, pv, s + l.r2(hi - 1), L::RS2, p.kg, true);
+        fwd_p1_ab(c, p, l, s, b, aff);
+    }
+    // forward P1 for block b: zero state -> local result in the vector slot of block b
+    static LB_HD void fwd_p1(const P& p, const L& l, double* s, int b, bool aff) {
+        AB c;
+        load_ab(p, c);
+        fwd_p1_ab(c, p, l, s, b, aff);
+    }
+    static LB_HD void fwd_p1_ab(const AB& c, const P& p, const L& l, double* s, int b, bool aff) {
+        const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
         const double* m = s + l.o_misc;
         double dx[NX], dth[NT];
 #pragma unroll
@@ -1146,44 +1165,51 @@ struct Core {
 
 // ------------------------------------------------------------------------------------------------
 // Cooperative Riccati factorisation for NT = NU = 1 (the Moore-Greitzer shape): ONE WARP per QP,
-// one dot product per lane per stage, with the adjoint (dual-residual) recursion riding on spare
-// lanes of the same instruction stream.
+// one dot product per lane per stage.  Three recursions ride on the same instruction stream:
+//   * the factorisation itself (cost-to-go matrix P over z = [x;theta]),
+//   * the adjoint recursion that gives the dual residual |r_d| (input g = cost gradient + G'lambda),
+//   * the backward substitution of the AFFINE (predictor) Newton system (input q),
+// so that after the sweep only forward substitutions are left for the predictor.
 //
-// A single warp issues at most one instruction every ~2 cycles on sm_100a (measured,
-// tools/microbench), so the stage time is  2.2 x (instructions per stage) + exposed latencies: the
-// design minimises instructions on the one stream and keeps latencies off the dependency chain.
+// The stage time is set by the dependency chain publish -> read -> dot -> shuffle -> update
+// (~130 cycles with the latencies measured in tools/microbench/lat.cu); everything else — the
+// reciprocal of the pivot, the stored factors, the stage inputs — is kept off that chain.
 //
-// Lane roles (NX = 4: NH = 15 unique entries of the symmetric NZ x NZ cost-to-go matrix):
-//   0..NH-1        entry (a,b), a <= b, kept SCALED by the pivot of the stage it came from:
-//                  Pt = rho P, ir = 1/rho
-//   NH..NH+NZ-1    F_uz[c] = (Abar' Pt Bbar)[c]            NH+NZ   F_uu = Bbar' Pt Bbar
-//   NH+NZ+1 ..+NZ  adjoint pi[a]                            +NZ+1   r_d lane: g_u + B'pi
+// Lane roles (NX = 4: NH = 15 unique entries of the symmetric NZ x NZ matrix):
+//   0..NH-1      entry (a,b), a <= b, kept SCALED by the pivot of the stage it came from: Pt = rho P
+//   kFz..+NZ-1   F_uz[c] = (Abar' Pt Bbar)[c]          kFu   F_uu = Bbar' Pt Bbar
+//   kPi..+NX-1   adjoint pi[a] (unscaled)              kRd   running max |g_u + B'pi|
+//   kPv..+NZ-1   affine costate pv[a], scaled: pvt = rho pv        kRt   B'pvt
 // One stage:  F = Abar_e' Pt Abar_e with Abar_e = [Abar Bbar]: every entry is a fixed linear form in
 // the unique entries of Pt, i.e. a dot product with a per-lane coefficient vector over NLD values
-// read from a lane-type dependent base of the exchange buffer; then
+// read from a lane-type dependent base of the exchange buffer.  With ir = 1/rho:
 //     Rt  = Wuu + Qd_u + F_uu ir ,  L = Wuz + F_uz ir
-//     Pt' = Rt (Wzz + Qd + [HG] + F_zz ir) - L'L ,  rho' = Rt
-// which is P' = Wzz + Qd + Abar'P Abar - L'L/Rt multiplied through by Rt.  The reciprocal of the
-// pivot is needed only one stage later (and for the stored factors RL = L/Rt, Ri = 1/Rt): its
-// hardware seed is issued as soon as Rt exists and its Newton refinement is interleaved with the
-// next stage's dot products, so it never sits on the stage-to-stage dependency chain.
-// The adjoint lanes compute pi' = g + Abar'pi and |g_u + B'pi| with the SAME dot instruction
-// (coefficients = columns of Abar / B, operands = the published pi).
+//     Pt' = Rt (Wzz + Qd + [HG] + F_zz ir) - L'L ,  rho' = Rt            (P' = Wzz+Qd+Abar'P Abar - L'L/Rt)
+//     pvt'= Rt (q + [GGL+DG] + (Abar'pvt) ir) - L' rtn ,  rtn = q_u + (B'pvt) ir ,  kappa = -rtn/Rt
+//     pi' = g + [GGL] + Abar'pi
+// The reciprocal of the pivot is needed only one stage later (and for the stored factors RL = L/Rt,
+// Ri = 1/Rt, kappa): its hardware seed is issued as soon as Rt exists and its Newton refinement is
+// interleaved with the next stage's dot products, so no division sits on the stage-to-stage chain.
+// The theta component of the adjoint needs no recursion (Abar is the identity there): it is the
+// plain sum of g_theta over the stages, reduced in the assembly phase (M_GTH).
 //
-// Exchange 1 (shared memory, xch): entry lanes publish Pt, adjoint lanes publish pi; layout
-// [xx block | (a,theta) | (theta,theta) | zero pad | pi | zero pad].  Exchange 2 (warp shuffles in
-// the kernel, `pub` in the emulation): entry lanes fetch F_uz[a], F_uz[b], F_uu.
-// The lane-phases st1/st2/st3 are separated by __syncwarp()/shuffles in the kernel; tests/emul
-// runs them as loops over the 32 lanes.
+// Exchange 1 (shared memory, double buffered: one __syncwarp per stage): publishing lanes store
+// their value, every lane reads NLD consecutive doubles from its base.  Layout of one buffer:
+// [xx block | (a,theta) | (theta,theta) | pad | pi | pad | pvt | pad], pads are zero and only ever
+// multiplied by zero coefficients.  Exchange 2 (warp shuffles): F_uz[a], F_uz[b] / B'pvt, F_uu.
+// The lane phases st1/st2/st3 are separated by __syncwarp()/shuffles in the kernel; tests/emul runs
+// them as loops over the 32 lanes.
 // ------------------------------------------------------------------------------------------------
 template <int NX>
 struct Coop {
     static constexpr int NT = 1, NU = 1, NZ = NX + 1, NV = NZ + 1, NH = NZ * (NZ + 1) / 2, NXX = NX * (NX + 1) / 2;
     static constexpr int NLD = (NXX + 1) & ~1;            // values each lane reads (even: 16-byte loads)
-    static constexpr int kFz = NH, kFu = NH + NZ, kPi = NH + NZ + 1, kRd = kPi + NZ;  // first lane of each role
-    static constexpr int kXpi = (NH - 1 + NLD + 1) & ~1;  // pi block of the exchange buffer
-    static constexpr int kXch = (kXpi + NLD + 1) & ~1;
-    static_assert(kRd < 32 && NX >= 2 && NZ <= NLD, "shape does not fit the one-warp mapping");
+    static constexpr int kFz = NH, kFu = NH + NZ, kPi = kFu + 1, kRd = kPi + NX, kPv = kRd + 1, kRt = kPv + NZ;
+    // exchange buffer (doubles); every read base is even
+    static constexpr int oXT = (NXX + 1) & ~1, oTT = (oXT + NX + 1) & ~1, oPi = (oTT + NLD + 1) & ~1,
+                         oPv = (oPi + NLD + 1) & ~1, oDummy = (oPv + NLD + 1) & ~1, kBuf = oDummy + 8;
+    static constexpr int kXch = 2 * kBuf;                 // two buffers, each with 8 never-read slots for the lanes that publish nothing
+    static_assert(kRt < 32 && NX >= 2 && NZ <= NLD, "shape does not fit the one-warp mapping");
     using P = Params<NX, 1, 1>;
     using L = Layout<NX, 1, 1>;
     using C = Core<NX, 1, 1>;
@@ -1193,14 +1219,21 @@ struct Coop {
         return b < NX ? a * NX - a * (a - 1) / 2 + (b - a) : (a < NX ? NXX + a : NH - 1);
     }
     struct Lane {
-        int a, b, base, in_off;  // entry owned / adjoint component a; read base in xch; stage-input offset in R2
-        bool isP, isPi, isRd, has_in;
-        double c1[NLD];          // the lane's linear form over xch[base..base+NLD)
-        double wzz, wa, wb, wuu;
-        double val, ir, d1, pub; // val: Pt entry / pi component / running |r_d|
-        double qdu, in, hgv;     // stage inputs fetched ahead: Qd_u; Qd_a (diagonal x entries) or g[a]; HG / GGL at kg
-        double rt, y0, la;       // pivot, reciprocal seed and L_a of the previous stage (deferred refinement)
-        bool ok, pend;           // pend: a previous stage's factors are waiting to be stored
+        // constants of the lane
+        double c[NLD];                 // linear form over xch[base .. base+NLD)
+        int a, b, base, pubi, in_off, in_step, out_off, srcA, srcB;
+        bool isP, isPi, isPv, isRd, isRt, plike, stDef, stRi;
+        // constants of the cost segment / of this factorisation
+        double wzz, wa, wb, wuu, hg;
+        // recursion state
+        double val;                    // Pt entry | pi | pvt | running |r_d|
+        double rt, y0;                 // pivot of the matrix being published and its reciprocal seed
+        double dmul;                   // deferred factor store: L_a (diagonal lanes), -rtn (kRt)
+        bool ok;
+        // stage temporaries handed from phase to phase
+        double qdu, qu, czz, d1, ir;
+        const double* in_ptr;          // stage input of this lane (walks the R2 records; a zero double otherwise)
+        double* out_ptr;               // deferred store target (walks the R2 records one stage behind)
     };
     static LB_HD double rcp_seed(double x) {
 #ifdef __CUDA_ARCH__
@@ -1217,10 +1250,24 @@ struct Coop {
         e = fma(-x, y, 1.0);
         return fma(y, e, y);
     }
+    // keep a lane constant in a register: without this the compiler re-derives it from threadIdx inside the
+    // stage loop (dozens of integer instructions per stage)
+    template <typename T>
+    static LB_HD void pin(T& v) {
+#ifdef __CUDA_ARCH__
+        if constexpr (sizeof(T) == 8) asm volatile("" : "+d"(*reinterpret_cast<double*>(&v)));
+        else asm volatile("" : "+r"(*reinterpret_cast<int*>(&v)));
+#else
+        (void)v;
+#endif
+    }
     static LB_HD void lane_init(const P& p, int h, Lane& ln) {
         ln.isP = h < NH;
-        ln.isPi = h >= kPi && h < kPi + NZ;
+        ln.isPi = h >= kPi && h < kPi + NX;
         ln.isRd = h == kRd;
+        ln.isPv = h >= kPv && h < kPv + NZ;
+        ln.isRt = h == kRt;
+        ln.plike = ln.isP || ln.isPv;
         ln.a = 0;
         ln.b = 0;
 #pragma unroll
@@ -1232,15 +1279,29 @@ struct Coop {
                     ln.b = b;
                 }
         if (ln.isPi) ln.a = ln.b = h - kPi;
+        if (ln.isPv) ln.a = ln.b = h - kPv;
         const bool xx = h < NXX, xt = (h >= NXX && h < NH - 1), tt = (h == NH - 1);
         const int fz = h - kFz;  // F_uz component for lanes kFz..kFz+NZ-1
         const bool fzx = (fz >= 0 && fz < NX), fzt = (fz == NX), fu = (h == kFu);
-        ln.base = (xt || fzt) ? NXX : (tt ? NH - 1 : ((ln.isPi || ln.isRd) ? kXpi : 0));
+        ln.base = (xt || fzt) ? oXT : (tt ? oTT : ((ln.isPi || ln.isRd) ? oPi : ((ln.isPv || ln.isRt) ? oPv : 0)));
+        // where the lane publishes its value (a private dummy slot if it has nothing to publish)
+        ln.pubi = xx ? h : (xt ? oXT + ln.a : (tt ? oTT : (ln.isPi ? oPi + ln.a : (ln.isPv ? oPv + ln.a : oDummy + (fz >= 0 && fz < NZ ? fz : (fu ? 5 : (ln.isRd ? 6 : 7)))))));
+        // stage input: Qd_a (diagonal x entries), g_a (adjoint), g_u (r_d lane), q_a / g_theta (affine costate)
         const bool dgx = ln.isP && ln.a == ln.b && ln.a < NX;
-        ln.has_in = dgx || ln.isPi || ln.isRd;
-        ln.in_off = dgx ? L::F_QD + ln.a : (ln.isPi ? L::F_G + ln.a : L::F_G + NZ);
+        const bool has_in = dgx || ln.isPi || ln.isRd || ln.isPv;
+        ln.in_off = dgx ? L::F_QD + ln.a
+                        : (ln.isPi ? L::F_G + ln.a
+                                   : (ln.isRd ? L::F_G + NZ : (ln.isPv ? (ln.a < NX ? L::F_Q + ln.a : L::F_G + NX) : 0)));
+        ln.in_step = has_in ? L::RS2 : 0;
+        // deferred stores: RL[a] from the diagonal lanes, kappa from kRt, Ri from kFu
+        ln.stDef = (ln.isP && ln.a == ln.b) || ln.isRt;
+        ln.stRi = fu;
+        ln.out_off = ln.isRt ? L::F_KAP : (fu ? L::F_RI : L::F_RL + ln.a);
+        // shuffle sources: F_uz[a] and F_uz[b]; the affine costate lanes take B'pvt through the b channel
+        ln.srcA = kFz + ln.a;
+        ln.srcB = (ln.isPv || ln.isRt) ? kRt : kFz + ln.b;
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) ln.c1[j] = 0.0;
+        for (int j = 0; j < NLD; ++j) ln.c[j] = 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c)
 #pragma unroll
@@ -1255,72 +1316,74 @@ struct Coop {
                 } else if (fu) {  // F_uu
                     v = p.B[c] * p.B[d] * (c != d ? 2.0 : 1.0);
                 }
-                if (xx || fzx || fu) ln.c1[ent(c, d)] = v;
+                if (xx || fzx || fu) ln.c[ent(c, d)] = v;
             }
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            if (xt) ln.c1[c] = p.A[c * NX + ln.a];                      // F_zz[a][theta] = sum_c A[c][a] Pt[c][theta]
-            if (fzt) ln.c1[c] = p.B[c];                                 // F_uz[theta]    = sum_c B[c] Pt[c][theta]
-            if (ln.isPi && ln.a < NX) ln.c1[c] = p.A[c * NX + ln.a];    // (Abar'pi)[a]
-            if (ln.isRd) ln.c1[c] = p.B[c];                             // B'pi
+            if (xt) ln.c[c] = p.A[c * NX + ln.a];                                   // F_zz[a][theta]
+            if (fzt) ln.c[c] = p.B[c];                                              // F_uz[theta]
+            if ((ln.isPi || ln.isPv) && ln.a < NX) ln.c[c] = p.A[c * NX + ln.a];    // (Abar'pi)[a]
+            if (ln.isRd || ln.isRt) ln.c[c] = p.B[c];                               // B'pi
         }
-        if (tt) ln.c1[0] = 1.0;                                         // F_zz[theta][theta] = Pt[theta][theta]
-        if (ln.isPi && ln.a == NX) ln.c1[NX] = 1.0;                     // (Abar'pi)[theta] = pi[theta]
+        if (tt) ln.c[0] = 1.0;                                                      // F_zz[theta][theta]
+        if (ln.isPv && ln.a == NX) ln.c[NX] = 1.0;                                  // (Abar'pv)[theta]
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) pin(ln.c[j]);
+        pin(ln.base); pin(ln.pubi); pin(ln.in_off); pin(ln.in_step); pin(ln.out_off); pin(ln.srcA); pin(ln.srcB);
         ln.ok = true;
-        ln.pend = false;
         ln.val = 0.0;
-        ln.ir = 1.0;
-        ln.d1 = ln.pub = 0.0;
-        ln.qdu = ln.in = ln.hgv = 0.0;
         ln.rt = ln.y0 = 1.0;
-        ln.la = 0.0;
-        ln.wzz = ln.wa = ln.wb = ln.wuu = 0.0;
+        ln.dmul = 0.0;
+        ln.wzz = ln.wa = ln.wb = ln.wuu = ln.hg = 0.0;
+        ln.qdu = ln.qu = ln.czz = ln.d1 = 0.0;
+        ln.ir = 1.0;
+        ln.in_ptr = nullptr;
+        ln.out_ptr = nullptr;
     }
     static LB_HD void load_type(const P& p, int t, Lane& ln) {
         const double* W = p.W[t];
-        ln.wzz = W[ln.a * NV + ln.b];
-        ln.wa = W[NZ * NV + ln.a];
-        ln.wb = W[NZ * NV + ln.b];
+        ln.wzz = ln.isP ? W[ln.a * NV + ln.b] : 0.0;
+        ln.wa = ln.plike ? W[NZ * NV + ln.a] : 0.0;
+        ln.wb = ln.isP ? W[NZ * NV + ln.b] : 0.0;
         ln.wuu = W[NZ * NV + NZ];
     }
-    // stage inputs of stage k (no dependence on the recursion: fetched before the exchange)
-    static LB_HD void fetch(const P& p, const L& l, const double* s, int k, Lane& ln) {
-        const double* r2 = s + l.r2(k);
-        ln.qdu = r2[L::F_QD + NX];
-        ln.in = ln.has_in ? r2[ln.in_off] : 0.0;
-        double hv = 0.0;
-        if (k == p.kg) {
-            if (ln.isP) hv = s[l.o_misc + L::M_HG + C::sym(ln.a, ln.b)];
-            else if (ln.isPi) hv = s[l.o_misc + L::M_GGL + ln.a];
-        }
-        ln.hgv = hv;
-    }
-    // terminal stage: Pt = Wzz + Qd (+HG), rho = 1 ; pi = g (+GGL)
-    static LB_HD void terminal(const P& p, const L& l, const double* s, Lane& ln) {
-        const int N = p.N;
-        load_type(p, C::stage_type(p, N), ln);
-        fetch(p, l, s, N, ln);
-        ln.val = ln.isP ? ln.wzz + ln.in + ln.hgv : (ln.isPi ? ln.in + ln.hgv : 0.0);
-        ln.ir = 1.0;
-        ln.rt = ln.y0 = 1.0;
-        ln.ok = true;
-        ln.pend = false;
-    }
-    // zero the pads of the exchange buffer once (read with zero coefficients)
+    // zero the exchange buffers once (pads are read with zero coefficients)
     static LB_HD void xch_init(int h, double* xch) {
         for (int j = h; j < kXch; j += 32) xch[j] = 0.0;
     }
-    static LB_HD void st1(const P& p, const L& l, const double* s, int k, int h, Lane& ln, double* xch) {
-        if (ln.isP) xch[h] = ln.val;
-        if (ln.isPi) xch[kXpi + ln.a] = ln.val;
-        fetch(p, l, s, k, ln);
+    // start of a factorisation: polytope terms of stage kg, pointers, terminal stage
+    //   Pt = Wzz + Qd (+HG), rho = 1 ; pi = g (+GGL) ; pvt = q | g_theta (+GGL+DG)
+    static LB_HD void begin(const P& p, const L& l, double* s, const double* zero, Lane& ln) {
+        const int N = p.N;
+        const double* m = s + l.o_misc;
+        double hv = 0.0;
+        if (ln.isP) hv = m[L::M_HG + C::sym(ln.a, ln.b)];
+        else if (ln.isPi) hv = m[L::M_GGL + ln.a];
+        else if (ln.isPv) hv = m[L::M_GGL + ln.a] + m[L::M_DG + ln.a];
+        ln.hg = hv;
+        load_type(p, C::stage_type(p, N), ln);
+        ln.in_ptr = ln.in_step ? s + l.r2(N) + ln.in_off : zero;
+        ln.out_ptr = s + l.r2(N) + ln.out_off;  // stage N has no factors: the first deferred store is a dummy
+        ln.val = (ln.wzz + *ln.in_ptr) + (p.kg == N ? ln.hg : 0.0);
+        ln.in_ptr -= ln.in_step;
+        ln.rt = ln.y0 = 1.0;
+        ln.dmul = 0.0;
+        ln.ok = true;
     }
-    // dot product + deferred refinement / store of the previous stage's reciprocal pivot
-    //   kprev = k + 1 (stage whose factors are pending)
-    static LB_HD void st2(const L& l, double* s, int kprev, int h, Lane& ln, const double* xch) {
+    // phase 1 of stage k: publish, fetch the stage inputs (rec = record R2 of stage k, xb = this stage's buffer)
+    static LB_HD void st1(Lane& ln, const double* rec, double* xb, bool atkg) {
+        xb[ln.pubi] = ln.val;
+        ln.qdu = rec[L::F_QD + NX];
+        ln.qu = rec[L::F_Q + NX];
+        const double in = *ln.in_ptr;
+        ln.in_ptr -= ln.in_step;
+        ln.czz = (ln.wzz + in) + (atkg ? ln.hg : 0.0);
+    }
+    // phase 2: the dot product; refinement of the previous pivot's reciprocal and the factor stores that wait for it
+    static LB_HD void st2(Lane& ln, const double* xb) {
         double v[NLD];
 #ifdef __CUDA_ARCH__
-        const double2* src = reinterpret_cast<const double2*>(xch + ln.base);
+        const double2* src = reinterpret_cast<const double2*>(xb + ln.base);
 #pragma unroll
         for (int j = 0; j < NLD / 2; ++j) {
             const double2 t = src[j];
@@ -1328,53 +1391,44 @@ struct Coop {
             v[2 * j + 1] = t.y;
         }
 #else
-        for (int j = 0; j < NLD; ++j) v[j] = xch[ln.base + j];
+        for (int j = 0; j < NLD; ++j) v[j] = xb[ln.base + j];
 #endif
         const double irn = rcp_refine(ln.rt, ln.y0);  // 1/rho of the matrix being read
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int j = 0; j < NLD; ++j) {
-            if (j & 1) a1 += ln.c1[j] * v[j];
-            else a0 += ln.c1[j] * v[j];
+            if (j & 1) a1 += ln.c[j] * v[j];
+            else a0 += ln.c[j] * v[j];
         }
         ln.d1 = a0 + a1;
-        ln.pub = ln.d1;
         ln.ir = irn;
-        if (ln.pend) {
-            if (ln.isP && ln.a == ln.b) s[l.i_L(ln.a, kprev)] = ln.la * irn;  // RL[a] of stage kprev
-            if (h == 0) s[l.i_Ri(0, kprev)] = irn;
-        }
+        if (ln.stDef) *ln.out_ptr = ln.dmul * irn;
+        if (ln.stRi) *ln.out_ptr = irn;
+        ln.out_ptr -= L::RS2;
     }
-    // fa, fb, fuu: F_uz[a], F_uz[b], F_uu (lanes kFz + a, kFz + b, kFu)
+    // phase 3.  fa, fb, fuu: d1 of lanes srcA, srcB, kFu
     static LB_HD void st3(Lane& ln, double fa, double fb, double fuu) {
         const double ir = ln.ir;
         const double Rt = (ln.wuu + ln.qdu) + fuu * ir;
-        const double La = ln.wa + fa * ir, Lb = ln.wb + fb * ir;
-        const double hz = (ln.wzz + ln.in + ln.hgv) + ln.d1 * ir;
-        const double pnew = Rt * hz - La * Lb;         // entry lanes
-        const double anew = (ln.in + ln.hgv) + ln.d1;  // adjoint lanes: pi' = g + Abar'pi (+GGL at kg)
-        const double av = lb_abs(ln.in + ln.d1);       // r_d lane: |g_u + B'pi|
-        ln.val = ln.isP ? pnew : (ln.isPi ? anew : (ln.isRd ? lb_nanmax(ln.val, av) : 0.0));
-        ln.ok = ln.ok && (Rt > 0.0);
+        const double La = ln.wa + fa * ir;
+        const double Lb = ((ln.isPv || ln.isRt) ? ln.qu : ln.wb) + fb * ir;
+        const double hz = ln.czz + ln.d1 * ir;
+        const double pnew = Rt * hz - La * Lb;            // entry lanes, affine costate lanes
+        const double anew = ln.czz + ln.d1;               // adjoint lanes: pi' = g + Abar'pi (+GGL at kg)
+        const double av = lb_abs(anew);                   // r_d lane: |g_u + B'pi|
+        const double mx = av > ln.val ? av : ln.val;
+        ln.val = ln.plike ? pnew : (ln.isRd ? mx : anew);
+        ln.ok = ln.ok && (Rt > 0.0) && !(ln.isRd && !(av < 1e300));
         ln.rt = Rt;
         ln.y0 = rcp_seed(Rt);
-        ln.la = La;
-        ln.pend = true;
+        ln.dmul = ln.isRt ? -Lb : La;
     }
-    // after stage 0: store its factors and the inverse of the theta block of P_0; the caller combines the r_d
-    // pieces (lane kRd: running max over the stages; lane kPi + NX: |pi_theta| at stage 0)
-    static LB_HD void finish(const L& l, double* s, int h, Lane& ln) {
+    // after stage 0: store its factors; returns val / rho_0 (lane NH-1: P_0[theta][theta]; lane kPv+NX: pv_theta(0))
+    static LB_HD double finish(Lane& ln) {
         const double irn = rcp_refine(ln.rt, ln.y0);
-        if (ln.pend) {
-            if (ln.isP && ln.a == ln.b) s[l.i_L(ln.a, 0)] = ln.la * irn;
-            if (h == 0) s[l.i_Ri(0, 0)] = irn;
-        }
-        if (h == NH - 1) {
-            const double ptt = ln.val * irn;
-            ln.ok = ln.ok && (ptt > 0.0);
-            s[l.o_misc + L::M_PTT] = 1.0 / ptt;
-        }
-        if (!ln.isP) ln.ok = true;
+        if (ln.stDef) *ln.out_ptr = ln.dmul * irn;
+        if (ln.stRi) *ln.out_ptr = irn;
+        return ln.val * irn;
     }
 };
 

@@ -105,7 +105,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <int NX, int NT, int NU>
 struct SmemPlan {
     using L = Layout<NX, NT, NU>;
-    static constexpr int kXchPerSlot = 40;  // >= Coop::kXch doubles per QP (even)
+    static constexpr int kXchPerSlot = 104;  // >= Coop::kXch doubles per QP (even)
     int slots, stride, xch_off, zero_off, g_off, hg_off, meta_off;  // offsets in doubles
     size_t bytes;
     __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
@@ -147,6 +147,22 @@ __device__ __forceinline__ void solve_sweeps(const Params<NX, NT, NU>& p, const 
     if (lane == 0) C::fwd_p2(l, slot);
     __syncwarp();
     if (lane < l.nb) C::fwd_p3(p, l, slot, lane, aff);
+    __syncwarp();
+}
+
+// predictor solve when the factor sweep has already run the affine backward substitution (kappa stored, d(theta)
+// at M_DTHA): block transfer matrices (homogeneous backward recursion, once per factorisation) + forward substitution
+template <int NX, int NT, int NU>
+__device__ __forceinline__ void affine_forward(const Params<NX, NT, NU>& p, const Layout<NX, NT, NU>& l, double* slot,
+                                               const double* zero_rec, int lane) {
+    using C = Core<NX, NT, NU>;
+    const int ntask = l.nb * NX;
+    for (int t = lane; t < ntask; t += 32) C::bwd_p1_T(p, l, slot, zero_rec, t);
+    if (lane < l.nb) C::fwd_p1(p, l, slot, lane, true);
+    __syncwarp();
+    if (lane == 0) C::fwd_p2(l, slot);
+    __syncwarp();
+    if (lane < l.nb) C::fwd_p3(p, l, slot, lane, true);
     __syncwarp();
 }
 
@@ -260,7 +276,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             //            QP) fused with the predictor assembly of this iteration
             // =================================================================================
             {
-                RedAsm ra{0.0, 0.0, 0.0, 0.0};
+                RedAsm ra{0.0, 0.0, 0.0, 0.0, 0.0};
                 if (iters > 0) {
                     for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra);
                 } else {
@@ -275,7 +291,9 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
                 const double rp = warp_max(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
+                const double gth = warp_sum(ra.gth);
                 if (lane == 0) {
+                    m[L::M_GTH] = gth + acc[NH + NX];
 #pragma unroll
                     for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
 #pragma unroll
@@ -299,30 +317,35 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             // =================================================================================
             const bool cert = m[L::M_LAM] >= p.inf_trigger;
             if constexpr (kCoop) {
-                CP::terminal(p, l, slot, ln);
+                CP::begin(p, l, slot, zero_rec, ln);
                 int type = C::stage_type(p, N), kseg = p.tseg[type];
-                for (int k = N - 1; k >= 0; --k) {
+                const double* rec = slot + l.r2(N - 1);
+                for (int k = N - 1; k >= 0; --k, rec -= L::RS2) {
                     if (k < kseg) {  // crossed into the previous cost segment
                         type = C::stage_type(p, k);
                         kseg = p.tseg[type];
                         CP::load_type(p, type, ln);
                     }
-                    CP::st1(p, l, slot, k, lane, ln, xch);
+                    double* const xb = xch + ((k & 1) ? CP::kBuf : 0);
+                    CP::st1(ln, rec, xb, k == p.kg);
                     __syncwarp();
-                    CP::st2(l, slot, k + 1, lane, ln, xch);
-                    const double fa = __shfl_sync(kFull, ln.pub, CP::kFz + ln.a);
-                    const double fb = __shfl_sync(kFull, ln.pub, CP::kFz + ln.b);
-                    const double fuu = __shfl_sync(kFull, ln.pub, CP::kFu);
+                    CP::st2(ln, xb);
+                    const double fa = __shfl_sync(kFull, ln.d1, ln.srcA);
+                    const double fb = __shfl_sync(kFull, ln.d1, ln.srcB);
+                    const double fuu = __shfl_sync(kFull, ln.d1, CP::kFu);
                     CP::st3(ln, fa, fb, fuu);
-                    __syncwarp();  // xch is rewritten by the next stage's st1
                 }
-                CP::finish(l, slot, lane, ln);
+                const double fin = CP::finish(ln);
                 const bool okall = __all_sync(kFull, ln.ok);
                 const double rdm = __shfl_sync(kFull, ln.val, CP::kRd);
-                const double pth = __shfl_sync(kFull, ln.val, CP::kPi + NX);
+                const double ptt = __shfl_sync(kFull, fin, NH - 1);
+                const double pvth = __shfl_sync(kFull, fin, CP::kPv + NX);
                 if (lane == 0) {
-                    m[L::M_PIV] = okall ? 1.0 : 0.0;
-                    m[L::M_RD] = lb_nanmax(rdm, lb_abs(pth));
+                    const double iptt = 1.0 / ptt;
+                    m[L::M_PIV] = (okall && ptt > 0.0) ? 1.0 : 0.0;
+                    m[L::M_PTT] = iptt;
+                    m[L::M_DTHA] = -iptt * pvth;
+                    m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
                 }
                 if (cert && lane == 0) C::adjoint_sweep(p, l, slot, true);
             } else {
@@ -341,7 +364,8 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 status = v;
                 break;
             }
-            solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, true, true);
+            if constexpr (kCoop) affine_forward<NX, NT, NU>(p, l, slot, zero_rec, lane);
+            else solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, true, true);
             LB_PROF(3)
 
             // =================================================================================

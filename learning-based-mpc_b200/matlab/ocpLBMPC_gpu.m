@@ -1,0 +1,57 @@
+function [sysHistory,art_refHistory,true_refHistory]...
+          =ocpLBMPC_gpu(x,x_wp,dx_init,dx_ref,u_wp,...
+                    N,Ts,iterations,options,opt_var,data,...
+                    A,B,Kstabil,Q,R,P,T,Mtheta,LAMBDA,PSI,m,...
+                    F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d,...
+                    sysHistory,art_refHistory,true_refHistory)
+% OCPLBMPC_GPU  drop-in for functions/ocpLBMPC.m (same 35 arguments, same 3 outputs).
+% The only change is the solver call: the fmincon-SQP solve of ocpLBMPC.m:27-31 becomes one
+% batched interior-point solve on the GPU (batch = 1 here) through lbmpc_mex -> liblbmpc_b200.so.
+% `options` (fmincon options) is accepted and ignored.
+%
+% The learned-oracle term of costLBMPC.m:27 is non-convex in the reference; here it enters as the
+% frozen per-stage offset d_k = g(x_k,u_k;data) evaluated along the previous solution
+% (lbmpc_mex('oracle',...)), i.e. one SQP/RTI linearisation per control step (DESIGN.md, H2).
+model = struct('A',A,'B',B,'K',Kstabil,'Q',Q,'R',R,'P',P,'T',T,'LAMBDA',LAMBDA,'PSI',PSI, ...
+               'F_x',F_x,'h_x',h_x,'F_u',F_u,'h_u',h_u,'F_w_N',F_w_N,'h_w_N',h_w_N, ...
+               'F_x_d',F_x_d,'h_x_d',h_x_d);
+cfg = struct('form','F','variant','LBMPC','N',N,'max_batch',1);
+h = lbmpc_mex('create', model, cfg);
+cleaner = onCleanup(@() lbmpc_mex('destroy', h));
+q = 100;                                   % moving window (ocpLBMPC.m:18)
+for k = 1:iterations
+    if k > 1
+        X = [x(1:2)-x_wp(1:2); u-u_wp];                        % ocpLBMPC.m:14
+        Y = (x_k1-x_wp) - (A*(x-x_wp) + B*(u-u_wp));           % ocpLBMPC.m:15
+        x = x_k1;
+        data = update_data(X,Y,q,k,data);                      % ocpLBMPC.m:19
+        dx = x - x_wp;
+    else
+        dx = dx_init;
+    end
+    d_off = [];
+    if size(data.X,2) > 1 || any(data.Y(:) ~= 0)
+        % inputs of the previous solution along the pre-stabilised rollout: du_k = K dx_k + c_k
+        c_prev = reshape(opt_var(1:end-m), m, N);
+        du = zeros(m*N,1); xk = dx;
+        for kk = 1:N
+            du((kk-1)*m+(1:m)) = Kstabil*xk + c_prev(:,kk);
+            xk = A*xk + B*du((kk-1)*m+(1:m));
+        end
+        d_off = lbmpc_mex('oracle', h, size(data.X,2), 0.5, 0.001, dx, du, data.X, data.Y, []);
+    end
+    out = lbmpc_mex('solve', h, dx, dx_ref, d_off, opt_var(:));    % replaces fmincon, ocpLBMPC.m:31
+    if out.status ~= 0
+        warning('lbmpc:status', 'step %d: solver status %d', k, out.status);
+    end
+    opt_var = [out.u_or_c; out.theta];
+    theta_opt = reshape(opt_var(end-m+1:end), m, 1);
+    c = reshape(opt_var(1:m), m, 1);
+    art_ref = Mtheta*theta_opt;
+    [x_k1, u] = transitionTrue(x, c, x_wp, u_wp, Kstabil, Ts);   % plant stays in MATLAB (ocpLBMPC.m:37)
+    his = [x-x_wp; u-u_wp];
+    sysHistory = [sysHistory his]; %#ok<*AGROW>
+    art_refHistory = [art_refHistory art_ref(1:m)];
+    true_refHistory = [true_refHistory dx_ref];
+end
+end

@@ -60,7 +60,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     int it = 0, st = 1;
     for (it = 0; it < p.max_iter; ++it) {
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
-        RedAsm ra{0, 0, 0, 0};
+        RedAsm ra{0, 0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) {
             if (it == 0) C::init_assemble_stage(p, l, s, k, ra);
             else C::update_assemble_stage(p, l, s, k, alpha, ra);
@@ -71,27 +71,35 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
         for (int a = 0; a < NZ; ++a) { m[L::M_GGL + a] = acc[NH + a]; m[L::M_DG + a] = acc[NH + NZ + a]; }
         m[L::M_RP] = ra.rp; m[L::M_MU] = ra.sl * p.inv_m; m[L::M_LAM] = ra.lam; m[L::M_HLAM] = ra.hl;
+        m[L::M_GTH] = ra.gth + acc[NH + NX];
         // ---- phase B: factorisation + adjoint (+ Farkas) recursions ----
         const bool cert = ra.lam >= p.inf_trigger;
         if constexpr (NT == 1 && NU == 1 && NX <= 4) {
             // 16-lane cooperative factorisation, lane-phases run as loops (kernel: __syncwarp between them)
             using CP = Coop<NX>;
-            typename CP::Lane ln[32];
-            double xch[CP::kXch];
-            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::terminal(p, l, s, ln[h]); }
+            static thread_local typename CP::Lane ln[32];
+            static thread_local double xch[CP::kXch];
+            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::begin(p, l, s, zero_rec.data(), ln[h]); }
             int type = C::stage_type(p, N);
             for (int k = N - 1; k >= 0; --k) {
                 const int t = C::stage_type(p, k);
                 if (t != type) { type = t; for (int h = 0; h < 32; ++h) CP::load_type(p, t, ln[h]); }
-                for (int h = 0; h < 32; ++h) CP::st1(p, l, s, k, h, ln[h], xch);
-                for (int h = 0; h < 32; ++h) CP::st2(l, s, k + 1, h, ln[h], xch);
+                double* xb = xch + ((k & 1) ? CP::kBuf : 0);
+                for (int h = 0; h < 32; ++h) CP::st1(ln[h], s + l.r2(k), xb, k == p.kg);
+                for (int h = 0; h < 32; ++h) CP::st2(ln[h], xb);
+                double d1[32];
+                for (int h = 0; h < 32; ++h) d1[h] = ln[h].d1;
                 for (int h = 0; h < 32; ++h)          // kernel: three warp shuffles
-                    CP::st3(ln[h], ln[CP::kFz + ln[h].a].pub, ln[CP::kFz + ln[h].b].pub, ln[CP::kFu].pub);
+                    CP::st3(ln[h], d1[ln[h].srcA], d1[ln[h].srcB], d1[CP::kFu]);
             }
             bool ok = true;
-            for (int h = 0; h < 32; ++h) { CP::finish(l, s, h, ln[h]); ok = ok && ln[h].ok; }
-            m[L::M_PIV] = ok ? 1.0 : 0.0;
-            m[L::M_RD] = lb_nanmax(ln[CP::kRd].val, lb_abs(ln[CP::kPi + NX].val));
+            double fin[32];
+            for (int h = 0; h < 32; ++h) { fin[h] = CP::finish(ln[h]); ok = ok && ln[h].ok; }
+            const double ptt = fin[NH - 1], iptt = 1.0 / ptt;
+            m[L::M_PIV] = (ok && ptt > 0.0) ? 1.0 : 0.0;
+            m[L::M_PTT] = iptt;
+            m[L::M_DTHA] = -iptt * fin[CP::kPv + NX];
+            m[L::M_RD] = lb_nanmax(ln[CP::kRd].val, lb_abs(m[L::M_GTH]));
         } else {
             C::factor_serial(p, l, s);
             C::adjoint_sweep(p, l, s, false);
@@ -100,7 +108,14 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
-        solve_sweeps(true, true);
+        if constexpr (NT == 1 && NU == 1 && NX <= 4) {   // affine backward substitution rode on the factor sweep
+            for (int t = 0; t < l.nb * NX; ++t) C::bwd_p1_T(p, l, s, zero_rec.data(), t);
+            for (int b = 0; b < l.nb; ++b) C::fwd_p1(p, l, s, b, true);
+            C::fwd_p2(l, s);
+            for (int b = l.nb - 1; b >= 0; --b) C::fwd_p3(p, l, s, b, true);
+        } else {
+            solve_sweeps(true, true);
+        }
         // ---- phase C: affine step length, sigma, corrector rhs ----
         RedStep rs{0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) C::affine_stage(p, l, s, k, rs);
@@ -127,7 +142,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // the box rows / x / u step is applied at the top of the next pass (update_assemble_stage)
     }
     if (it == p.max_iter)  // ran out of iterations: apply the last step so that the outputs are the last iterate
-        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra); }
+        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra); }
     double J = m[L::M_CCONST];
     for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k);
     for (int k = 0; k < N; ++k)
