@@ -46,6 +46,7 @@ struct Params {
     int tseg[kMaxTypes + 1];  // cost type t covers stages [tseg[t], tseg[t+1])
     unsigned rowmask;         // bit (2*j+side) set: bound (variable j, side) is finite
     double A[NX * NX], B[NX * NU], Kinit[NU * NX], Kout[NU * NX];  // row-major
+    double Apow[NX * NX];                                          // A^bm, bm = Layout::block_len(N) (blocked adjoint recursion)
     double W[kMaxTypes][NV * NV];                                  // stage Hessians, v=[x;theta;u]
     double lo[NVB], hi[NVB];
     double Lref[NZ * NX], Tm[NX * NX];
@@ -77,7 +78,7 @@ struct Layout {
     static constexpr int F_X = 0, F_U = NX, F_S = NVB, F_LB = 3 * NVB, RS1 = (5 * NVB) | 1;
     static constexpr int F_QD = 0, F_Q = NVB, F_G = 2 * NVB, F_RL = F_G + NV, F_RI = F_RL + NU * NZ,
                          F_KAP = F_RI + NU * NU, RS2 = (F_KAP + NU) | 1;
-    static constexpr int F_DX = 0, F_DU = NX, F_DXA = NVB, F_DUA = NVB + NX, RS3 = (2 * NVB) | 1;
+    static constexpr int F_DX = 0, F_DU = NX, F_DXA = NVB, F_DUA = NVB + NX, F_RDK = 2 * NVB, RS3 = (2 * NVB) | 1;
     static_assert(NV <= RS3, "Farkas scratch does not fit record R3");
     // [qd | q | g | RL] are dead once the corrector sweeps are done: the final step-length pass
     // parks the row directions ds, dl (2 x 2 NVB per stage) there
@@ -154,6 +155,33 @@ LB_HD double lb_rcp(double x) {
     return 1.0 / x;
 #endif
 }
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory addresses of the latency-critical loops.  On the device they are 32-bit shared-space
+// addresses used through ld.shared / st.shared (no generic-address arithmetic inside the loops); on
+// the host (tests/emul) they are plain pointers.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+typedef unsigned SA;
+__device__ __forceinline__ SA sa_of(const double* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ SA sa_add(SA a, int n) { return a + 8u * (unsigned)n; }
+__device__ __forceinline__ double sa_ld(SA a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sa_ld2(SA a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sa_st(SA a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+#else
+typedef double* SA;
+inline SA sa_of(const double* p) { return const_cast<double*>(p); }
+inline SA sa_add(SA a, int n) { return a + n; }
+inline double sa_ld(SA a) { return *a; }
+inline void sa_ld2(SA a, double& x, double& y) { x = a[0]; y = a[1]; }
+inline void sa_st(SA a, double v) { *a = v; }
+#endif
 
 template <int NX, int NT, int NU>
 struct Core {
@@ -667,9 +695,103 @@ struct Core {
         }
     }
 
+    // ---- the same adjoint recursion BLOCKED over the horizon (Farkas use; the transition matrix is the constant
+    //      Abar, so the block transfer matrix is A^bm from Params): P1 lanes = blocks, zero incoming costate ->
+    //      local result; P2 one lane chains the blocks; P3 lanes = blocks, true incoming costate -> per-lane
+    //      pieces of |G_red'lambda|inf and y'(G'lambda)_red, combined by the caller with warp reductions.
+    //      The vector slots of the block scratch hold the local results / incoming costates. ----
+    static LB_HD void adj_block(const P& p, const L& l, const double* s, int b, double* pi, double& nrm, double& ydot) {
+        const double* m = s + l.o_misc;
+        AB c;
+        load_ab(p, c);
+        const int lo = b * l.bm, hi = (lo + l.bm < p.N) ? lo + l.bm : p.N;
+        const double* src = s + l.r3(hi - 1);
+        const double* r1 = s + l.r1(hi - 1);
+        for (int k = hi - 1; k >= lo; --k) {
+            AdjOps o;
+            adj_load(src, r1, o);
+            adj_step(c, o, pi, nrm, ydot);
+            if (p.kg == k) {
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
+            }
+            src -= L::RS3;
+            r1 -= L::RS1;
+        }
+    }
+    static LB_HD void farkas_p1(const P& p, const L& l, double* s, int b) {
+        const double* m = s + l.o_misc;
+        double pi[NZ], nrm = 0.0, ydot = 0.0;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) pi[a] = 0.0;
+        if (b == l.nb - 1) {
+            const double* src = s + l.r3(p.N);
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) pi[a] = src[a] + (p.kg == p.N ? m[L::M_GGL + a] : 0.0);
+        }
+        adj_block(p, l, s, b, pi, nrm, ydot);
+        double* v = s + l.blk(b) + L::TS;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) v[a] = pi[a];
+    }
+    // one lane: costate entering block b from above = Abar'^bm (costate entering b+1) + local(b+1); left in the
+    // vector slot of block b+1 (block nb-1 starts from the terminal costate: its slot is not read)
+    static LB_HD void farkas_p2(const P& p, const L& l, double* s) {
+        double out[NZ];
+        {
+            const double* v = s + l.blk(l.nb - 1) + L::TS;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) out[a] = v[a];
+        }
+        for (int b = l.nb - 2; b >= 0; --b) {
+            double* v = s + l.blk(b) + L::TS;      // local result of block b (zero incoming costate)
+            double* vin = s + l.blk(b + 1) + L::TS;  // becomes the costate entering block b
+            double nv[NZ];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) {
+                double acc = v[a];
+#pragma unroll
+                for (int cc = 0; cc < NX; ++cc) acc += p.Apow[cc * NX + a] * out[cc];
+                nv[a] = acc;
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) nv[NX + t] = v[NX + t] + out[NX + t];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) {
+                vin[a] = out[a];
+                out[a] = nv[a];
+            }
+        }
+        double* v0 = s + l.blk(0) + L::TS;  // costate at stage 0 (theta part = (G_red'lambda)_theta)
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) v0[a] = out[a];
+    }
+    // incoming costate of block b (read by every block lane BEFORE lane 0's slot is reused)
+    static LB_HD void farkas_p3(const P& p, const L& l, const double* s, int b, double& nrm, double& ydot) {
+        const double* m = s + l.o_misc;
+        double pi[NZ];
+        if (b == l.nb - 1) {
+            const double* src = s + l.r3(p.N);
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) pi[a] = src[a] + (p.kg == p.N ? m[L::M_GGL + a] : 0.0);
+        } else {
+            const double* v = s + l.blk(b + 1) + L::TS;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) pi[a] = v[a];
+        }
+        adj_block(p, l, s, b, pi, nrm, ydot);
+        if (b == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                nrm = lb_nanmax(nrm, lb_abs(pi[NX + t]));
+                ydot += pi[NX + t] * m[L::M_TH + t];
+            }
+        }
+    }
+
     // ---- backward / forward substitution with the stored factors, BLOCKED over the horizon ----
-    //   backward (gradient recursion): rt = q_u + B'pv ; kap_k = -Ri rt ; pv <- q_z + Abar'pv - RL' rt
-    //   forward                      : du_k = kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k
+    //   backward (gradient recursion): rt = q_u + B'pv ; kap_k = Ri rt ; pv <- q_z + Abar'pv - RL' rt
+    //   forward                      : du_k = -kap_k - RL_k dz_k ; dx_{k+1} = A dx_k + B du_k
     // Both recursions are affine in their state, so the horizon is cut into nb blocks of bm stages and
     // one LANE per block runs them concurrently (one instruction stream for the whole warp instead of
     // one per stage chain):
@@ -726,8 +848,8 @@ struct Core {
             for (int i = 0; i < NU; ++i) {
                 double v = 0.0;
 #pragma unroll
-                for (int j = 0; j < NU; ++j) v -= o.Ri[i * NU + j] * rt[j];
-                r2[L::F_KAP + i] = v;
+                for (int j = 0; j < NU; ++j) v += o.Ri[i * NU + j] * rt[j];
+                r2[L::F_KAP + i] = v;  // kappa_n = Ri rt (the forward sweep subtracts it)
             }
         }
 #pragma unroll
@@ -855,7 +977,7 @@ struct Core {
         double du[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-            double v0 = o.kap[i], v1 = 0.0;
+            double v0 = -o.kap[i], v1 = 0.0;
 #pragma unroll
             for (int t = 0; t < NT; ++t) v0 -= o.RL[i * NZ + NX + t] * dth[t];
 #pragma unroll
@@ -1221,19 +1343,19 @@ struct Coop {
     struct Lane {
         // constants of the lane
         double c[NLD];                 // linear form over xch[base .. base+NLD)
-        int a, b, base, pubi, in_off, in_step, out_off, srcA, srcB;
+        int a, b, in_off, in_step, out_off, out_step, srcA, srcB;
         bool isP, isPi, isPv, isRd, isRt, plike, stDef, stRi;
+        SA pub[2], base[2];            // publish / read addresses in the two exchange buffers
         // constants of the cost segment / of this factorisation
         double wzz, wa, wb, wuu, hg;
         // recursion state
-        double val;                    // Pt entry | pi | pvt | running |r_d|
+        double val;                    // Pt entry | pi | pvt
         double rt, y0;                 // pivot of the matrix being published and its reciprocal seed
-        double dmul;                   // deferred factor store: L_a (diagonal lanes), -rtn (kRt)
-        bool ok;
+        double dmul;                   // deferred factor store: L_a (diagonal lanes), rtn (kRt)
         // stage temporaries handed from phase to phase
-        double qdu, qu, czz, d1, ir;
-        const double* in_ptr;          // stage input of this lane (walks the R2 records; a zero double otherwise)
-        double* out_ptr;               // deferred store target (walks the R2 records one stage behind)
+        double qdu, wbk, czz, d1, ir;
+        SA in_ptr;                     // stage input of this lane (walks the R2 records; a zero double otherwise)
+        SA out_ptr;                    // store target: deferred factors (R2, one stage behind) / |r_d| of the stage (kRd, R3)
     };
     static LB_HD double rcp_seed(double x) {
 #ifdef __CUDA_ARCH__
@@ -1261,7 +1383,7 @@ struct Coop {
         (void)v;
 #endif
     }
-    static LB_HD void lane_init(const P& p, int h, Lane& ln) {
+    static LB_HD void lane_init(const P& p, int h, double* xch, Lane& ln) {
         ln.isP = h < NH;
         ln.isPi = h >= kPi && h < kPi + NX;
         ln.isRd = h == kRd;
@@ -1283,20 +1405,29 @@ struct Coop {
         const bool xx = h < NXX, xt = (h >= NXX && h < NH - 1), tt = (h == NH - 1);
         const int fz = h - kFz;  // F_uz component for lanes kFz..kFz+NZ-1
         const bool fzx = (fz >= 0 && fz < NX), fzt = (fz == NX), fu = (h == kFu);
-        ln.base = (xt || fzt) ? oXT : (tt ? oTT : ((ln.isPi || ln.isRd) ? oPi : ((ln.isPv || ln.isRt) ? oPv : 0)));
-        // where the lane publishes its value (a private dummy slot if it has nothing to publish)
-        ln.pubi = xx ? h : (xt ? oXT + ln.a : (tt ? oTT : (ln.isPi ? oPi + ln.a : (ln.isPv ? oPv + ln.a : oDummy + (fz >= 0 && fz < NZ ? fz : (fu ? 5 : (ln.isRd ? 6 : 7)))))));
-        // stage input: Qd_a (diagonal x entries), g_a (adjoint), g_u (r_d lane), q_a / g_theta (affine costate)
+        const int base = (xt || fzt) ? oXT : (tt ? oTT : ((ln.isPi || ln.isRd) ? oPi : ((ln.isPv || ln.isRt) ? oPv : 0)));
+        // where the lane publishes its value (a never-read slot if it has nothing to publish)
+        const int pubi = xx ? h : (xt ? oXT + ln.a : (tt ? oTT : (ln.isPi ? oPi + ln.a : (ln.isPv ? oPv + ln.a
+                              : oDummy + (fz >= 0 && fz < NZ ? fz : (fu ? 5 : (ln.isRd ? 6 : 7)))))));
+        const SA x0 = sa_of(xch);
+        ln.pub[0] = sa_add(x0, pubi);
+        ln.pub[1] = sa_add(x0, kBuf + pubi);
+        ln.base[0] = sa_add(x0, base);
+        ln.base[1] = sa_add(x0, kBuf + base);
+        // stage input: Qd_a (diagonal x entries), g_a (adjoint), g_u (r_d lane), q_a / g_theta (affine costate), q_u (kRt)
         const bool dgx = ln.isP && ln.a == ln.b && ln.a < NX;
-        const bool has_in = dgx || ln.isPi || ln.isRd || ln.isPv;
+        const bool has_in = dgx || ln.isPi || ln.isRd || ln.isPv || ln.isRt;
         ln.in_off = dgx ? L::F_QD + ln.a
                         : (ln.isPi ? L::F_G + ln.a
-                                   : (ln.isRd ? L::F_G + NZ : (ln.isPv ? (ln.a < NX ? L::F_Q + ln.a : L::F_G + NX) : 0)));
+                                   : (ln.isRd ? L::F_G + NZ
+                                              : (ln.isPv ? (ln.a < NX ? L::F_Q + ln.a : L::F_G + NX) : (ln.isRt ? L::F_Q + NX : 0))));
         ln.in_step = has_in ? L::RS2 : 0;
-        // deferred stores: RL[a] from the diagonal lanes, kappa from kRt, Ri from kFu
+        // stores: RL[a] from the diagonal lanes, kappa_n = rtn/Rt from kRt, Ri from kFu (all one stage behind, record R2);
+        // |g_u + B'pi| of the stage from kRd (spare field of record R3)
         ln.stDef = (ln.isP && ln.a == ln.b) || ln.isRt;
         ln.stRi = fu;
         ln.out_off = ln.isRt ? L::F_KAP : (fu ? L::F_RI : L::F_RL + ln.a);
+        ln.out_step = ln.isRd ? L::RS3 : L::RS2;
         // shuffle sources: F_uz[a] and F_uz[b]; the affine costate lanes take B'pvt through the b channel
         ln.srcA = kFz + ln.a;
         ln.srcB = (ln.isPv || ln.isRt) ? kRt : kFz + ln.b;
@@ -1329,16 +1460,15 @@ struct Coop {
         if (ln.isPv && ln.a == NX) ln.c[NX] = 1.0;                                  // (Abar'pv)[theta]
 #pragma unroll
         for (int j = 0; j < NLD; ++j) pin(ln.c[j]);
-        pin(ln.base); pin(ln.pubi); pin(ln.in_off); pin(ln.in_step); pin(ln.out_off); pin(ln.srcA); pin(ln.srcB);
-        ln.ok = true;
+        pin(ln.in_off); pin(ln.in_step); pin(ln.out_off); pin(ln.out_step); pin(ln.srcA); pin(ln.srcB);
+        pin(ln.pub[0]); pin(ln.pub[1]); pin(ln.base[0]); pin(ln.base[1]);
         ln.val = 0.0;
         ln.rt = ln.y0 = 1.0;
         ln.dmul = 0.0;
         ln.wzz = ln.wa = ln.wb = ln.wuu = ln.hg = 0.0;
-        ln.qdu = ln.qu = ln.czz = ln.d1 = 0.0;
+        ln.qdu = ln.wbk = ln.czz = ln.d1 = 0.0;
         ln.ir = 1.0;
-        ln.in_ptr = nullptr;
-        ln.out_ptr = nullptr;
+        ln.in_ptr = ln.out_ptr = x0;
     }
     static LB_HD void load_type(const P& p, int t, Lane& ln) {
         const double* W = p.W[t];
@@ -1362,37 +1492,36 @@ struct Coop {
         else if (ln.isPv) hv = m[L::M_GGL + ln.a] + m[L::M_DG + ln.a];
         ln.hg = hv;
         load_type(p, C::stage_type(p, N), ln);
-        ln.in_ptr = ln.in_step ? s + l.r2(N) + ln.in_off : zero;
-        ln.out_ptr = s + l.r2(N) + ln.out_off;  // stage N has no factors: the first deferred store is a dummy
-        ln.val = (ln.wzz + *ln.in_ptr) + (p.kg == N ? ln.hg : 0.0);
-        ln.in_ptr -= ln.in_step;
+        ln.in_ptr = ln.in_step ? sa_of(s + l.r2(N) + ln.in_off) : sa_of(zero);
+        // stage N has no factors: the first deferred store lands in its (unused) factor fields.  The r_d lane
+        // stores in phase 3, after the pointer has moved to the stage being processed: start one record up.
+        ln.out_ptr = ln.isRd ? sa_of(s + l.r3(N) + L::F_RDK) : sa_of(s + l.r2(N) + ln.out_off);
+        ln.val = ln.isRt ? 0.0 : (ln.wzz + sa_ld(ln.in_ptr)) + (p.kg == N ? ln.hg : 0.0);
+        ln.in_ptr = sa_add(ln.in_ptr, -ln.in_step);
         ln.rt = ln.y0 = 1.0;
         ln.dmul = 0.0;
-        ln.ok = true;
     }
-    // phase 1 of stage k: publish, fetch the stage inputs (rec = record R2 of stage k, xb = this stage's buffer)
-    static LB_HD void st1(Lane& ln, const double* rec, double* xb, bool atkg) {
-        xb[ln.pubi] = ln.val;
-        ln.qdu = rec[L::F_QD + NX];
-        ln.qu = rec[L::F_Q + NX];
-        const double in = *ln.in_ptr;
-        ln.in_ptr -= ln.in_step;
-        ln.czz = (ln.wzz + in) + (atkg ? ln.hg : 0.0);
+    // phase 1 of stage k: publish, fetch the stage inputs (rec = record R2 of stage k, B = exchange buffer k & 1)
+    template <int B>
+    static LB_HD void st1(Lane& ln, SA rec, bool atkg) {
+        sa_st(ln.pub[B], ln.val);
+        ln.qdu = sa_ld(sa_add(rec, L::F_QD + NX));
+        const double qu = sa_ld(sa_add(rec, L::F_Q + NX));
+        const double in = sa_ld(ln.in_ptr);
+        ln.in_ptr = sa_add(ln.in_ptr, -ln.in_step);
+        double czz = ln.wzz + in;
+        if (atkg) czz += ln.hg;
+        ln.czz = czz;
+        double wbk = ln.wb;
+        if (ln.isPv) wbk = qu;
+        ln.wbk = wbk;
     }
     // phase 2: the dot product; refinement of the previous pivot's reciprocal and the factor stores that wait for it
-    static LB_HD void st2(Lane& ln, const double* xb) {
+    template <int B>
+    static LB_HD void st2(Lane& ln) {
         double v[NLD];
-#ifdef __CUDA_ARCH__
-        const double2* src = reinterpret_cast<const double2*>(xb + ln.base);
 #pragma unroll
-        for (int j = 0; j < NLD / 2; ++j) {
-            const double2 t = src[j];
-            v[2 * j] = t.x;
-            v[2 * j + 1] = t.y;
-        }
-#else
-        for (int j = 0; j < NLD; ++j) v[j] = xb[ln.base + j];
-#endif
+        for (int j = 0; j < NLD / 2; ++j) sa_ld2(sa_add(ln.base[B], 2 * j), v[2 * j], v[2 * j + 1]);
         const double irn = rcp_refine(ln.rt, ln.y0);  // 1/rho of the matrix being read
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -1402,33 +1531,40 @@ struct Coop {
         }
         ln.d1 = a0 + a1;
         ln.ir = irn;
-        if (ln.stDef) *ln.out_ptr = ln.dmul * irn;
-        if (ln.stRi) *ln.out_ptr = irn;
-        ln.out_ptr -= L::RS2;
+        if (ln.stDef) sa_st(ln.out_ptr, ln.dmul * irn);
+        if (ln.stRi) sa_st(ln.out_ptr, irn);
+        ln.out_ptr = sa_add(ln.out_ptr, -ln.out_step);
     }
     // phase 3.  fa, fb, fuu: d1 of lanes srcA, srcB, kFu
     static LB_HD void st3(Lane& ln, double fa, double fb, double fuu) {
         const double ir = ln.ir;
         const double Rt = (ln.wuu + ln.qdu) + fuu * ir;
         const double La = ln.wa + fa * ir;
-        const double Lb = ((ln.isPv || ln.isRt) ? ln.qu : ln.wb) + fb * ir;
-        const double hz = ln.czz + ln.d1 * ir;
-        const double pnew = Rt * hz - La * Lb;            // entry lanes, affine costate lanes
+        const double Lb = ln.wbk + fb * ir;
+        const double hz = ln.czz + ln.d1 * ir;            // kRt: rtn = q_u + (B'pvt) ir
         const double anew = ln.czz + ln.d1;               // adjoint lanes: pi' = g + Abar'pi (+GGL at kg)
-        const double av = lb_abs(anew);                   // r_d lane: |g_u + B'pi|
-        const double mx = av > ln.val ? av : ln.val;
-        ln.val = ln.plike ? pnew : (ln.isRd ? mx : anew);
-        ln.ok = ln.ok && (Rt > 0.0) && !(ln.isRd && !(av < 1e300));
+        double nv = anew;
+        if (ln.plike) nv = Rt * hz - La * Lb;             // entry lanes, affine costate lanes
+        ln.val = nv;
+        if (ln.isRd) sa_st(ln.out_ptr, lb_abs(anew));     // |g_u + B'pi| of this stage
         ln.rt = Rt;
         ln.y0 = rcp_seed(Rt);
-        ln.dmul = ln.isRt ? -Lb : La;
+        double dm = La;
+        if (ln.isRt) dm = hz;
+        ln.dmul = dm;
     }
     // after stage 0: store its factors; returns val / rho_0 (lane NH-1: P_0[theta][theta]; lane kPv+NX: pv_theta(0))
     static LB_HD double finish(Lane& ln) {
         const double irn = rcp_refine(ln.rt, ln.y0);
-        if (ln.stDef) *ln.out_ptr = ln.dmul * irn;
-        if (ln.stRi) *ln.out_ptr = irn;
+        if (ln.stDef) sa_st(ln.out_ptr, ln.dmul * irn);
+        if (ln.stRi) sa_st(ln.out_ptr, irn);
         return ln.val * irn;
+    }
+    // pivots and dual residual of the sweep, stage k (lanes stride over the stages afterwards)
+    static LB_HD void check_stage(const L& l, const double* s, int k, bool& ok, double& rd) {
+        const double ri = s[l.r2(k) + L::F_RI];
+        ok = ok && (ri > 0.0) && (ri < 1e300);
+        rd = lb_nanmax(rd, s[l.r3(k) + L::F_RDK]);
     }
 };
 

@@ -208,7 +208,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
     typename CP::Lane ln;
     double* const xch = smem + plan.xch_off + warp * SmemPlan<NX, NT, NU>::kXchPerSlot;
     if constexpr (kCoop) {
-        CP::lane_init(p, lane, ln);
+        CP::lane_init(p, lane, xch, ln);
         CP::xch_init(lane, xch);
     }
     const double* const zero_rec = smem + plan.zero_off;
@@ -319,25 +319,38 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             if constexpr (kCoop) {
                 CP::begin(p, l, slot, zero_rec, ln);
                 int type = C::stage_type(p, N), kseg = p.tseg[type];
-                const double* rec = slot + l.r2(N - 1);
-                for (int k = N - 1; k >= 0; --k, rec -= L::RS2) {
-                    if (k < kseg) {  // crossed into the previous cost segment
-                        type = C::stage_type(p, k);
-                        kseg = p.tseg[type];
-                        CP::load_type(p, type, ln);
-                    }
-                    double* const xb = xch + ((k & 1) ? CP::kBuf : 0);
-                    CP::st1(ln, rec, xb, k == p.kg);
-                    __syncwarp();
-                    CP::st2(ln, xb);
-                    const double fa = __shfl_sync(kFull, ln.d1, ln.srcA);
-                    const double fb = __shfl_sync(kFull, ln.d1, ln.srcB);
-                    const double fuu = __shfl_sync(kFull, ln.d1, CP::kFu);
-                    CP::st3(ln, fa, fb, fuu);
+                SA rec = sa_of(slot + l.r2(N - 1));
+                int k = N - 1;
+#define LB_STAGE(B)                                                          \
+    {                                                                        \
+        if (k < kseg) { /* crossed into the previous cost segment */         \
+            type = C::stage_type(p, k);                                      \
+            kseg = p.tseg[type];                                             \
+            CP::load_type(p, type, ln);                                      \
+        }                                                                    \
+        CP::template st1<B>(ln, rec, k == p.kg);                             \
+        __syncwarp();                                                        \
+        CP::template st2<B>(ln);                                             \
+        const double fa = __shfl_sync(kFull, ln.d1, ln.srcA);                \
+        const double fb = __shfl_sync(kFull, ln.d1, ln.srcB);                \
+        const double fuu = __shfl_sync(kFull, ln.d1, CP::kFu);               \
+        CP::st3(ln, fa, fb, fuu);                                            \
+        rec = sa_add(rec, -L::RS2);                                          \
+        --k;                                                                 \
+    }
+                if (!(k & 1)) LB_STAGE(0)
+                while (k >= 1) {  // k odd here: exchange buffer 1, then 0
+                    LB_STAGE(1)
+                    LB_STAGE(0)
                 }
+#undef LB_STAGE
                 const double fin = CP::finish(ln);
-                const bool okall = __all_sync(kFull, ln.ok);
-                const double rdm = __shfl_sync(kFull, ln.val, CP::kRd);
+                __syncwarp();
+                bool okl = true;
+                double rdl = 0.0;
+                for (int kk = lane; kk < N; kk += 32) CP::check_stage(l, slot, kk, okl, rdl);
+                const bool okall = __all_sync(kFull, okl);
+                const double rdm = warp_max_nan(rdl);
                 const double ptt = __shfl_sync(kFull, fin, NH - 1);
                 const double pvth = __shfl_sync(kFull, fin, CP::kPv + NX);
                 if (lane == 0) {
@@ -347,7 +360,21 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     m[L::M_DTHA] = -iptt * pvth;
                     m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
                 }
-                if (cert && lane == 0) C::adjoint_sweep(p, l, slot, true);
+                if (cert) {  // Farkas recursion, blocked over the horizon (lanes = blocks)
+                    __syncwarp();
+                    if (lane < l.nb) C::farkas_p1(p, l, slot, lane);
+                    __syncwarp();
+                    if (lane == 0) C::farkas_p2(p, l, slot);
+                    __syncwarp();
+                    double nrm = 0.0, yd = 0.0;
+                    if (lane < l.nb) C::farkas_p3(p, l, slot, lane, nrm, yd);
+                    nrm = warp_max_nan(nrm);
+                    yd = warp_sum(yd);
+                    if (lane == 0) {
+                        m[L::M_CERT] = nrm;
+                        m[L::M_HLAM] += yd;
+                    }
+                }
             } else {
                 if (lane == 0) C::factor_serial(p, l, slot);
                 else if (lane == 1) C::adjoint_sweep(p, l, slot, false);

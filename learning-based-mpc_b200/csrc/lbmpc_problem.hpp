@@ -233,6 +233,21 @@ inline Params<NX, NT, NU> to_params(const HostProblem& hp) {
     for (int t = 0; t <= kMaxTypes; ++t) p.tseg[t] = hp.tseg[t];
     p.rowmask = hp.rowmask;
     for (int i = 0; i < NX * NX; ++i) p.A[i] = hp.A[i];
+    {  // A^bm for the blocked adjoint recursion
+        const int bm = Layout<NX, NT, NU>::block_len(hp.N);
+        double acc[NX * NX], tmp[NX * NX];
+        for (int i = 0; i < NX * NX; ++i) acc[i] = (i / NX == i % NX) ? 1.0 : 0.0;
+        for (int r = 0; r < bm; ++r) {
+            for (int i = 0; i < NX; ++i)
+                for (int j = 0; j < NX; ++j) {
+                    double v = 0.0;
+                    for (int k = 0; k < NX; ++k) v += acc[i * NX + k] * hp.A[k * NX + j];
+                    tmp[i * NX + j] = v;
+                }
+            for (int i = 0; i < NX * NX; ++i) acc[i] = tmp[i];
+        }
+        for (int i = 0; i < NX * NX; ++i) p.Apow[i] = acc[i];
+    }
     for (int i = 0; i < NX * NU; ++i) p.B[i] = hp.B[i];
     for (int i = 0; i < NU * NX; ++i) { p.Kinit[i] = hp.Kinit[i]; p.Kout[i] = hp.Kout[i]; }
     for (int t = 0; t < hp.ntypes; ++t)

@@ -79,32 +79,54 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
             using CP = Coop<NX>;
             static thread_local typename CP::Lane ln[32];
             static thread_local double xch[CP::kXch];
-            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, ln[h]); CP::xch_init(h, xch); CP::begin(p, l, s, zero_rec.data(), ln[h]); }
+            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, xch, ln[h]); CP::xch_init(h, xch); CP::begin(p, l, s, zero_rec.data(), ln[h]); }
             int type = C::stage_type(p, N);
             for (int k = N - 1; k >= 0; --k) {
                 const int t = C::stage_type(p, k);
                 if (t != type) { type = t; for (int h = 0; h < 32; ++h) CP::load_type(p, t, ln[h]); }
-                double* xb = xch + ((k & 1) ? CP::kBuf : 0);
-                for (int h = 0; h < 32; ++h) CP::st1(ln[h], s + l.r2(k), xb, k == p.kg);
-                for (int h = 0; h < 32; ++h) CP::st2(ln[h], xb);
+                double* rec = s + l.r2(k);
+                if (k & 1) {
+                    for (int h = 0; h < 32; ++h) CP::template st1<1>(ln[h], rec, k == p.kg);
+                    for (int h = 0; h < 32; ++h) CP::template st2<1>(ln[h]);
+                } else {
+                    for (int h = 0; h < 32; ++h) CP::template st1<0>(ln[h], rec, k == p.kg);
+                    for (int h = 0; h < 32; ++h) CP::template st2<0>(ln[h]);
+                }
                 double d1[32];
                 for (int h = 0; h < 32; ++h) d1[h] = ln[h].d1;
                 for (int h = 0; h < 32; ++h)          // kernel: three warp shuffles
                     CP::st3(ln[h], d1[ln[h].srcA], d1[ln[h].srcB], d1[CP::kFu]);
             }
             bool ok = true;
-            double fin[32];
-            for (int h = 0; h < 32; ++h) { fin[h] = CP::finish(ln[h]); ok = ok && ln[h].ok; }
+            double fin[32], rdm = 0.0;
+            for (int h = 0; h < 32; ++h) fin[h] = CP::finish(ln[h]);
+            for (int k = 0; k < N; ++k) CP::check_stage(l, s, k, ok, rdm);
             const double ptt = fin[NH - 1], iptt = 1.0 / ptt;
             m[L::M_PIV] = (ok && ptt > 0.0) ? 1.0 : 0.0;
             m[L::M_PTT] = iptt;
             m[L::M_DTHA] = -iptt * fin[CP::kPv + NX];
-            m[L::M_RD] = lb_nanmax(ln[CP::kRd].val, lb_abs(m[L::M_GTH]));
+            m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
         } else {
             C::factor_serial(p, l, s);
             C::adjoint_sweep(p, l, s, false);
         }
-        if (cert) C::adjoint_sweep(p, l, s, true);
+        if (cert) {
+            if constexpr (NT == 1 && NU == 1 && NX <= 4) {   // blocked Farkas recursion (kernel: lanes = blocks)
+                for (int b = 0; b < l.nb; ++b) C::farkas_p1(p, l, s, b);
+                C::farkas_p2(p, l, s);
+                double nrm = 0.0, yd = 0.0;
+                for (int b = 0; b < l.nb; ++b) {
+                    double n1 = 0.0, y1 = 0.0;
+                    C::farkas_p3(p, l, s, b, n1, y1);
+                    nrm = lb_nanmax(nrm, n1);
+                    yd += y1;
+                }
+                m[L::M_CERT] = nrm;
+                m[L::M_HLAM] += yd;
+            } else {
+                C::adjoint_sweep(p, l, s, true);
+            }
+        }
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
