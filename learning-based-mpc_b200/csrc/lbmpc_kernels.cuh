@@ -219,11 +219,19 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
     // optional phase timing (diagnostic): lane 0 of warp 0 of CTA 0 accumulates clock64 deltas per phase
     const bool prof_on = io.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long t_prev = prof_on ? clock64() : 0;
+    long long t_prev2 = t_prev;
 #define LB_PROF(idx)                                           \
     if (prof_on) {                                             \
         const long long t_now = clock64();                     \
         io.prof[idx] += (unsigned long long)(t_now - t_prev);  \
         t_prev = t_now;                                        \
+        t_prev2 = t_now;                                       \
+    }
+#define LB_PROF2(idx)                                           \
+    if (prof_on) {                                              \
+        const long long t_now = clock64();                      \
+        io.prof[idx] += (unsigned long long)(t_now - t_prev2);  \
+        t_prev2 = t_now;                                        \
     }
 
     for (;;) {
@@ -284,10 +292,12 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
                 }
                 __syncwarp();  // x_kg of the new iterate is read by the polytope rows
+                LB_PROF2(13)
                 double acc[NACC];
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
                 for (int i = lane; i < p.ng; i += 32) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
+                LB_PROF2(14)
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = warp_sum(acc[a]);
                 const double rp = warp_max(ra.rp), sl = warp_sum(ra.sl), lam = warp_max(ra.lam), hl = warp_sum(ra.hl);
@@ -308,6 +318,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 }
                 __syncwarp();
             }
+            LB_PROF2(15)
             LB_PROF(1)
             if (iters >= p.max_iter) break;
 
@@ -318,6 +329,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             const bool cert = m[L::M_LAM] >= p.inf_trigger;
             if constexpr (kCoop) {
                 CP::begin(p, l, slot, zero_rec, ln);
+                LB_PROF2(9)
                 int type = C::stage_type(p, N), kseg = p.tseg[type];
                 SA rec = sa_of(slot + l.r2(N - 1));
                 int k = N - 1;
@@ -344,6 +356,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     LB_STAGE(0)
                 }
 #undef LB_STAGE
+                LB_PROF2(10)
                 const double fin = CP::finish(ln);
                 __syncwarp();
                 bool okl = true;
@@ -360,6 +373,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     m[L::M_DTHA] = -iptt * pvth;
                     m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
                 }
+                LB_PROF2(11)
                 if (cert) {  // Farkas recursion, blocked over the horizon (lanes = blocks)
                     __syncwarp();
                     if (lane < l.nb) C::farkas_p1(p, l, slot, lane);
@@ -381,6 +395,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 else if (lane == 2 && cert) C::adjoint_sweep(p, l, slot, true);
             }
             __syncwarp();
+            LB_PROF2(12)
             LB_PROF(2)
 
             // =================================================================================
@@ -485,6 +500,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         LB_PROF(8)
     }
 #undef LB_PROF
+#undef LB_PROF2
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -17,5 +17,5 @@ if os.environ.get("LBMPC_PHASES"):
     out = sol.solve_batch(dx0)
     ph = sol.phase_cycles(False)
     it = max(ph.pop("iterations"), 1)
-    print("phase cycles per iteration of warp 0 of CTA 0 (", it, "iterations ):", {k: v // it for k, v in ph.items()})
+    print("phase cycles/iter (", it, "it):", {k: v // it for k, v in ph.items()})
 print(form, variant, N, nb, "kernel_ms", sol.last_kernel_ms, "iters_mean", out["iters"].mean(), "status", np.bincount(out["status"]))
