@@ -82,9 +82,10 @@ typedef struct lbmpc_config {
     double delta;              /* C-form stage weight (DMS_tracking_LMPC_casadi.m:84); ignored in F-form */
     double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1, 100 |lambda|inf)      */
     double tol_mu;             /* 0 -> 1e-10  complementarity gap                                  */
-    double inf_radius;         /* 0 -> auto   Farkas test radius R: status 2 when h'lambda < 0 and
-                                  |G'lambda|inf R <= -h'lambda (reduced space); auto = 2 x (sum of input
-                                  bounds + 10 per unbounded variable)                               */
+    double inf_radius;         /* 0 -> auto   Farkas test: status 2 when h'lambda < 0 and
+                                  2 sum_j |(G'lambda)_j| ybar_j <= -h'lambda in the reduced space y = [u;theta], ybar_j
+                                  = input bound (10 per unbounded variable); a value R > 0 replaces the factor 2
+                                  by R / sum_j ybar_j (i.e. R plays the role of a radius of the feasible set)  */
     int32_t max_iter;          /* 0 -> 60                                                          */
     int64_t max_batch;         /* largest batch of one solve call (device I/O staging is sized on it) */
     int32_t pointers_on_device;/* 0: batch arrays are host pointers (calls are synchronous);

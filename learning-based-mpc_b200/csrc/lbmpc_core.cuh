@@ -50,7 +50,10 @@ struct Params {
     double W[kMaxTypes][NV * NV];                                  // stage Hessians, v=[x;theta;u]
     double lo[NVB], hi[NVB];
     double Lref[NZ * NX], Tm[NX * NX];
-    double tol_res, tol_mu, inf_trigger, inf_radius, inv_m;
+    double tol_res, tol_mu, inf_trigger, inv_m;
+    // Farkas test: status 2 when h_red'lambda < 0 and inf_scale * sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda, ybar_j an
+    // upper bound of |y_j| on the feasible set: fk_u (input bound) inside the stage range of the input rows, fk_free else
+    double fk_u[NU], fk_free, inf_scale;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -621,13 +624,14 @@ struct Core {
 #pragma unroll
         for (int i = 0; i < NU; ++i) o.u[i] = r1[L::F_U + i];
     }
-    static LB_HD void adj_step(const AB& c, const AdjOps& o, double* pi, double& nrm, double& ydot) {
+    // wu: weights of the certificate norm (Farkas use: nrm accumulates sum |v| wu) or nullptr (dual residual: max |v|)
+    static LB_HD void adj_step(const AB& c, const AdjOps& o, double* pi, double& nrm, double& ydot, const double* wu) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
             double v = o.g[NZ + i];
 #pragma unroll
             for (int cc = 0; cc < NX; ++cc) v += c.B[cc * NU + i] * pi[cc];
-            nrm = lb_nanmax(nrm, lb_abs(v));
+            nrm = wu ? nrm + lb_abs(v) * wu[i] : lb_nanmax(nrm, lb_abs(v));
             ydot += v * o.u[i];
         }
         double np_[NX];
@@ -643,13 +647,18 @@ struct Core {
 #pragma unroll
         for (int t = 0; t < NT; ++t) pi[NX + t] += o.g[NX + t];
     }
+    static LB_HD void farkas_weights(const P& p, int k, double* wu) {
+        const bool in = k >= p.ku0 && k <= p.ku1;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) wu[i] = in ? p.fk_u[i] : p.fk_free;
+    }
     static LB_HD void adjoint_sweep(const P& p, const L& l, double* s, bool farkas) {
         double pi[NZ];
         double* m = s + l.o_misc;
         const int N = p.N;
         AB c;
         load_ab(p, c);
-        double nrm = 0.0, ydot = 0.0;
+        double nrm = 0.0, ydot = 0.0, wu[NU];
         const int step = farkas ? L::RS3 : L::RS2;
         const double* src = s + (farkas ? l.r3(N) : l.r2(N) + L::F_G);
         const double* r1 = s + l.r1(N - 1);
@@ -661,7 +670,8 @@ struct Core {
         int k = N - 1;
         for (; k >= 1; k -= 2) {
             adj_load(src - step, r1 - L::RS1, o1);
-            adj_step(c, o0, pi, nrm, ydot);
+            farkas_weights(p, k, wu);
+            adj_step(c, o0, pi, nrm, ydot, farkas ? wu : nullptr);
             if (p.kg == k) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
@@ -669,14 +679,16 @@ struct Core {
             src -= 2 * step;
             r1 -= 2 * L::RS1;
             adj_load(k >= 2 ? src : src + step, k >= 2 ? r1 : r1 + L::RS1, o0);
-            adj_step(c, o1, pi, nrm, ydot);
+            farkas_weights(p, k - 1, wu);
+            adj_step(c, o1, pi, nrm, ydot, farkas ? wu : nullptr);
             if (p.kg == k - 1) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
             }
         }
         if (k == 0) {
-            adj_step(c, o0, pi, nrm, ydot);
+            farkas_weights(p, 0, wu);
+            adj_step(c, o0, pi, nrm, ydot, farkas ? wu : nullptr);
             if (p.kg == 0) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
@@ -684,7 +696,7 @@ struct Core {
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            nrm = lb_nanmax(nrm, lb_abs(pi[NX + t]));
+            nrm = farkas ? nrm + lb_abs(pi[NX + t]) * p.fk_free : lb_nanmax(nrm, lb_abs(pi[NX + t]));
             ydot += pi[NX + t] * m[L::M_TH + t];
         }
         if (farkas) {
@@ -698,7 +710,7 @@ struct Core {
     // ---- the same adjoint recursion BLOCKED over the horizon (Farkas use; the transition matrix is the constant
     //      Abar, so the block transfer matrix is A^bm from Params): P1 lanes = blocks, zero incoming costate ->
     //      local result; P2 one lane chains the blocks; P3 lanes = blocks, true incoming costate -> per-lane
-    //      pieces of |G_red'lambda|inf and y'(G'lambda)_red, combined by the caller with warp reductions.
+    //      pieces of sum_j |(G_red'lambda)_j| ybar_j and y'(G'lambda)_red, combined by the caller with warp reductions.
     //      The vector slots of the block scratch hold the local results / incoming costates. ----
     static LB_HD void adj_block(const P& p, const L& l, const double* s, int b, double* pi, double& nrm, double& ydot) {
         const double* m = s + l.o_misc;
@@ -709,8 +721,10 @@ struct Core {
         const double* r1 = s + l.r1(hi - 1);
         for (int k = hi - 1; k >= lo; --k) {
             AdjOps o;
+            double wu[NU];
             adj_load(src, r1, o);
-            adj_step(c, o, pi, nrm, ydot);
+            farkas_weights(p, k, wu);
+            adj_step(c, o, pi, nrm, ydot, wu);
             if (p.kg == k) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) pi[a] += m[L::M_GGL + a];
@@ -783,7 +797,7 @@ struct Core {
         if (b == 0) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                nrm = lb_nanmax(nrm, lb_abs(pi[NX + t]));
+                nrm += lb_abs(pi[NX + t]) * p.fk_free;
                 ydot += pi[NX + t] * m[L::M_TH + t];
             }
         }
@@ -1280,7 +1294,7 @@ struct Core {
         if (!pivots_ok || !(rd == rd) || !(rp == rp) || !(mu == mu) || isinf(rd) || isinf(mu)) return 3;
         const double rd_tol = p.tol_res * (100.0 * lam > 1.0 ? 100.0 * lam : 1.0);
         if (rd < rd_tol && rp < p.tol_res && mu < p.tol_mu) return 0;
-        if (cert && m[L::M_HLAM] < 0.0 && m[L::M_CERT] * p.inf_radius <= -m[L::M_HLAM]) return 2;
+        if (cert && m[L::M_HLAM] < 0.0 && m[L::M_CERT] * p.inf_scale <= -m[L::M_HLAM]) return 2;
         return -1;
     }
 };

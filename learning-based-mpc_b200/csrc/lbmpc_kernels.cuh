@@ -382,7 +382,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     __syncwarp();
                     double nrm = 0.0, yd = 0.0;
                     if (lane < l.nb) C::farkas_p3(p, l, slot, lane, nrm, yd);
-                    nrm = warp_max_nan(nrm);
+                    nrm = warp_sum(nrm);
                     yd = warp_sum(yd);
                     if (lane == 0) {
                         m[L::M_CERT] = nrm;

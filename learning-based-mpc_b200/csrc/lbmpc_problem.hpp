@@ -38,7 +38,8 @@ struct HostProblem {
     unsigned rowmask = 0;
     std::vector<double> A, B, Kinit, Kout, W, lo, hi, Lref, Tm;  // row-major
     std::vector<double> G, hg;                                   // G component-major [NZ][ngp]
-    double tol_res = 1e-9, tol_mu = 1e-10, inf_trigger = 1e2, inf_radius = 0.0;
+    double tol_res = 1e-9, tol_mu = 1e-10, inf_trigger = 1e2, inf_scale = 2.0;
+    std::vector<double> fk_u;
 };
 
 namespace detail {
@@ -206,19 +207,20 @@ inline int build_problem(const lbmpc_model* m, const lbmpc_config* c, HostProble
             rows += ((hp.rowmask >> (2 * j)) & 1u) + ((hp.rowmask >> (2 * j + 1)) & 1u);
         }
     hp.m_rows = rows;
-    // radius of the Farkas infeasibility test: twice an upper bound of |[u;theta]|_1 on the feasible
-    // set (box bounds where they exist, 10 per unbounded variable)
+    // Farkas infeasibility test: per-variable upper bounds ybar_j of |y_j| on the feasible set (input box bounds
+    // where they exist, 10 per unbounded variable), safety factor 2:  2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
     double Rb = 10.0 * nt;
+    hp.fk_u.assign(nu, 10.0);
+    for (int j = nx; j < nx + nu; ++j) {
+        const double bnd = std::fmax(std::fabs(hp.lo[j]), std::fabs(hp.hi[j]));
+        if (std::isfinite(bnd)) hp.fk_u[j - nx] = bnd;
+    }
     for (int k = 0; k < N; ++k)
-        for (int j = nx; j < nx + nu; ++j) {
-            const bool in = k >= hp.ku0 && k <= hp.ku1;
-            const double bnd = std::fmax(std::fabs(hp.lo[j]), std::fabs(hp.hi[j]));
-            Rb += (in && std::isfinite(bnd)) ? bnd : 10.0;
-        }
-    hp.inf_radius = 2.0 * Rb;
+        for (int j = nx; j < nx + nu; ++j) Rb += (k >= hp.ku0 && k <= hp.ku1) ? hp.fk_u[j - nx] : 10.0;
+    hp.inf_scale = 2.0;
     if (c->tol_res > 0) hp.tol_res = c->tol_res;
     if (c->tol_mu > 0) hp.tol_mu = c->tol_mu;
-    if (c->inf_radius > 0) hp.inf_radius = c->inf_radius;
+    if (c->inf_radius > 0) hp.inf_scale = c->inf_radius / Rb;  // a caller-supplied radius rescales the bounds
     if (c->max_iter > 0) hp.max_iter = c->max_iter;
     return LBMPC_OK;
 }
@@ -258,7 +260,8 @@ inline Params<NX, NT, NU> to_params(const HostProblem& hp) {
     }
     for (int i = 0; i < NZ * NX; ++i) p.Lref[i] = hp.Lref[i];
     for (int i = 0; i < NX * NX; ++i) p.Tm[i] = hp.Tm[i];
-    p.tol_res = hp.tol_res; p.tol_mu = hp.tol_mu; p.inf_trigger = hp.inf_trigger; p.inf_radius = hp.inf_radius;
+    p.tol_res = hp.tol_res; p.tol_mu = hp.tol_mu; p.inf_trigger = hp.inf_trigger; p.inf_scale = hp.inf_scale; p.fk_free = 10.0;
+    for (int i = 0; i < NU; ++i) p.fk_u[i] = hp.fk_u[i];
     p.inv_m = 1.0 / (double)hp.m_rows;
     return p;
 }

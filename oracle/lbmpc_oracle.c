@@ -21,9 +21,9 @@
  *              corrector: r_c = s.lambda + ds_a.dl_a - sigma mu ; alpha = min(1, 0.99 alpha_max)
  *              both Newton systems solved by ONE Riccati factorisation over the augmented state
  *              z = [x;theta] (backward sweep) + two backward/forward substitution sweeps
- *   infeasible when lambda is a Farkas certificate on the ball |[u;theta]|_1 <= R that contains the
- *              box-feasible set:  h_red'lambda < 0 and |G_red'lambda|_inf R <= -h_red'lambda
- *              (checked once |lambda|_inf >= 1e2; R = 2 x sum of input bounds, 10 per unbounded var)
+ *   infeasible when lambda is a Farkas certificate on the box |y_j| <= ybar_j that contains the feasible set
+ *              (y = [u;theta]):  h_red'lambda < 0 and 2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
+ *              (checked once |lambda|_inf >= 1e2; ybar = input bounds, 10 per unbounded variable)
  */
 #include "lbmpc_oracle.h"
 
@@ -59,7 +59,8 @@ struct lbo_problem {
     int ng, kg;
     double *G, *hg; /* ng*nz, ng */
     int m_rows;
-    double tol_res, tol_mu, inf_trigger, inf_radius;
+    double tol_res, tol_mu, inf_trigger, inf_scale, inf_bound_sum;
+    double fk_u[MAXNU], fk_free; /* Farkas test: upper bounds of |u_i| (inside the input-row stage range) / of a free variable */
     int max_iter;
 };
 
@@ -186,16 +187,19 @@ static void count_rows(lbo_problem *p) {
             m += isfinite(p->lo[j]) ? 1 : 0;
         }
     p->m_rows = m;
-    /* radius of the Farkas test: twice an upper bound of |[u;theta]|_1 over the feasible set
-     * (box bounds where they exist, 10 per unbounded variable) */
+    /* Farkas test: per-variable upper bounds ybar_j of |y_j| over the feasible set (input box bounds where they
+     * exist, 10 per unbounded variable), safety factor 2:
+     *     h_red'lambda < 0  and  2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda                          */
     double R = 10.0 * p->nt;
+    p->fk_free = 10.0;
+    for (int j = p->nx; j < p->nvb; ++j) {
+        const double b = fmax(fabs(p->lo[j]), fabs(p->hi[j]));
+        p->fk_u[j - p->nx] = isfinite(b) ? b : 10.0;
+    }
     for (int k = 0; k < p->N; ++k)
-        for (int j = p->nx; j < p->nvb; ++j) {
-            const int in = (k >= p->ku0 && k <= p->ku1);
-            const double b = fmax(fabs(p->lo[j]), fabs(p->hi[j]));
-            R += (in && isfinite(b)) ? b : 10.0;
-        }
-    p->inf_radius = 2.0 * R;
+        for (int j = p->nx; j < p->nvb; ++j) R += (k >= p->ku0 && k <= p->ku1) ? p->fk_u[j - p->nx] : 10.0;
+    p->inf_bound_sum = R;
+    p->inf_scale = 2.0;
 }
 
 static void set_ref_terms(lbo_problem *p, const double *T, const double *Lam, int kT) {
@@ -325,7 +329,7 @@ void lbo_set_options(lbo_problem *p, double tol_res, double tol_mu, int max_iter
     if (tol_res > 0) p->tol_res = tol_res;
     if (tol_mu > 0) p->tol_mu = tol_mu;
     if (max_iter > 0) p->max_iter = max_iter;
-    if (inf_radius > 0) p->inf_radius = inf_radius;
+    if (inf_radius > 0) p->inf_scale = inf_radius / p->inf_bound_sum; /* a caller-supplied radius rescales the bounds */
 }
 
 int lbo_num_rows(const lbo_problem *p) { return p->m_rows; }
@@ -615,7 +619,7 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
                 for (int i = 0; i < nu; ++i) {
                     double v = w->gcon[k * nv + nz + i];
                     for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * pc[c];
-                    if (fabs(v) > ci) ci = fabs(v);
+                    ci += fabs(v) * ((k >= p->ku0 && k <= p->ku1) ? p->fk_u[i] : p->fk_free);
                     ydot += v * w->u[k * nu + i];
                 }
                 for (int a = 0; a < nz; ++a) {
@@ -638,7 +642,7 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
             if (fabs(pi[nx + a]) > rdi) rdi = fabs(pi[nx + a]);
             if (pi[nx + a] != pi[nx + a]) rdi = NAN;
             if (cert) {
-                if (fabs(pc[nx + a]) > ci) ci = fabs(pc[nx + a]);
+                ci += fabs(pc[nx + a]) * p->fk_free;
                 ydot += pc[nx + a] * w->th[a];
             }
         }
@@ -780,7 +784,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
             const double rd_tol = p->tol_res * (100.0 * lam_inf > 1.0 ? 100.0 * lam_inf : 1.0);
             if (rd_inf < rd_tol && rp_inf < p->tol_res && mu < p->tol_mu) { st = LBO_ST_OPTIMAL; break; }
         }
-        if (want_cert && hlam + cert[1] < 0.0 && cert[0] * p->inf_radius <= -(hlam + cert[1])) {
+        if (want_cert && hlam + cert[1] < 0.0 && cert[0] * p->inf_scale <= -(hlam + cert[1])) {
             st = LBO_ST_INFEASIBLE; break;
         }
         forward(p, w);

@@ -118,7 +118,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
                 for (int b = 0; b < l.nb; ++b) {
                     double n1 = 0.0, y1 = 0.0;
                     C::farkas_p3(p, l, s, b, n1, y1);
-                    nrm = lb_nanmax(nrm, n1);
+                    nrm += n1;
                     yd += y1;
                 }
                 m[L::M_CERT] = nrm;
