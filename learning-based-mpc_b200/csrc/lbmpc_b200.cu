@@ -8,12 +8,14 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/lbmpc.h"
 #include "lbmpc_kernels.cuh"
+#include "lbmpc_kernel_cta.cuh"
 #include "lbmpc_problem.hpp"
 
 using namespace lbmpc;
@@ -45,6 +47,8 @@ struct lbmpc_handle {
     HostProblem hp;
     int shape = 0;  // 0: <4,1,1>  1: <2,2,2>
     int max_slots = 0, stage_g = 0, num_sms = 0;
+    int cta_blocks_per_sm[2] = {0, 0};  // [0] > 0: the CTA-per-QP latency kernel (4 warps per QP) is available: resident CTAs per SM
+    size_t cta_smem = 0;
     bool dev_ptrs = false;
     int64_t max_batch = 0;
     double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
@@ -97,6 +101,28 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io, cudaStream_t s
     return cudaGetLastError();
 }
 
+// Few QPs per SM: the launch lasts as long as its slowest QP, so the latency variant (one CTA per QP) wins; many QPs
+// per SM: the warp-per-QP kernel keeps more QPs resident.  LBMPC_KERNEL=warp|cta overrides (experiments).
+// returns 0: warp-per-QP kernel, 4 / 2: CTA-per-QP kernel with that many warps per QP
+static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
+    if (h->cta_blocks_per_sm[0] <= 0) return 0;
+    if (const char* e = getenv("LBMPC_KERNEL")) return e[0] == 'c' ? 4 : 0;   // warp | cta (tests, experiments)
+    // measured on B200 (C-form LBMPC, N = 50): one CTA per QP wins up to ~5 QPs per SM (1.2x at 1 and at 5 QPs/SM); beyond
+    // that the QPs that have to queue behind the resident CTAs cost more than the faster iterations gain
+    if (batch <= (int64_t)h->num_sms * std::min(5, h->cta_blocks_per_sm[0] + 1)) return 4;
+    return 0;
+}
+static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, int warps) {
+    const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
+    const int per_sm = h->cta_blocks_per_sm[warps == 4 ? 0 : 1];
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * per_sm, io.batch);
+    cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    ipm_kernel_cta<4, 1, 1, 4><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
+    h->launches += 1;
+    return cudaGetLastError();
+}
+
 static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int q, double inv_h2, double lambda,
                           const double* dx0, const double* du, long long du_ld, const double* X, const double* Y,
                           const double* valid, double* d_off) {
@@ -111,6 +137,10 @@ static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int
 }
 
 static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st) {
+    if (h->shape == 0) {
+        const int w = pick_kernel(h, io.batch);
+        if (w) return launch_ipm_cta(h, io, st, w);
+    }
     return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
 }
 
@@ -168,6 +198,14 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(cudaFuncSetAttribute(ipm_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     else
         CU_TRY(cudaFuncSetAttribute(ipm_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (h->shape == 0 && hp.ng <= 64) {  // latency variant: one CTA per QP (small polytope blocks only)
+        const CtaPlan<4, 1, 1> cplan(hp.N, hp.ngp);
+        if (cplan.bytes <= (size_t)max_smem) {
+            CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[0], ipm_kernel_cta<4, 1, 1, 4>, 128, cplan.bytes));
+            h->cta_smem = cplan.bytes;
+        }
+    }
     const int nz = hp.nx + hp.nt;
     CU_TRY(dmalloc(&h->dG, (size_t)nz * hp.ngp));
     CU_TRY(dmalloc(&h->dhg, (size_t)hp.ngp));

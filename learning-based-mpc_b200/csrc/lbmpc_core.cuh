@@ -390,6 +390,187 @@ struct Core {
         asm_core(p, l, s, k, rows, r, red);
     }
 
+    // ============================================================================================
+    // Row phases over ITEMS (CTA-per-QP kernel: one thread per item).  Item (k, j), j < NVB: the
+    // bounded variable j of [x;u] at stage k with its two box rows; theta_item: the theta rows of
+    // the cost gradient of stage k.  Rows that do not exist at a stage (stage_rows mask) are replaced
+    // by the neutral pair s = 1, lambda = 0 through selects.  Thread-indexed constants come from a
+    // RowTab in shared memory (the constant bank serialises divergent indices).
+    // ============================================================================================
+    struct RowTab {
+        double W[kMaxTypes][NV * NV];
+        double lo[NVB], hi[NVB];
+    };
+    static LB_HD void fill_rowtab(const P& p, RowTab& T, int tid, int nthreads) {
+        for (int i = tid; i < kMaxTypes * NV * NV; i += nthreads) T.W[i / (NV * NV)][i % (NV * NV)] = p.W[i / (NV * NV)][i % (NV * NV)];
+        for (int i = tid; i < NVB; i += nthreads) {
+            T.lo[i] = p.lo[i];
+            T.hi[i] = p.hi[i];
+        }
+    }
+    // fresh QP: s = max(h - a v, 1), lambda = 1
+    static LB_HD void init_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j) {
+        const unsigned rows = stage_rows(p, k);
+        double* r1 = s + l.r1(k);
+        const double v = r1[j];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int q = 2 * j + side;
+            const double slack = side == 0 ? T.hi[j] - v : v - T.lo[j];
+            if ((rows >> q) & 1u) {
+                r1[L::F_S + q] = slack > 1.0 ? slack : 1.0;
+                r1[L::F_LB + q] = 1.0;
+            }
+        }
+    }
+    // running QP: apply the step parked by fin_item (ds, dl in the scratch block of R2; dx, du in R3)
+    static LB_HD void upd_item(const P& p, const L& l, double* s, int k, int j, double alpha) {
+        const unsigned rows = stage_rows(p, k);
+        double* r1 = s + l.r1(k);
+        const double* r2 = s + l.r2(k);
+        const double* r3 = s + l.r3(k);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int q = 2 * j + side;
+            if ((rows >> q) & 1u) {
+                r1[L::F_S + q] += alpha * r2[q];
+                r1[L::F_LB + q] += alpha * r2[2 * NVB + q];
+            }
+        }
+        if (j < NX || k < p.N) r1[j] += alpha * r3[j];
+    }
+    // cost gradient row a of stage k: W_type(k)[a,:] v_k (+ lin at kT)
+    static LB_HD double grad_row(const P& p, const RowTab& T, const L& l, const double* s, int k, int a) {
+        const bool last = k >= p.N;
+        const double* r1 = s + l.r1(k);
+        const double* W = T.W[stage_type(p, k)] + a * NV;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < NV; ++b) {
+            const double vb = b < NX ? r1[b] : (b < NZ ? s[l.o_misc + L::M_TH + (b - NX)] : (last ? 0.0 : r1[NX + (b - NZ)]));
+            if (b & 1) a1 += W[b] * vb;
+            else a0 += W[b] * vb;
+        }
+        double g = (last && a >= NZ) ? 0.0 : a0 + a1;
+        if (k == p.kT && a < NZ) g += s[l.o_misc + L::M_LIN + a];
+        return g;
+    }
+    // theta rows of stage k: gradient only
+    static LB_HD void asm_theta_item(const P& p, const RowTab& T, const L& l, double* s, int k, RedAsm& red) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double g = grad_row(p, T, l, s, k, NX + t);
+            s[l.r2(k) + L::F_G + NX + t] = g;
+            s[l.r3(k) + NX + t] = 0.0;
+            if (t == 0) red.gth += g;
+        }
+    }
+    // predictor assembly of item (k, j): cost gradient row, barrier diagonal, Newton rhs, Farkas input, reductions
+    static LB_HD void asm_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedAsm& red) {
+        const bool last = k >= p.N;
+        const double* r1 = s + l.r1(k);
+        double* r2 = s + l.r2(k);
+        double* r3 = s + l.r3(k);
+        const int a = zidx(j);
+        const double g = grad_row(p, T, l, s, k, a);
+        const unsigned rows = stage_rows(p, k);
+        const double vj = (last && j >= NX) ? 0.0 : r1[j];
+        double qd = 0.0, gl = 0.0, gp = 0.0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int q = 2 * j + side;
+            const bool act = (rows >> q) & 1u;
+            const double S = act ? r1[L::F_S + q] : 1.0, Lm = act ? r1[L::F_LB + q] : 0.0;
+            const double slack = side == 0 ? T.hi[j] - vj : vj - T.lo[j];
+            const double rp = act ? S - slack : 0.0;
+            const double w = Lm * lb_rcp(S);
+            qd += w;
+            if (side == 0) {
+                gl += Lm;
+                gp += w * rp;
+            } else {
+                gl -= Lm;
+                gp -= w * rp;
+            }
+            red.rp = lb_max(red.rp, lb_abs(rp));
+            red.sl += S * Lm;
+            red.lam = lb_max(red.lam, Lm);
+            red.hl += Lm * slack;
+        }
+        r2[L::F_QD + j] = qd;
+        r2[L::F_Q + j] = g + gp;
+        r2[L::F_G + a] = g + gl;
+        r3[a] = gl;
+    }
+    // affine (predictor) row directions of item (k, j): step-length ratio, the three sums of mu_aff, the
+    // sigma-independent part of the corrector rhs (to q) and the coefficient of sigma*mu (to the dx/du scratch)
+    static LB_HD void aff_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedStep& red) {
+        const unsigned rows = stage_rows(p, k);
+        const double* r1 = s + l.r1(k);
+        double* r2 = s + l.r2(k);
+        double* r3 = s + l.r3(k);
+        double aj = 0.0, bj = 0.0;
+        const double v = r1[j], dva = r3[NVB + j];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int q = 2 * j + side;
+            const bool act = (rows >> q) & 1u;
+            const double S = act ? r1[L::F_S + q] : 1.0, Lm = act ? r1[L::F_LB + q] : 0.0;
+            const double slack = side == 0 ? T.hi[j] - v : v - T.lo[j];
+            const double rp = act ? S - slack : 0.0, is = lb_rcp(S), w = Lm * is;
+            const double sdva = side == 0 ? dva : -dva;
+            const double dsa = act ? -rp - sdva : 0.0, dla = -Lm - w * dsa;
+            const double rr = dsa * is;
+            red.ratio = lb_max(red.ratio, act ? lb_max(-rr, 1.0 + rr) : 0.0);
+            red.s0 += S * Lm;
+            red.s1 += S * dla + Lm * dsa;
+            red.s2 += dsa * dla;
+            const double t = w * rp - dsa * dla * is - Lm;
+            if (side == 0) {
+                aj += t;
+                bj += act ? is : 0.0;
+            } else {
+                aj -= t;
+                bj -= act ? is : 0.0;
+            }
+        }
+        if (j < NX || k < p.N) {
+            r2[L::F_Q + j] = r2[L::F_G + zidx(j)] + aj;
+            r3[j] = bj;
+        }
+    }
+    static LB_HD void corr_item(const P& p, const L& l, double* s, int k, int j, double sigmu) {
+        if (j >= NX && k >= p.N) return;
+        s[l.i_q(j, k)] += sigmu * s[l.i_dv(j, k, false)];
+    }
+    // final (corrector) row directions of item (k, j): parks ds, dl in the scratch block at the start of record
+    // R2, returns the step-length ratio
+    static LB_HD double fin_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, double sigmu) {
+        const unsigned rows = stage_rows(p, k);
+        const double* r1 = s + l.r1(k);
+        double* r2 = s + l.r2(k);
+        const double* r3 = s + l.r3(k);
+        double ratio = 0.0;
+        const double v = r1[j], dva = r3[NVB + j], dv = r3[j];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int q = 2 * j + side;
+            const bool act = (rows >> q) & 1u;
+            const double S = act ? r1[L::F_S + q] : 1.0, Lm = act ? r1[L::F_LB + q] : 1.0;
+            const double slack = side == 0 ? T.hi[j] - v : v - T.lo[j];
+            const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
+            const double sdva = side == 0 ? dva : -dva, sdv = side == 0 ? dv : -dv;
+            const double dsa = -rp - sdva, dla = -Lm - w * dsa;
+            const double ds = -rp - sdv;
+            const double rc = S * Lm + dsa * dla - sigmu;
+            const double dl = (-rc - Lm * ds) * is;
+            ratio = lb_max(ratio, act ? lb_max(-ds * is, -dl * lb_rcp(Lm)) : 0.0);
+            r2[q] = act ? ds : 0.0;
+            r2[2 * NVB + q] = act ? dl : 0.0;
+        }
+        return ratio;
+    }
+
     // row: predictor assembly of polytope row i.  acc = {HG (NH packed), gGl (NZ), dG (NZ)}
     static LB_HD void assemble_gen_row(const P& p, const L& l, const double* s, const double* G,
                                        const double* hg, int i, double* acc, RedAsm& red) {
@@ -1155,6 +1336,82 @@ struct Core {
             s[l.i_q(j, k)] += sigmu * s[l.i_dv(j, k, false)];
         }
     }
+    // ---- polytope rows, CTA-per-QP kernel: a thread per row writes the row's scalars to a row buffer
+    //      (rb: 3 x ngp doubles), then a thread per OUTPUT entry sums over the rows (no cross-thread reduction) ----
+    static LB_HD void gen_row_asm_scalars(const P& p, const L& l, const double* s, const double* G, const double* hg, int i,
+                                          double* rb, RedAsm& red) {
+        const double slack = gen_slack(p, l, s, G, hg, i);
+        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double rp = S - slack, w = Lm * lb_rcp(S), t = w * rp;
+        red.rp = lb_nanmax(red.rp, lb_abs(rp));
+        red.sl += S * Lm;
+        red.lam = lb_max(red.lam, Lm);
+        red.hl += Lm * slack;
+        rb[i] = w;
+        rb[p.ngp + i] = Lm;
+        rb[2 * p.ngp + i] = t - Lm;
+    }
+    // output e of the predictor assembly: e < NH packed Hessian entry, then G'lambda (NZ), then the rhs part dG (NZ)
+    static LB_HD double gen_output_asm(const P& p, const double* G, const double* rb, int e) {
+        int a = 0, b = 0, c = 0;
+        if (e < NH) {
+            int idx = 0;
+#pragma unroll
+            for (int aa = 0; aa < NZ; ++aa)
+#pragma unroll
+                for (int bb = aa; bb < NZ; ++bb) {
+                    if (idx == e) {
+                        a = aa;
+                        b = bb;
+                    }
+                    ++idx;
+                }
+        } else {
+            c = e < NH + NZ ? 1 : 2;
+            a = e - NH - (c - 1) * NZ;
+            b = -1;
+        }
+        const double* ga = G + a * p.ngp;
+        const double* gb = G + (b < 0 ? 0 : b) * p.ngp;
+        const double* co = rb + c * p.ngp;
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i + 1 < p.ng; i += 2) {
+            a0 += co[i] * ga[i] * (b < 0 ? 1.0 : gb[i]);
+            a1 += co[i + 1] * ga[i + 1] * (b < 0 ? 1.0 : gb[i + 1]);
+        }
+        if (p.ng & 1) a0 += co[p.ng - 1] * ga[p.ng - 1] * (b < 0 ? 1.0 : gb[p.ng - 1]);
+        return a0 + a1;
+    }
+    static LB_HD void gen_row_aff_scalars(const P& p, const L& l, const double* s, const double* G, const double* hg, int i,
+                                          double* rb, RedStep& red) {
+        const double* m = s + l.o_misc;
+        const double slack = gen_slack(p, l, s, G, hg, i);
+        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
+        double adva = 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) adva += G[a * p.ngp + i] * s[l.i_dv(a, p.kg, true)];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) adva += G[(NX + t) * p.ngp + i] * m[L::M_DTHA + t];
+        const double dsa = -rp - adva, dla = -Lm - w * dsa, rr = dsa * is;
+        red.ratio = lb_max(red.ratio, lb_max(-rr, 1.0 + rr));
+        red.s0 += S * Lm;
+        red.s1 += S * dla + Lm * dsa;
+        red.s2 += dsa * dla;
+        rb[i] = w * rp - dsa * dla * is - Lm;
+        rb[p.ngp + i] = is;
+    }
+    // corrector rhs part of component a: sum_i G[a][i] (t1_i + sigmu / s_i)
+    static LB_HD double gen_output_aff(const P& p, const double* G, const double* rb, int a, double sigmu) {
+        const double* ga = G + a * p.ngp;
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i < p.ng; ++i) {
+            a0 += ga[i] * rb[i];
+            a1 += ga[i] * rb[p.ngp + i];
+        }
+        return a0 + sigmu * a1;
+    }
+
     // polytope row i: acc[0..NZ) += G (t1 - lambda), acc[NZ..2NZ) += G / s   (dG = acc1 + sigmu acc2)
     static LB_HD void affine_gen_row(const P& p, const L& l, const double* s, const double* G,
                                      const double* hg, int i, double* acc, RedStep& red) {
@@ -1357,7 +1614,7 @@ struct Coop {
     struct Lane {
         // constants of the lane
         double c[NLD];                 // linear form over xch[base .. base+NLD)
-        int a, b, in_off, in_step, out_off, out_step, srcA, srcB;
+        int a, b, in_off, in_step, out_off, out_step, srcA, srcB, pubi, basei;
         bool isP, isPi, isPv, isRd, isRt, plike, stDef, stRi;
         SA pub[2], base[2];            // publish / read addresses in the two exchange buffers
         // constants of the cost segment / of this factorisation
@@ -1423,6 +1680,8 @@ struct Coop {
         // where the lane publishes its value (a never-read slot if it has nothing to publish)
         const int pubi = xx ? h : (xt ? oXT + ln.a : (tt ? oTT : (ln.isPi ? oPi + ln.a : (ln.isPv ? oPv + ln.a
                               : oDummy + (fz >= 0 && fz < NZ ? fz : (fu ? 5 : (ln.isRd ? 6 : 7)))))));
+        ln.pubi = pubi;
+        ln.basei = base;
         const SA x0 = sa_of(xch);
         ln.pub[0] = sa_add(x0, pubi);
         ln.pub[1] = sa_add(x0, kBuf + pubi);
@@ -1476,6 +1735,46 @@ struct Coop {
         for (int j = 0; j < NLD; ++j) pin(ln.c[j]);
         pin(ln.in_off); pin(ln.in_step); pin(ln.out_off); pin(ln.out_step); pin(ln.srcA); pin(ln.srcB);
         pin(ln.pub[0]); pin(ln.pub[1]); pin(ln.base[0]); pin(ln.base[1]);
+        ln.val = 0.0;
+        ln.rt = ln.y0 = 1.0;
+        ln.dmul = 0.0;
+        ln.wzz = ln.wa = ln.wb = ln.wuu = ln.hg = 0.0;
+        ln.qdu = ln.wbk = ln.czz = ln.d1 = 0.0;
+        ln.ir = 1.0;
+        ln.in_ptr = ln.out_ptr = x0;
+    }
+    // The lane constants are the same for every warp and every factorisation.  The CTA-per-QP kernel computes them
+    // once per CTA into a shared-memory table (field-major: conflict-free) and reloads them at the start of each
+    // factorisation, so that they occupy no registers during the other phases of the iteration.
+    static constexpr int kTabInts = 11;
+    struct LaneTab {
+        double c[NLD][32];
+        int iv[kTabInts][32];
+    };
+    static LB_HD void lane_store(const Lane& ln, int h, LaneTab& t) {
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) t.c[j][h] = ln.c[j];
+        const int flags = (ln.isP ? 1 : 0) | (ln.isPi ? 2 : 0) | (ln.isPv ? 4 : 0) | (ln.isRd ? 8 : 0) | (ln.isRt ? 16 : 0) |
+                          (ln.stDef ? 32 : 0) | (ln.stRi ? 64 : 0);
+        const int iv[kTabInts] = {ln.a, ln.b, ln.in_off, ln.in_step, ln.out_off, ln.out_step, ln.srcA, ln.srcB, ln.pubi, ln.basei, flags};
+#pragma unroll
+        for (int j = 0; j < kTabInts; ++j) t.iv[j][h] = iv[j];
+    }
+    static LB_HD void lane_load(const LaneTab& t, int h, double* xch, Lane& ln) {
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) ln.c[j] = t.c[j][h];
+        ln.a = t.iv[0][h]; ln.b = t.iv[1][h]; ln.in_off = t.iv[2][h]; ln.in_step = t.iv[3][h];
+        ln.out_off = t.iv[4][h]; ln.out_step = t.iv[5][h]; ln.srcA = t.iv[6][h]; ln.srcB = t.iv[7][h];
+        ln.pubi = t.iv[8][h]; ln.basei = t.iv[9][h];
+        const int flags = t.iv[10][h];
+        ln.isP = flags & 1; ln.isPi = flags & 2; ln.isPv = flags & 4; ln.isRd = flags & 8; ln.isRt = flags & 16;
+        ln.stDef = flags & 32; ln.stRi = flags & 64;
+        ln.plike = ln.isP || ln.isPv;
+        const SA x0 = sa_of(xch);
+        ln.pub[0] = sa_add(x0, ln.pubi);
+        ln.pub[1] = sa_add(x0, kBuf + ln.pubi);
+        ln.base[0] = sa_add(x0, ln.basei);
+        ln.base[1] = sa_add(x0, kBuf + ln.basei);
         ln.val = 0.0;
         ln.rt = ln.y0 = 1.0;
         ln.dmul = 0.0;

@@ -131,23 +131,37 @@ struct SmemPlan {
 // blocked backward + forward substitution of one QP by its warp (lanes = blocks / block x vector tasks)
 template <int NX, int NT, int NU>
 __device__ __forceinline__ void solve_sweeps(const Params<NX, NT, NU>& p, const Layout<NX, NT, NU>& l, double* slot,
-                                             const double* zero_rec, int lane, bool aff, bool with_T) {
+                                             const double* zero_rec, int lane, bool aff, bool with_T,
+                                             unsigned long long* prof = nullptr) {
     using C = Core<NX, NT, NU>;
     constexpr int NZ = NX + NT;
+    long long t0 = prof ? clock64() : 0;
+#define LB_SW(i)                                             \
+    if (prof) {                                              \
+        const long long t1 = clock64();                      \
+        prof[i] += (unsigned long long)(t1 - t0);            \
+        t0 = t1;                                             \
+    }
     const int ntask = l.nb * (with_T ? NX + 1 : 1);
     for (int t = lane; t < ntask; t += 32) C::bwd_p1(p, l, slot, zero_rec, t, with_T);
     __syncwarp();
+    LB_SW(9)
     if (lane == 0) C::bwd_p2(l, slot, aff);
     __syncwarp();
+    LB_SW(10)
     double pv[NZ];
     if (lane < l.nb) C::bwd_p3_in(p, l, slot, lane, pv);
     __syncwarp();
     if (lane < l.nb) C::bwd_p3_fwd_p1(p, l, slot, lane, pv, aff);
     __syncwarp();
+    LB_SW(11)
     if (lane == 0) C::fwd_p2(l, slot);
     __syncwarp();
+    LB_SW(12)
     if (lane < l.nb) C::fwd_p3(p, l, slot, lane, aff);
     __syncwarp();
+    LB_SW(13)
+#undef LB_SW
 }
 
 // predictor solve when the factor sweep has already run the affine backward substitution (kappa stored, d(theta)
@@ -292,7 +306,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
                 }
                 __syncwarp();  // x_kg of the new iterate is read by the polytope rows
-                LB_PROF2(13)
                 double acc[NACC];
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
@@ -329,7 +342,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             const bool cert = m[L::M_LAM] >= p.inf_trigger;
             if constexpr (kCoop) {
                 CP::begin(p, l, slot, zero_rec, ln);
-                LB_PROF2(9)
                 int type = C::stage_type(p, N), kseg = p.tseg[type];
                 SA rec = sa_of(slot + l.r2(N - 1));
                 int k = N - 1;
@@ -356,7 +368,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     LB_STAGE(0)
                 }
 #undef LB_STAGE
-                LB_PROF2(10)
                 const double fin = CP::finish(ln);
                 __syncwarp();
                 bool okl = true;
@@ -373,7 +384,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                     m[L::M_DTHA] = -iptt * pvth;
                     m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
                 }
-                LB_PROF2(11)
                 if (cert) {  // Farkas recursion, blocked over the horizon (lanes = blocks)
                     __syncwarp();
                     if (lane < l.nb) C::farkas_p1(p, l, slot, lane);
@@ -395,7 +405,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 else if (lane == 2 && cert) C::adjoint_sweep(p, l, slot, true);
             }
             __syncwarp();
-            LB_PROF2(12)
             LB_PROF(2)
 
             // =================================================================================
@@ -443,7 +452,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             // =================================================================================
             // phase D: corrector backward/forward substitution
             // =================================================================================
-            solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, false, false);
+            solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, false, false, prof_on ? io.prof : nullptr);
             LB_PROF(5)
 
             // =================================================================================

@@ -196,8 +196,8 @@ class Solver:
         out = np.zeros(16, np.uint64)
         self._check(self.lib.lbmpc_debug_phase_cycles(self.h, int(enable), _ptr(out)), "lbmpc_debug_phase_cycles")
         names = ("load_rollout", "EA_update_assemble", "B_factor_adjoint", "B2_affine_sweeps", "C_affine_step",
-                 "D_corrector_sweeps", "E_final_step", "iterations", "store", "B_begin", "B_loop", "B_finish", "B_farkas",
-                 "EA_rows", "EA_gen", "EA_reduce")
+                 "D_corrector_sweeps", "E_final_step", "iterations", "store", "D_bwd_p1", "D_bwd_p2", "D_bwd_p3_fwd_p1", "D_fwd_p2",
+                 "D_fwd_p3", "EA_gen", "EA_reduce")
         return dict(zip(names, (int(v) for v in out[:16])))
 
     def _check(self, rc, what):

@@ -222,3 +222,21 @@ def test_closed_loop_matches_oracle(models):
             if (ref["status"] == 0).all():
                 assert np.abs(got["x"][b] - ref["x"]).max() < 1e-6
                 assert np.abs(got["u"][b] - ref["u"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+@pytest.mark.parametrize("form,N,nb", [("C", 50, 300), ("F", 50, 64), ("C", 20, 33), ("C", 200, 9)])
+def test_both_solver_kernels_against_oracle(models, monkeypatch, kernel, form, N, nb):
+    """The engine has two kernels for the 4-state shape: one warp per QP (throughput) and one CTA per QP (latency, picked
+    for small batches).  Both are forced here (LBMPC_KERNEL) on the same inputs, with reference / offsets / warm start."""
+    monkeypatch.setenv("LBMPC_KERNEL", kernel)
+    mdl = models["LBMPC"]
+    rng = np.random.default_rng(11)
+    X0 = sample_ics(nb, seed=N + nb)
+    xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.05, 0.05, (nb, 1))
+    d_off = 2e-4 * rng.standard_normal((nb, N, 4))
+    warm = np.concatenate([0.02 * rng.standard_normal((nb, N)), 0.01 * rng.standard_normal((nb, 1))], axis=1)
+    sol = solver(mdl, form, "LBMPC", N, max_batch=nb)
+    P = OracleProblem(form, "LBMPC", mdl, N)
+    assert_parity(sol.solve_batch(X0), P.solve_batch(X0, nthreads=8))
+    assert_parity(sol.solve_batch(X0, xref, d_off, warm), P.solve_batch(X0, xref, d_off, warm, nthreads=8))
