@@ -110,6 +110,8 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     // measured on B200 (C-form LBMPC, N = 50): one CTA per QP wins up to ~5 QPs per SM (1.2x at 1 and at 5 QPs/SM); beyond
     // that the QPs that have to queue behind the resident CTAs cost more than the faster iterations gain
     if (batch <= (int64_t)h->num_sms * std::min(5, h->cta_blocks_per_sm[0] + 1)) return 4;
+    // long horizons: shared memory holds only 1-2 QPs per SM either way, so the four warps of a CTA are free (N = 200: 1.18x)
+    if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return 4;
     return 0;
 }
 static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, int warps) {
