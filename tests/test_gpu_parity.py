@@ -240,3 +240,29 @@ def test_both_solver_kernels_against_oracle(models, monkeypatch, kernel, form, N
     P = OracleProblem(form, "LBMPC", mdl, N)
     assert_parity(sol.solve_batch(X0), P.solve_batch(X0, nthreads=8))
     assert_parity(sol.solve_batch(X0, xref, d_off, warm), P.solve_batch(X0, xref, d_off, warm, nthreads=8))
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_iteration_cap_bad_inputs_and_options(models, monkeypatch, kernel):
+    """Verdicts other than optimal / infeasible: the iteration cap (status 1, outputs = last iterate) and non-finite
+    inputs (status 3) come out like the oracle's; a caller-supplied Farkas radius and tolerances are honoured."""
+    monkeypatch.setenv("LBMPC_KERNEL", kernel)
+    mdl = models["LBMPC"]
+    X0 = sample_ics(40, seed=9)
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=40, max_iter=4)
+    P = OracleProblem("C", "LBMPC", mdl, 50)
+    P.set_options(max_iter=4)
+    got, ref = sol.solve_batch(X0), P.solve_batch(X0, nthreads=4)
+    assert (got["status"] == 1).all() and (ref["status"] == 1).all() and (got["iters"] == 4).all()
+    assert np.abs(got["uc"] - ref["uc"]).max() < 1e-9 and np.abs(got["theta"] - ref["theta"]).max() < 1e-9
+    bad = X0.copy()
+    bad[3, 1] = np.nan
+    bad[7, 0] = np.inf
+    sol2 = solver(mdl, "C", "LBMPC", 50, max_batch=40, tol_res=1e-7, tol_mu=1e-8, inf_radius=500.0)
+    P2 = OracleProblem("C", "LBMPC", mdl, 50)
+    P2.set_options(tol_res=1e-7, tol_mu=1e-8, inf_radius=500.0)
+    got, ref = sol2.solve_batch(bad), P2.solve_batch(bad, nthreads=4)
+    assert got["status"][3] == 3 and got["status"][7] == 3 and ref["status"][3] == 3 and ref["status"][7] == 3
+    keep = np.ones(40, bool)
+    keep[[3, 7]] = False
+    assert_parity({k: v[keep] for k, v in got.items()}, {k: v[keep] for k, v in ref.items()}, tol=1e-6)
