@@ -83,8 +83,8 @@ typedef struct lbmpc_config {
     double tol_res;            /* 0 -> 1e-9   |r_p|inf and |r_d|inf / max(1, 100 |lambda|inf)      */
     double tol_mu;             /* 0 -> 1e-10  complementarity gap                                  */
     double inf_radius;         /* 0 -> auto   Farkas test: status 2 when h'lambda < 0 and
-                                  2 sum_j |(G'lambda)_j| ybar_j <= -h'lambda in the reduced space y = [u;theta], ybar_j
-                                  = input bound (10 per unbounded variable); a value R > 0 replaces the factor 2
+                                  1.01 sum_j |(G'lambda)_j| ybar_j <= -h'lambda in the reduced space y = [u;theta], ybar_j
+                                  = input bound (10 per unbounded variable); a value R > 0 replaces the factor 1.01
                                   by R / sum_j ybar_j (i.e. R plays the role of a radius of the feasible set)  */
     int32_t max_iter;          /* 0 -> 60                                                          */
     int64_t max_batch;         /* largest batch of one solve call (device I/O staging is sized on it) */

@@ -38,7 +38,7 @@ struct HostProblem {
     unsigned rowmask = 0;
     std::vector<double> A, B, Kinit, Kout, W, lo, hi, Lref, Tm;  // row-major
     std::vector<double> G, hg;                                   // G component-major [NZ][ngp]
-    double tol_res = 1e-9, tol_mu = 1e-10, inf_trigger = 1e2, inf_scale = 2.0;
+    double tol_res = 1e-9, tol_mu = 1e-10, inf_trigger = 1e2, inf_scale = 1.01;
     std::vector<double> fk_u;
 };
 
@@ -208,7 +208,9 @@ inline int build_problem(const lbmpc_model* m, const lbmpc_config* c, HostProble
         }
     hp.m_rows = rows;
     // Farkas infeasibility test: per-variable upper bounds ybar_j of |y_j| on the feasible set (input box bounds
-    // where they exist, 10 per unbounded variable), safety factor 2:  2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
+    // where they exist, 10 per unbounded variable), margin 1 % for round-off:  1.01 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
+    // (raising the box multipliers of u_j by |(G_red'lambda)_j| cancels that component exactly and costs ybar_j each: the
+    // test says the corrected lambda is an exact Farkas certificate)
     double Rb = 10.0 * nt;
     hp.fk_u.assign(nu, 10.0);
     for (int j = nx; j < nx + nu; ++j) {
@@ -217,7 +219,7 @@ inline int build_problem(const lbmpc_model* m, const lbmpc_config* c, HostProble
     }
     for (int k = 0; k < N; ++k)
         for (int j = nx; j < nx + nu; ++j) Rb += (k >= hp.ku0 && k <= hp.ku1) ? hp.fk_u[j - nx] : 10.0;
-    hp.inf_scale = 2.0;
+    hp.inf_scale = 1.01;
     if (c->tol_res > 0) hp.tol_res = c->tol_res;
     if (c->tol_mu > 0) hp.tol_mu = c->tol_mu;
     if (c->inf_radius > 0) hp.inf_scale = c->inf_radius / Rb;  // a caller-supplied radius rescales the bounds

@@ -22,7 +22,7 @@
  *              both Newton systems solved by ONE Riccati factorisation over the augmented state
  *              z = [x;theta] (backward sweep) + two backward/forward substitution sweeps
  *   infeasible when lambda is a Farkas certificate on the box |y_j| <= ybar_j that contains the feasible set
- *              (y = [u;theta]):  h_red'lambda < 0 and 2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
+ *              (y = [u;theta]):  h_red'lambda < 0 and 1.01 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
  *              (checked once |lambda|_inf >= 1e2; ybar = input bounds, 10 per unbounded variable)
  */
 #include "lbmpc_oracle.h"
@@ -188,8 +188,10 @@ static void count_rows(lbo_problem *p) {
         }
     p->m_rows = m;
     /* Farkas test: per-variable upper bounds ybar_j of |y_j| over the feasible set (input box bounds where they
-     * exist, 10 per unbounded variable), safety factor 2:
-     *     h_red'lambda < 0  and  2 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda                          */
+     * exist, 10 per unbounded variable), 1 % margin for round-off:
+     *     h_red'lambda < 0  and  1.01 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
+     * (raising the box multipliers of u_j by |(G_red'lambda)_j| cancels that component exactly at the price ybar_j each,
+     *  so the test says: the corrected lambda is an exact Farkas certificate)                                 */
     double R = 10.0 * p->nt;
     p->fk_free = 10.0;
     for (int j = p->nx; j < p->nvb; ++j) {
@@ -199,7 +201,7 @@ static void count_rows(lbo_problem *p) {
     for (int k = 0; k < p->N; ++k)
         for (int j = p->nx; j < p->nvb; ++j) R += (k >= p->ku0 && k <= p->ku1) ? p->fk_u[j - p->nx] : 10.0;
     p->inf_bound_sum = R;
-    p->inf_scale = 2.0;
+    p->inf_scale = 1.01;
 }
 
 static void set_ref_terms(lbo_problem *p, const double *T, const double *Lam, int kT) {
