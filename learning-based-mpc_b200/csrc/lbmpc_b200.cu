@@ -49,6 +49,7 @@ struct lbmpc_handle {
     int max_slots = 0, stage_g = 0, num_sms = 0;
     int cta_blocks_per_sm[2] = {0, 0};  // [0] > 0: the CTA-per-QP latency kernel (4 warps per QP) is available: resident CTAs per SM
     size_t cta_smem = 0;
+    bool cta_big = false;              // large polytope block: G stays in global memory, sums by block reduction
     bool dev_ptrs = false;
     int64_t max_batch = 0;
     double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
@@ -107,9 +108,11 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io, cudaStream_t s
 static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     if (h->cta_blocks_per_sm[0] <= 0) return 0;
     if (const char* e = getenv("LBMPC_KERNEL")) return e[0] == 'c' ? 4 : 0;   // warp | cta (tests, experiments)
-    // measured on B200 (C-form LBMPC, N = 50): one CTA per QP wins up to ~5 QPs per SM (1.2x at 1 and at 5 QPs/SM); beyond
-    // that the QPs that have to queue behind the resident CTAs cost more than the faster iterations gain
-    if (batch <= (int64_t)h->num_sms * std::min(5, h->cta_blocks_per_sm[0] + 1)) return 4;
+    // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins up to ~5 QPs per SM (1.2x at 1 and at 5
+    // QPs/SM); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
+    // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, even at 28.
+    const int per_sm = h->cta_big ? 24 : std::min(5, h->cta_blocks_per_sm[0] + 1);
+    if (batch <= (int64_t)h->num_sms * per_sm) return 4;
     // long horizons: shared memory holds only 1-2 QPs per SM either way, so the four warps of a CTA are free (N = 200: 1.18x)
     if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return 4;
     return 0;
@@ -120,7 +123,8 @@ static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io, cudaStream
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * per_sm, io.batch);
     cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    ipm_kernel_cta<4, 1, 1, 4><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
+    if (h->cta_big) ipm_kernel_cta<4, 1, 1, 4, true><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
+    else ipm_kernel_cta<4, 1, 1, 4, false><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
     h->launches += 1;
     return cudaGetLastError();
 }
@@ -200,11 +204,17 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(cudaFuncSetAttribute(ipm_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     else
         CU_TRY(cudaFuncSetAttribute(ipm_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    if (h->shape == 0 && hp.ng <= 64) {  // latency variant: one CTA per QP (small polytope blocks only)
-        const CtaPlan<4, 1, 1> cplan(hp.N, hp.ngp);
+    if (h->shape == 0) {  // latency variant: one CTA per QP
+        h->cta_big = hp.ng > 64;
+        const CtaPlan<4, 1, 1> cplan(hp.N, hp.ngp, h->cta_big);
         if (cplan.bytes <= (size_t)max_smem) {
-            CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[0], ipm_kernel_cta<4, 1, 1, 4>, 128, cplan.bytes));
+            if (h->cta_big) {
+                CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[0], ipm_kernel_cta<4, 1, 1, 4, true>, 128, cplan.bytes));
+            } else {
+                CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[0], ipm_kernel_cta<4, 1, 1, 4, false>, 128, cplan.bytes));
+            }
             h->cta_smem = cplan.bytes;
         }
     }

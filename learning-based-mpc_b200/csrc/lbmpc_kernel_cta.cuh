@@ -25,17 +25,18 @@ struct CtaPlan {
     using CP = Coop<NX>;
     int xch_off, zero_off, ltab_off, rtab_off, rb_off, red_off, g_off, hg_off, ctl_off;  // doubles
     size_t bytes;
-    __host__ __device__ CtaPlan(int N, int ngp) {
+    // big: large polytope block (G stays in global memory / L2, polytope sums by per-thread accumulation + block reduction)
+    __host__ __device__ CtaPlan(int N, int ngp, bool big) {
         const L l(N, ngp);
         int o = (l.stride + 1) & ~1;
         xch_off = o;   o += (CP::kXch + 1) & ~1;
         zero_off = o;  o += (L::RS2 + 1) & ~1;
         ltab_off = o;  o += (int)((sizeof(typename CP::LaneTab) + 15) / 16) * 2;
         rtab_off = o;  o += (int)((sizeof(typename C::RowTab) + 15) / 16) * 2;
-        rb_off = o;    o += 3 * ngp + (ngp & 1);          // polytope row buffer
-        red_off = o;   o += 8 * kCtaMaxWarps;             // per-warp partial reductions
-        g_off = o;     o += (NX + NT) * ngp;              // staged polytope matrix (component-major)
-        hg_off = o;    o += ngp + (ngp & 1);
+        rb_off = o;    o += big ? 0 : 3 * ngp + (ngp & 1);  // polytope row buffer
+        red_off = o;   o += 32 * kCtaMaxWarps;            // per-warp partial reductions
+        g_off = o;     o += big ? 0 : (NX + NT) * ngp;     // staged polytope matrix (component-major)
+        hg_off = o;    o += big ? 0 : ngp + (ngp & 1);
         ctl_off = o;   o += 4;                            // QP index (as double), spare
         bytes = (size_t)o * sizeof(double);
     }
@@ -51,28 +52,48 @@ __device__ __forceinline__ void block_reduce(double (&sum)[NSUM], double (&mx)[N
     __syncthreads();  // scratch may still be read from the previous use
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NSUM; ++i) scratch[warp * 8 + i] = sum[i];
+        for (int i = 0; i < NSUM; ++i) scratch[warp * 32 + i] = sum[i];
 #pragma unroll
-        for (int i = 0; i < NMAX; ++i) scratch[warp * 8 + NSUM + i] = mx[i];
+        for (int i = 0; i < NMAX; ++i) scratch[warp * 32 + NSUM + i] = mx[i];
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NSUM; ++i) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) v += scratch[w * 8 + i];
+        for (int w = 0; w < W; ++w) v += scratch[w * 32 + i];
         sum[i] = v;
     }
 #pragma unroll
     for (int i = 0; i < NMAX; ++i) {
         double v = scratch[NSUM + i];
 #pragma unroll
-        for (int w = 1; w < W; ++w) v = lb_nanmax(v, scratch[w * 8 + NSUM + i]);
+        for (int w = 1; w < W; ++w) v = lb_nanmax(v, scratch[w * 32 + NSUM + i]);
         mx[i] = v;
     }
 }
 
-template <int NX, int NT, int NU, int W>
+// block-wide sums of NV per-thread values; thread e < NV returns the total of element e (others: garbage)
+template <int W, int NV>
+__device__ __forceinline__ double block_sum_scatter(double (&v)[NV], double* scratch, int warp, int lane, int tid) {
+    static_assert(NV <= 32, "scratch row");
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[warp * 32 + i] = v[i];
+    }
+    __syncthreads();
+    double t = 0.0;
+    if (tid < NV) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) t += scratch[w * 32 + tid];
+    }
+    return t;
+}
+
+template <int NX, int NT, int NU, int W, bool BIG>
 __global__ void __launch_bounds__(32 * W, W == 4 ? 4 : 7)
 ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const double* __restrict__ Gglob,
                const double* __restrict__ hgglob) {
@@ -86,7 +107,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
     const L l(N, p.ngp);
-    const CtaPlan<NX, NT, NU> plan(N, p.ngp);
+    const CtaPlan<NX, NT, NU> plan(N, p.ngp, BIG);
     double* const slot = smem;
     double* const m = slot + l.o_misc;
     double* const xch = smem + plan.xch_off;
@@ -95,13 +116,15 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
     typename C::RowTab& tab = *reinterpret_cast<typename C::RowTab*>(smem + plan.rtab_off);
     double* const rb = smem + plan.rb_off;
     double* const red = smem + plan.red_off;
-    double* const Gs = smem + plan.g_off;
-    double* const hgs = smem + plan.hg_off;
+    const double* const Gs = BIG ? Gglob : smem + plan.g_off;
+    const double* const hgs = BIG ? hgglob : smem + plan.hg_off;
     double* const ctl = smem + plan.ctl_off;
 
     // ---- one-time CTA setup ----
-    for (int i = tid; i < NZ * p.ngp; i += kCtaThreads) Gs[i] = Gglob[i];
-    for (int i = tid; i < p.ngp; i += kCtaThreads) hgs[i] = hgglob[i];
+    if (!BIG) {
+        for (int i = tid; i < NZ * p.ngp; i += kCtaThreads) smem[plan.g_off + i] = Gglob[i];
+        for (int i = tid; i < p.ngp; i += kCtaThreads) smem[plan.hg_off + i] = hgglob[i];
+    }
     for (int i = tid; i < L::RS2; i += kCtaThreads) smem[plan.zero_off + i] = 0.0;
     C::fill_rowtab(p, tab, tid, kCtaThreads);
     if (warp == 0) {
@@ -183,13 +206,23 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
                 RedAsm ra{0.0, 0.0, 0.0, 0.0, 0.0};
                 for (int it = tid; it < nitems; it += kCtaThreads) C::asm_item(p, tab, l, slot, it / NVB, it % NVB, ra);
                 for (int k = tid; k <= N; k += kCtaThreads) C::asm_theta_item(p, tab, l, slot, N - k, ra);  // from the other end: spreads the work
-                for (int i = tid; i < p.ng; i += kCtaThreads) C::gen_row_asm_scalars(p, l, slot, Gs, hgs, i, rb, ra);
+                double acc[NOUT];
+                if (BIG) {
+#pragma unroll
+                    for (int a = 0; a < NOUT; ++a) acc[a] = 0.0;
+                    for (int i = tid; i < p.ng; i += kCtaThreads) C::assemble_gen_row(p, l, slot, Gs, hgs, i, acc, ra);
+                } else {
+                    for (int i = tid; i < p.ng; i += kCtaThreads) C::gen_row_asm_scalars(p, l, slot, Gs, hgs, i, rb, ra);
+                }
                 double sm[3] = {ra.sl, ra.hl, ra.gth}, mx[2] = {ra.rp, ra.lam};
                 block_reduce<W, 3, 2>(sm, mx, red, warp, lane);  // (also orders the row buffer before its readers)
-                if (tid < NOUT) {
-                    const double v = C::gen_output_asm(p, Gs, rb, tid);
-                    m[L::M_HG + tid] = v;  // HG, GGL, DG are contiguous
-                    if (tid == NH + NX) m[L::M_GTH] = sm[2] + v;
+                {
+                    const double v = BIG ? block_sum_scatter<W, NOUT>(acc, red, warp, lane, tid)
+                                         : (tid < NOUT ? C::gen_output_asm(p, Gs, rb, tid) : 0.0);
+                    if (tid < NOUT) {
+                        m[L::M_HG + tid] = v;  // HG, GGL, DG are contiguous
+                        if (tid == NH + NX) m[L::M_GTH] = sm[2] + v;
+                    }
                 }
                 if (tid == kCtaThreads - 1) {
                     m[L::M_RP] = mx[0];
@@ -289,7 +322,14 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
             {
                 RedStep rs{0.0, 0.0, 0.0, 0.0};
                 for (int it = tid; it < nitems; it += kCtaThreads) C::aff_item(p, tab, l, slot, it / NVB, it % NVB, rs);
-                for (int i = tid; i < p.ng; i += kCtaThreads) C::gen_row_aff_scalars(p, l, slot, Gs, hgs, i, rb, rs);
+                double acc[2 * NZ];
+                if (BIG) {
+#pragma unroll
+                    for (int a = 0; a < 2 * NZ; ++a) acc[a] = 0.0;
+                    for (int i = tid; i < p.ng; i += kCtaThreads) C::affine_gen_row(p, l, slot, Gs, hgs, i, acc, rs);
+                } else {
+                    for (int i = tid; i < p.ng; i += kCtaThreads) C::gen_row_aff_scalars(p, l, slot, Gs, hgs, i, rb, rs);
+                }
                 double sm[3] = {rs.s0, rs.s1, rs.s2}, mx[1] = {rs.ratio};
                 block_reduce<W, 3, 1>(sm, mx, red, warp, lane);
                 const double aaff = mx[0] > 1.0 ? 1.0 / mx[0] : 1.0;
@@ -298,7 +338,14 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
                 const double sr = mu_aff / mu;
                 sigmu = sr * sr * sr * mu;
                 for (int it = tid; it < nitems; it += kCtaThreads) C::corr_item(p, l, slot, it / NVB, it % NVB, sigmu);
-                if (tid < NZ) m[L::M_DG + tid] = C::gen_output_aff(p, Gs, rb, tid, sigmu);
+                if (BIG) {
+                    const double t = block_sum_scatter<W, 2 * NZ>(acc, red, warp, lane, tid);  // thread a: acc[a], thread NZ + a: acc[NZ + a]
+                    if (tid >= NZ && tid < 2 * NZ) red[tid] = t;                               // (row 0 of the scratch has been consumed)
+                    __syncthreads();
+                    if (tid < NZ) m[L::M_DG + tid] = t + sigmu * red[NZ + tid];
+                } else if (tid < NZ) {
+                    m[L::M_DG + tid] = C::gen_output_aff(p, Gs, rb, tid, sigmu);
+                }
             }
             __syncthreads();
             LB_PROF(4)
