@@ -135,6 +135,17 @@ int lbmpc_closed_loop(lbmpc_handle *h, int64_t batch, int32_t steps, int32_t q, 
                       double *u_hist, double *theta_hist, int32_t *iters_hist,
                       int32_t *status_hist, void *stream);
 
+/* next row of the scope table: the learned-oracle problem (costLBMPC.m:27, DMS_LBMPC_casadi.m:252-319 roll the
+ * L2NW oracle inside the optimisation, a non-convex NLP) as a SEQUENCE of QPs.  Outer iteration j = 0..sqp_iters-1:
+ *     d_k = g([x1;x2;u]_k ; X, Y) along the learned-model rollout of the previous inputs (u^-1 = warm or 0)   [lbmpc_oracle_apply]
+ *     one QP with the frozen offsets d_k, started from the previous solution                                   [lbmpc_solve_batch]
+ * Outputs are those of the last QP; du_step (batch x sqp_iters, may be NULL) = |u^j - u^{j-1}|_inf per outer iteration.
+ * C-form handles on the 4-state model; array conventions as in lbmpc_solve_batch / lbmpc_oracle_apply. */
+int lbmpc_solve_sqp(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t q, double bandwidth, double lambda,
+                    const double *dx0, const double *dx_ref, const double *X, const double *Y, const double *valid,
+                    const double *warm, double *u, double *theta, double *x_traj, double *obj, int32_t *iters,
+                    int32_t *status, double *du_step, void *stream);
+
 /* introspection used by the host mirrors, tests and bench */
 int lbmpc_num_rows(const lbmpc_handle *h);            /* inequality rows m of one QP                     */
 int lbmpc_slots_per_cta(const lbmpc_handle *h);       /* QPs resident per CTA (shared-memory bound)      */

@@ -64,6 +64,10 @@ struct lbmpc_handle {
     int64_t launches = 0;
     bool timed = false;
     LoopScratch loop;
+    // outer-iteration (SQP) scratch, grown on demand
+    int64_t sqp_batch = 0;
+    int sqp_iters = 0;
+    double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr;
 };
 
 template <int NX, int NT, int NU>
@@ -332,6 +336,83 @@ int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwid
     return LBMPC_OK;
 }
 
+int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q, double bandwidth, double lambda,
+                    const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
+                    const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
+                    int32_t* status, double* du_step, void* stream) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (batch < 0 || sqp_iters < 1) return fail(LBMPC_EINVAL, "batch must be >= 0 and sqp_iters >= 1");
+    if (batch == 0) return LBMPC_OK;
+    if (!dx0 || !X || !Y || !u || !theta || !obj || !iters || !status) return fail(LBMPC_EINVAL, "required array is NULL");
+    if (h->shape != 0 || h->hp.form != LBMPC_FORM_C)
+        return fail(LBMPC_ESHAPE, "solve_sqp: C-form handle on the 4-state Moore-Greitzer model");
+    if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
+    if (!(bandwidth > 0)) return fail(LBMPC_EINVAL, "bandwidth must be positive");
+    if (!h->dev_ptrs && batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(h->device));
+    const HostProblem& hp = h->hp;
+    const size_t b = (size_t)batch, N = hp.N, nx = hp.nx, nt = hp.nt;
+    if (h->sqp_batch < batch || h->sqp_iters < sqp_iters) {
+        cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step);
+        h->q_ulin = h->q_warm = h->q_doff = h->q_step = nullptr;
+        CU_TRY(dmalloc(&h->q_ulin, b * N)); CU_TRY(dmalloc(&h->q_warm, b * (N + nt)));
+        CU_TRY(dmalloc(&h->q_doff, b * nx * N)); CU_TRY(dmalloc(&h->q_step, b * (size_t)sqp_iters));
+        h->sqp_batch = batch; h->sqp_iters = sqp_iters;
+    }
+    // device views of the inputs / outputs
+    const double *d_dx0 = dx0, *d_ref = dx_ref, *d_X = X, *d_Y = Y, *d_V = valid, *d_warm = warm;
+    double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
+    int *d_it = iters, *d_st = status;
+    double *tX = nullptr, *tY = nullptr, *tV = nullptr;
+    if (!h->dev_ptrs) {
+        CU_TRY(dmalloc(&tX, b * 3 * q)); CU_TRY(dmalloc(&tY, b * 4 * q));
+        if (valid) CU_TRY(dmalloc(&tV, b * q));
+        CU_TRY(cudaMemcpyAsync(tX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(tY, Y, 8 * b * 4 * q, cudaMemcpyHostToDevice, st));
+        if (valid) CU_TRY(cudaMemcpyAsync(tV, valid, 8 * b * q, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, 8 * b * nx, cudaMemcpyHostToDevice, st));
+        if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, 8 * b * nx, cudaMemcpyHostToDevice, st));
+        if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, 8 * b * (N + nt), cudaMemcpyHostToDevice, st));
+        d_dx0 = h->s_dx0; d_ref = dx_ref ? h->s_ref : nullptr; d_X = tX; d_Y = tY; d_V = tV; d_warm = warm ? h->s_warm : nullptr;
+        d_u = h->s_uc; d_th = h->s_theta; d_xt = x_traj ? h->s_x : nullptr; d_obj = h->s_obj; d_it = h->s_it; d_st = h->s_st;
+    }
+    if (d_warm) CU_TRY(cudaMemcpy2DAsync(h->q_ulin, 8 * N, d_warm, 8 * (N + nt), 8 * N, b, cudaMemcpyDeviceToDevice, st));
+    else CU_TRY(cudaMemsetAsync(h->q_ulin, 0, 8 * b * N, st));
+    const double inv_h2 = 1.0 / (bandwidth * bandwidth);
+    const unsigned ug = (unsigned)((batch + 3) / 4);
+    CU_TRY(cudaEventRecord(h->ev0, st));
+    for (int j = 0; j < sqp_iters; ++j) {
+        launch_oracle(h, st, batch, q, inv_h2, lambda, d_dx0, h->q_ulin, (long long)N, d_X, d_Y, d_V, h->q_doff);
+        CU_TRY(cudaGetLastError());
+        BatchIO io{};
+        io.batch = batch; io.queue = h->dqueue; io.prof = nullptr;
+        io.dx0 = d_dx0; io.dx_ref = d_ref; io.d_off = h->q_doff; io.warm = j == 0 ? d_warm : h->q_warm;
+        io.uc = d_u; io.theta = d_th; io.xtraj = d_xt; io.obj = d_obj; io.iters = d_it; io.status = d_st;
+        CU_TRY(launch_ipm_any(h, io, st));
+        sqp_update_kernel<<<ug, 128, 0, st>>>(batch, hp.N, hp.nt, d_u, d_th, h->q_ulin, h->q_warm, du_step ? h->q_step : nullptr,
+                                              sqp_iters, j);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    if (h->dev_ptrs) {
+        if (du_step) CU_TRY(cudaMemcpyAsync(du_step, h->q_step, 8 * b * sqp_iters, cudaMemcpyDeviceToDevice, st));
+        return LBMPC_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(u, h->s_uc, 8 * b * N, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(theta, h->s_theta, 8 * b * nt, cudaMemcpyDeviceToHost, st));
+    if (x_traj) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, 8 * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(obj, h->s_obj, 8 * b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(iters, h->s_it, 4 * b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(status, h->s_st, 4 * b, cudaMemcpyDeviceToHost, st));
+    if (du_step) CU_TRY(cudaMemcpyAsync(du_step, h->q_step, 8 * b * sqp_iters, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(tX); cudaFree(tY); if (tV) cudaFree(tV);
+    return LBMPC_OK;
+}
+
 static void free_loop(LoopScratch& L) {
     cudaFree(L.x); cudaFree(L.dx0); cudaFree(L.X); cudaFree(L.Y); cudaFree(L.V); cudaFree(L.warm); cudaFree(L.uc);
     cudaFree(L.theta); cudaFree(L.obj); cudaFree(L.doff); cudaFree(L.x_init); cudaFree(L.nd); cudaFree(L.iters);
@@ -484,6 +565,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_theta); cudaFree(h->s_x); cudaFree(h->s_obj); cudaFree(h->s_it); cudaFree(h->s_st);
+    cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -725,6 +725,27 @@ __global__ void loop_init_kernel(LoopState S, const double* __restrict__ x_init,
 }
 
 // ---------------------------------------------------------------------------------------------
+// outer (SQP) iteration bookkeeping: step = |u - u_lin|inf, u_lin <- u, next warm start <- [u; theta]   (warp per QP)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sqp_update_kernel(long long batch, int N, int nt, const double* __restrict__ uc, const double* __restrict__ theta,
+                  double* __restrict__ ulin, double* __restrict__ warm2, double* __restrict__ step, int step_ld, int j) {
+    const int lane = threadIdx.x & 31;
+    const long long qp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qp >= batch) return;
+    double mx = 0.0;
+    for (int k = lane; k < N; k += 32) {
+        const double u = uc[qp * N + k];
+        mx = fmax(mx, fabs(u - ulin[qp * N + k]));
+        ulin[qp * N + k] = u;
+        warm2[qp * (N + nt) + k] = u;
+    }
+    if (lane < nt) warm2[qp * (N + nt) + N + lane] = theta[qp * nt + lane];
+    mx = warp_max(mx);
+    if (lane == 0 && step) step[qp * step_ld + j] = mx;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64-FMA peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
 // 8 independent register-resident DFMA chains per thread.
 // ---------------------------------------------------------------------------------------------

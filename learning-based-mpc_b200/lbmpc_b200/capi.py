@@ -103,6 +103,8 @@ def load_library(path=None):
     lib.lbmpc_solve_batch.restype = C.c_int
     lib.lbmpc_oracle_apply.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [vp]
     lib.lbmpc_oracle_apply.restype = C.c_int
+    lib.lbmpc_solve_sqp.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
+    lib.lbmpc_solve_sqp.restype = C.c_int
     lib.lbmpc_closed_loop.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double,
                                       vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp]
     lib.lbmpc_closed_loop.restype = C.c_int
@@ -266,6 +268,28 @@ class Solver:
                                              _ptr(valid), _ptr(d), None)
         self._check(rc, "lbmpc_oracle_apply")
         return d
+
+    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, want_x=True):
+        """Learned-oracle problem as a sequence of QPs (lbmpc_solve_sqp): X (batch,q,3), Y (batch,q,nx) data windows.
+        Host arrays.  Returns the last QP's solution plus du_step (batch, sqp_iters)."""
+        if self.device_pointers:
+            raise LbmpcError("solve_sqp is exposed for host-pointer handles")
+        nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
+        dx0 = np.ascontiguousarray(dx0, np.float64).reshape(-1, nx)
+        nb = dx0.shape[0]
+        c = lambda a, shp: None if a is None else np.ascontiguousarray(a, np.float64).reshape(shp)
+        X, Y = np.ascontiguousarray(X, np.float64), np.ascontiguousarray(Y, np.float64)
+        q = X.shape[1]
+        valid, dx_ref, warm = c(valid, (nb, q)), c(dx_ref, (nb, nx)), c(warm, (nb, N * nu + nt))
+        o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)), xtraj=np.empty((nb, N + 1, nx)) if want_x else None,
+                 obj=np.empty(nb), iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32),
+                 du_step=np.empty((nb, sqp_iters)))
+        rc = self.lib.lbmpc_solve_sqp(self.h, nb, int(sqp_iters), int(q), float(bandwidth), float(lam), _ptr(dx0), _ptr(dx_ref),
+                                      _ptr(X), _ptr(Y), _ptr(valid), _ptr(warm), _ptr(o["uc"]), _ptr(o["theta"]),
+                                      _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]),
+                                      _ptr(o["du_step"]), None)
+        self._check(rc, "lbmpc_solve_sqp")
+        return o
 
     def closed_loop(self, x_init, steps, x_eq, u_eq, q=100, use_oracle=False, warm_shift=True, wbar=None, seed=0,
                     scenario0=0):

@@ -12,6 +12,7 @@
  *              out.u_or_c (nu*N x batch), out.theta (nt x batch), out.x (nx x (N+1) x batch),
  *              out.f (1 x batch), out.iters, out.status (int32 1 x batch)
  *   d_off    = lbmpc_mex('oracle', h, q, bandwidth, lambda, dx0, du, X, Y, valid)
+ *   out      = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm)   out.du_step added
  *   hist     = lbmpc_mex('closed_loop', h, steps, q, use_oracle, warm_shift, x_eq, u_eq, x_init, wbar, seed)
  *   lbmpc_mex('destroy', h)        v = lbmpc_mex('version')
  *
@@ -163,6 +164,39 @@ static void cmd_oracle(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[
     (void)nlhs;
 }
 
+static void cmd_solve_sqp(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    static const char *names[] = {"u_or_c", "theta", "x", "f", "iters", "status", "du_step"};
+    entry_t *e;
+    int64_t batch;
+    int its, rc;
+    mwSize d3[3];
+    mxArray *uc, *th, *x, *f, *it, *st, *ds;
+    if (nrhs < 10)
+        mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm)");
+    e = lookup(get_handle(prhs[1]));
+    its = (int)mxGetScalar(prhs[2]);
+    if ((int)mxGetM(prhs[6]) != e->nx) mexErrMsgIdAndTxt("lbmpc:args", "dx0 must be nx x batch");
+    batch = (int64_t)mxGetN(prhs[6]);
+    uc = mxCreateDoubleMatrix((mwSize)(e->nu * e->N), (mwSize)batch, mxREAL);
+    th = mxCreateDoubleMatrix((mwSize)e->nt, (mwSize)batch, mxREAL);
+    d3[0] = (mwSize)e->nx; d3[1] = (mwSize)(e->N + 1); d3[2] = (mwSize)batch;
+    x = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
+    f = mxCreateDoubleMatrix(1, (mwSize)batch, mxREAL);
+    it = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
+    st = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
+    ds = mxCreateDoubleMatrix((mwSize)(its > 0 ? its : 1), (mwSize)batch, mxREAL);
+    rc = lbmpc_solve_sqp(e->h, batch, its, (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), mxGetScalar(prhs[5]),
+                         dptr(prhs[6]), dptr(prhs[7]), dptr(prhs[8]), dptr(prhs[9]), nrhs > 10 ? dptr(prhs[10]) : NULL,
+                         nrhs > 11 ? dptr(prhs[11]) : NULL, mxGetPr(uc), mxGetPr(th), mxGetPr(x), mxGetPr(f),
+                         (int32_t *)mxGetData(it), (int32_t *)mxGetData(st), mxGetPr(ds), NULL);
+    if (rc != LBMPC_OK) fail_rc("lbmpc_solve_sqp", rc);
+    plhs[0] = mxCreateStructMatrix(1, 1, 7, names);
+    mxSetField(plhs[0], 0, "u_or_c", uc); mxSetField(plhs[0], 0, "theta", th); mxSetField(plhs[0], 0, "x", x);
+    mxSetField(plhs[0], 0, "f", f); mxSetField(plhs[0], 0, "iters", it); mxSetField(plhs[0], 0, "status", st);
+    mxSetField(plhs[0], 0, "du_step", ds);
+    (void)nlhs;
+}
+
 static void cmd_closed_loop(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     static const char *names[] = {"x", "u", "theta", "iters", "status"};
     entry_t *e;
@@ -201,6 +235,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     if (strcmp(cmd, "create") == 0) cmd_create(nlhs, plhs, nrhs, prhs);
     else if (strcmp(cmd, "solve") == 0) cmd_solve(nlhs, plhs, nrhs, prhs);
     else if (strcmp(cmd, "oracle") == 0) cmd_oracle(nlhs, plhs, nrhs, prhs);
+    else if (strcmp(cmd, "solve_sqp") == 0) cmd_solve_sqp(nlhs, plhs, nrhs, prhs);
     else if (strcmp(cmd, "closed_loop") == 0) cmd_closed_loop(nlhs, plhs, nrhs, prhs);
     else if (strcmp(cmd, "destroy") == 0) {
         entry_t *e;

@@ -145,6 +145,29 @@ class OracleProblem:
                                  C.c_double(bandwidth), C.c_double(lam), _p(d))
         return d
 
+    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001):
+        """CPU mirror of lbmpc_solve_sqp (include/lbmpc.h): oracle offsets along the previous inputs, then one QP, repeated.
+        X (batch,q,3), Y (batch,q,nx), valid (batch,q) or None."""
+        dx0 = np.ascontiguousarray(dx0, float).reshape(-1, self.nx)
+        nb, N = dx0.shape[0], self.N
+        outs, steps = [], np.empty((nb, sqp_iters))
+        for b in range(nb):
+            ulin = np.zeros(N) if warm is None else np.array(warm[b][:N], float)
+            w = None if warm is None else np.array(warm[b], float)[None, :]
+            xr = None if dx_ref is None else np.asarray(dx_ref[b], float)[None, :]
+            for j in range(sqp_iters):
+                d = self.oracle_offsets(dx0[b], ulin, np.ascontiguousarray(X[b].T), np.ascontiguousarray(Y[b].T),
+                                        None if valid is None else valid[b], bandwidth, lam)
+                o = self.solve_batch(dx0[b:b + 1], xr, d[None], w)
+                u = o["uc"][0, :, 0]
+                steps[b, j] = np.abs(u - ulin).max()
+                ulin = u.copy()
+                w = np.concatenate([u, o["theta"][0]])[None, :]
+            outs.append(o)
+        res = {k: np.concatenate([o[k] for o in outs]) for k in outs[0] if outs[0][k] is not None}
+        res["du_step"] = steps
+        return res
+
     def closed_loop(self, x_eq, u_eq, x_init, steps, q=100, use_oracle=False, warm_shift=True, wbar=None, seed=0,
                     scenario=0):
         xe, xi, wb = _d(x_eq), _d(x_init), _d(wbar)

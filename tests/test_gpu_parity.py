@@ -266,3 +266,28 @@ def test_iteration_cap_bad_inputs_and_options(models, monkeypatch, kernel):
     keep = np.ones(40, bool)
     keep[[3, 7]] = False
     assert_parity({k: v[keep] for k, v in got.items()}, {k: v[keep] for k, v in ref.items()}, tol=1e-6)
+
+
+def test_sqp_outer_loop_matches_oracle_and_contracts(fx, models):
+    """SURVEY 8f-1: the learned-oracle problem as a sequence of QPs (lbmpc_solve_sqp) vs the CPU mirror of the same loop;
+    the outer iteration contracts (the oracle correction is O(1e-3) of the dynamics, oracleL2NW.m / train_data.mat)."""
+    mdl = models["LBMPC"]
+    data = fx["casadi_train_data__data"]
+    nb, N, q, its = 24, 50, 100, 4
+    rng = np.random.default_rng(4)
+    X0 = sample_ics(nb, seed=12) * 0.5
+    offs = rng.integers(0, data.shape[1] - q, nb)
+    Xw = np.stack([data[:3, o:o + q].T for o in offs])
+    Yw = np.stack([data[3:7, o:o + q].T for o in offs]) * 20.0          # exaggerate the model error: visible outer iterations
+    sol = solver(mdl, "C", "LBMPC", N, max_batch=nb)
+    got = sol.solve_sqp(X0, Xw, Yw, sqp_iters=its)
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_sqp(X0, Xw, Yw, sqp_iters=its)
+    assert_parity(got, ref)
+    ok = ref["status"] == 0
+    assert np.abs(got["du_step"][ok] - ref["du_step"][ok]).max() < 1e-7
+    st = got["du_step"][ok]
+    # the outer loop contracts: the change of the inputs shrinks from one linearisation to the next
+    assert (st[:, 1:] <= st[:, :-1] + 1e-12).all() and np.median(st[:, -1]) < 1e-3 * np.median(st[:, 0]), st
+    one = sol.solve_batch(X0, d_off=sol.oracle_apply(X0, np.zeros((nb, N, 1)), Xw, Yw))  # first outer iteration = plain RTI step
+    first = sol.solve_sqp(X0, Xw, Yw, sqp_iters=1)
+    assert np.array_equal(one["uc"], first["uc"])
