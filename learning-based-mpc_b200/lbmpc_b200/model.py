@@ -86,6 +86,29 @@ def getCONS(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, x_wp=X_WP, u_wp=U_WP):
     return F_x, h_x, F_u, h_u, d["term_set_F_w_N"].copy(), d["term_set_h_w_N"].copy()
 
 
+def pdiff(F_u, h_u, F_v, h_v):
+    """Pontryagin difference {x: F_u x <= h_u} (-) {v: F_v v <= h_v} in H-representation, as utilities/pdiff.m:8-17: one
+    LP per row (support function of the subtrahend in the direction of the row).  Host-side, scipy linprog (HiGHS)."""
+    from scipy.optimize import linprog
+    F_u, h_u = np.atleast_2d(np.asarray(F_u, float)), np.asarray(h_u, float).ravel()
+    sup = np.empty(len(h_u))
+    for i, row in enumerate(F_u):
+        res = linprog(-row, A_ub=np.atleast_2d(F_v), b_ub=np.asarray(h_v, float).ravel(), bounds=[(None, None)] * F_u.shape[1],
+                      method="highs")
+        if res.status != 0:
+            raise ValueError(f"pdiff: support LP of row {i} failed ({res.message})")
+        sup[i] = -res.fun
+    return F_u.copy(), h_u - sup
+
+
+def tightened_state_set(F_x, h_x, state_uncert):
+    """X (-) D of getCONSPOLY.m:17-30 with the box D = {|d_j| <= state_uncert_j} (:17-19): [F_x_d, h_x_d].  (MPT's
+    minHRep only reorders / normalises the rows of this box-minus-box; the rows here keep the order of F_x.)"""
+    w = np.asarray(state_uncert, float).ravel()
+    n = w.size
+    return pdiff(F_x, h_x, np.vstack([np.eye(n), -np.eye(n)]), np.concatenate([w, w]))
+
+
 def getCONSPOLY(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, state_uncert=(0.02, 5e-4, 0.0, 0.0), x_wp=X_WP,
                 u_wp=U_WP):
     """[F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d] of getCONSPOLY.m for the reference's default

@@ -148,3 +148,18 @@ def test_flop_counter_matches_closed_form(models):
         per_iter = r["stats"][3] / max(int(r["iters"]), 1)
         model = 1355 * 50 + 108 * ng
         assert 0.75 * model < per_iter < 1.25 * model, (variant, per_iter, model)
+
+
+def test_tightened_state_set_reproduces_getconspoly(models):
+    """X (-) D of getCONSPOLY.m:25-30 (MPT Pontryagin difference + minHRep) from utilities/pdiff.m's LP recipe, host-side:
+    the same 8 half-spaces as the reference's own F_x_d, h_x_d (row order / scaling aside)."""
+    import lbmpc_b200
+    m = models["LBMPC"]
+    F, h = lbmpc_b200.tightened_state_set(m["F_x"], m["h_x"], (0.02, 5e-4, 0.0, 0.0))
+    Fd, hd = np.asarray(m["F_x_d"]), np.asarray(m["h_x_d"]).ravel()
+
+    def rows(F, h):
+        return np.array(sorted(tuple(np.r_[f, v] / np.abs(f).max()) for f, v in zip(F, h)))
+    assert F.shape == Fd.shape and np.abs(rows(F, h) - rows(Fd, hd)).max() < 1e-12
+    F2, h2 = lbmpc_b200.pdiff(m["F_x"], m["h_x"], np.vstack([np.eye(4), -np.eye(4)]), np.zeros(8))   # D = {0}
+    assert np.array_equal(F2, m["F_x"]) and np.abs(h2 - np.asarray(m["h_x"]).ravel()).max() < 1e-12
