@@ -153,10 +153,12 @@ int64_t lbmpc_kernel_launches(const lbmpc_handle *h); /* kernels launched by thi
 /* last solve call: device time of the IPM kernel in ms (CUDA events on the launch stream) */
 float lbmpc_last_kernel_ms(lbmpc_handle *h);
 
-/* diagnostic: SM-cycle counters of CTA 0 per kernel phase, accumulated over the solve calls made while enabled:
- * out8 = {C: affine step/sigma/refill, D: corrector sweeps, E+A: update+assembly, B: factorisation,
- * B2: verdict+affine sweeps, lock-step iterations, factor warp, adjoint warp, 8 spare}; out8 holds 16 values.  Reads and clears the counters, then sets `enable`. */
-int lbmpc_debug_phase_cycles(lbmpc_handle *h, int enable, uint64_t *out8);
+/* diagnostic: SM-cycle counters (clock64) of the first warp / CTA of the solve kernel, accumulated per phase over the solve
+ * calls made while enabled.  out16[0..8] = {load + rollout, E+A update + assembly, B factorisation (+ dual residual, affine
+ * backward substitution, Farkas), B2 affine forward substitution, C affine rows + sigma, D corrector substitution,
+ * E final rows + step length, number of iterations, store}; out16[9..15] = sub-phases (corrector sweep P1/P2/P3, polytope
+ * rows and reductions of the assembly; warp-per-QP kernel only).  Reads and clears the counters, then sets `enable`. */
+int lbmpc_debug_phase_cycles(lbmpc_handle *h, int enable, uint64_t *out16);
 
 /* roofline denominator: measured FP64-FMA throughput of the device in TFLOP/s (register-resident DFMA
  * chains, best of 5 after one warm-up; MEASURED_PEAKS.json carries no FP64 entry) */
