@@ -7,8 +7,9 @@ across ranks.  Nothing here computes a solve on the CPU.
 """
 from .capi import (FORM, VARIANT, ST_OPTIMAL, ST_MAXITER, ST_INFEASIBLE, ST_NUMERICAL, LbmpcError, Solver,
                    load_library, pack_model, make_config, measure_fp64_peak)
-from .model import (mgcmDLTI, matOCP, getCONS, getCONSPOLY, pdiff, tightened_state_set, moore_greitzer_model, X_WP, U_WP)
+from .model import (mgcmDLTI, matOCP, getCONS, getCONSPOLY, pdiff, tightened_state_set, moore_greitzer_model, double_integrator_model,
+                    X_WP, U_WP)
 
 __all__ = ["FORM", "VARIANT", "ST_OPTIMAL", "ST_MAXITER", "ST_INFEASIBLE", "ST_NUMERICAL", "LbmpcError", "Solver",
            "load_library", "pack_model", "make_config", "measure_fp64_peak", "mgcmDLTI", "matOCP", "getCONS", "getCONSPOLY",
-           "pdiff", "tightened_state_set", "moore_greitzer_model", "X_WP", "U_WP"]
+           "pdiff", "tightened_state_set", "moore_greitzer_model", "double_integrator_model", "X_WP", "U_WP"]

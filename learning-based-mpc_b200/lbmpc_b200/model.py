@@ -134,3 +134,29 @@ def moore_greitzer_model(variant="LMPC"):
         mdl.update(F_x_d=F_x_d, h_x_d=h_x_d)
     mdl.update(F_x=F_x, h_x=h_x, F_u=F_u, h_u=h_u, F_w_N=F_w_N, h_w_N=h_w_N)
     return mdl
+
+
+def double_integrator_model(lam=0.99):
+    """The second problem shape of the reference (matlab/trackingMPC/RunExample.m): sampled double integrator with two
+    inputs (:20-28), LQR gain, P = dare(A+BK,B,Q,R), T = 100 P (:57-62), boxes |x| <= 5, |u| <= 0.3 (:64-67), steady-state
+    parametrisation null space (:40-45) and the extended admissible set X_ext of (x, theta) written out in closed form at
+    :84-93 (the MPT invariant-set iteration that follows it, :105-108, stays offline: out of scope).  nx = nu = nt = 2."""
+    A = np.array([[1.0, 1.0], [0.0, 1.0]])
+    B = np.array([[0.0, 0.5], [1.0, 0.5]])
+    Cm = np.array([[1.0, 0.0]])
+    n, m, o = 2, 2, 1
+    Q, R = np.eye(n), np.eye(m)
+    M = np.block([[A - np.eye(n), B, np.zeros((n, o))], [Cm, np.zeros((o, m)), -np.eye(o)]])
+    Mtheta = sla.null_space(M)
+    LAMBDA, PSI = Mtheta[:n, :], Mtheta[n:n + m, :]
+    K = -_dlqr(A, B, Q, R)
+    P = sla.solve_discrete_are(A + B @ K, B, Q, R)
+    T = 100.0 * P
+    F_u = np.vstack([np.eye(m), -np.eye(m)]); h_u = np.full(2 * m, 0.3)
+    F_x = np.vstack([np.eye(n), -np.eye(n)]); h_x = np.full(2 * n, 5.0)
+    L = PSI - K @ LAMBDA
+    F_w = np.block([[F_x, np.zeros((2 * n, m))], [np.zeros((2 * n, n)), F_x @ LAMBDA], [F_u @ K, F_u @ L],
+                    [np.zeros((2 * m, n)), F_u @ PSI]])
+    h_w = np.concatenate([h_x, lam * h_x, h_u, lam * h_u])
+    return dict(A=A, B=B, K=K, Q=Q, R=R, P=P, T=T, Mtheta=Mtheta, LAMBDA=LAMBDA, PSI=PSI, F_x=F_x, h_x=h_x, F_u=F_u, h_u=h_u,
+                F_w_N=F_w, h_w_N=h_w, x_wp=np.zeros(n), u_wp=np.zeros(m))

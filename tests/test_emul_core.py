@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import assert_parity, sample_ics
+from conftest import assert_parity, double_integrator_cases, drop_numerical, sample_ics
 from lbmpc_b200 import capi
 from oracle_py import OracleProblem
 
@@ -58,3 +58,19 @@ def test_long_horizon(emul_lib, models):
     got = emul_solve(emul_lib, mdl, "C", "LBMPC", 200, X0)
     ref = OracleProblem("C", "LBMPC", mdl, 200).solve_batch(X0)
     assert_parity(got, ref)
+
+
+@pytest.mark.parametrize("form", ["F", "C"])
+@pytest.mark.parametrize("N", [3, 10])
+def test_second_shape_double_integrator(emul_lib, form, N):
+    """nx = nu = nt = 2 (matlab/trackingMPC/RunExample.m:20-22), matrix-valued T, thread-local factorisation path."""
+    mdl, X0, xref = double_integrator_cases(96, seed=N)
+    got = emul_solve(emul_lib, mdl, form, "LMPC", N, X0, xref)
+    ref = OracleProblem(form, "LMPC", mdl, N).solve_batch(X0, xref, nthreads=4)
+    g, r = drop_numerical(got, ref)
+    if form == "F":   # two inputs, and the F-form leaves the last two input vectors without stage cost (costLMPC.m:30-35): the
+        g = {k: g[k] for k in ("status", "iters", "obj")}   # minimiser is not unique here; verdict, iterations, objective are
+        r = {k: r[k] for k in ("status", "iters", "obj")}
+    # vertex solutions with a 0.01-weighted input cost: many more weakly determined minimisers than on the compressor model;
+    # the objective still has to agree to 1e-7 for every QP (this shape is covered at that level: SURVEY 8c calls it unpinned)
+    assert_parity(g, r, tol=1e-7, frac_tight=0.8, max_dit=2, caps=(1e-3, 1e-2))

@@ -7,7 +7,7 @@ Parity rule: identical status, iterations within +-1, 1e-8 rela
 import numpy as np
 import pytest
 
-from conftest import assert_parity, sample_ics
+from conftest import assert_parity, double_integrator_cases, drop_numerical, sample_ics
 from oracle_py import OracleProblem, plant_rk4
 
 pytestmark = pytest.mark.gpu
@@ -291,3 +291,21 @@ def test_sqp_outer_loop_matches_oracle_and_contracts(fx, models):
     one = sol.solve_batch(X0, d_off=sol.oracle_apply(X0, np.zeros((nb, N, 1)), Xw, Yw))  # first outer iteration = plain RTI step
     first = sol.solve_sqp(X0, Xw, Yw, sqp_iters=1)
     assert np.array_equal(one["uc"], first["uc"])
+
+
+@pytest.mark.parametrize("form", ["F", "C"])
+@pytest.mark.parametrize("N", [3, 10, 40])
+def test_second_shape_double_integrator(form, N):
+    """The other compiled shape, nx = nu = nt = 2 (matlab/trackingMPC/RunExample.m:20-22: sampled double integrator,
+    horizon 3), with the closed-form extended admissible set (:84-93) as terminal set and the matrix-valued T = 100 P."""
+    mdl, X0, xref = double_integrator_cases(300, seed=N)
+    got = solver(mdl, form, "LMPC", N, max_batch=300).solve_batch(X0, xref)
+    ref = OracleProblem(form, "LMPC", mdl, N).solve_batch(X0, xref, nthreads=8)
+    assert (ref["status"] == 0).mean() > 0.5
+    g, r = drop_numerical(got, ref)
+    if form == "F":   # two inputs, and the F-form leaves the last two input vectors without stage cost (costLMPC.m:30-35): the
+        g = {k: g[k] for k in ("status", "iters", "obj")}   # minimiser is not unique here; verdict, iterations, objective are
+        r = {k: r[k] for k in ("status", "iters", "obj")}
+    # vertex solutions with a 0.01-weighted input cost: many more weakly determined minimisers than on the compressor model;
+    # the objective still has to agree to 1e-7 for every QP (this shape is covered at that level: SURVEY 8c calls it unpinned)
+    assert_parity(g, r, tol=1e-7, frac_tight=0.8, max_dit=2, caps=(1e-3, 1e-2))
