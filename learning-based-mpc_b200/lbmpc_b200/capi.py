@@ -293,9 +293,24 @@ class Solver:
 
     def closed_loop(self, x_init, steps, x_eq, u_eq, q=100, use_oracle=False, warm_shift=True, wbar=None, seed=0,
                     scenario0=0):
-        """Batch of closed-loop scenarios (host arrays).  Returns dict x (batch,steps+1,nx), u, theta, iters, status."""
+        """Batch of closed-loop scenarios.  Returns dict x (batch,steps+1,nx), u, theta, iters, status (numpy arrays for a
+        host-pointer handle; torch tensors on x_init's device, filled asynchronously, for a device-pointer handle)."""
         if self.device_pointers:
-            raise LbmpcError("closed_loop is exposed for host-pointer handles")
+            import torch
+            nb, dev = x_init.shape[0], x_init.device
+            x_eq = np.ascontiguousarray(x_eq, np.float64)                      # tiny parameter vectors: always host
+            wbar = None if wbar is None else np.ascontiguousarray(wbar, np.float64)
+            o = dict(x=torch.empty((nb, steps + 1, self.nx), dtype=torch.float64, device=dev),
+                     u=torch.empty((nb, steps), dtype=torch.float64, device=dev),
+                     theta=torch.empty((nb, steps), dtype=torch.float64, device=dev),
+                     iters=torch.empty((nb, steps), dtype=torch.int32, device=dev),
+                     status=torch.empty((nb, steps), dtype=torch.int32, device=dev))
+            st = torch.cuda.current_stream(dev).cuda_stream
+            rc = self.lib.lbmpc_closed_loop(self.h, nb, steps, q, int(use_oracle), int(warm_shift), _ptr(x_eq), float(u_eq),
+                                            _ptr(x_init), _ptr(wbar), seed, scenario0, _ptr(o["x"]), _ptr(o["u"]),
+                                            _ptr(o["theta"]), _ptr(o["iters"]), _ptr(o["status"]), C.c_void_p(st))
+            self._check(rc, "lbmpc_closed_loop")
+            return o
         nx = self.nx
         x_init = np.ascontiguousarray(x_init, np.float64).reshape(-1, nx)
         nb = x_init.shape[0]

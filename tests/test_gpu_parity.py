@@ -309,3 +309,32 @@ def test_second_shape_double_integrator(form, N):
     # vertex solutions with a 0.01-weighted input cost: many more weakly determined minimisers than on the compressor model;
     # the objective still has to agree to 1e-7 for every QP (this shape is covered at that level: SURVEY 8c calls it unpinned)
     assert_parity(g, r, tol=1e-7, frac_tight=0.8, max_dit=2, caps=(1e-3, 1e-2))
+
+
+def test_device_pointer_mode_oracle_and_closed_loop(fx, models):
+    """lbmpc_oracle_apply and lbmpc_closed_loop with device pointers (asynchronous on the caller's stream) give the bits of
+    the host-pointer calls."""
+    import torch
+    mdl = models["LBMPC"]
+    data = fx["casadi_train_data__data"]
+    nb, N, q, steps = 20, 50, 60, 6
+    rng = np.random.default_rng(8)
+    X0 = sample_ics(nb, seed=21)
+    du = 0.05 * rng.standard_normal((nb, N, 1))
+    offs = rng.integers(0, data.shape[1] - q, nb)
+    Xw = np.stack([data[:3, o:o + q].T for o in offs])
+    Yw = np.stack([data[3:7, o:o + q].T for o in offs])
+    hs = solver(mdl, "C", "LBMPC", N, max_batch=nb)
+    ds = solver(mdl, "C", "LBMPC", N, device_pointers=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_host = hs.oracle_apply(X0, du, Xw, Yw)
+    d_dev = ds.oracle_apply(t(X0), t(du), t(Xw), t(Yw))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dev.cpu().numpy(), d_host)
+    x_init = X_EQ + 0.3 * X0
+    wbar = np.array([0.02, 5e-4, 0.0, 0.0])
+    h = hs.closed_loop(x_init, steps, X_EQ, U_EQ, q=10, use_oracle=True, wbar=wbar, seed=3, scenario0=7)
+    d = ds.closed_loop(t(x_init), steps, X_EQ, U_EQ, q=10, use_oracle=True, wbar=wbar, seed=3, scenario0=7)
+    torch.cuda.synchronize()
+    for k in ("x", "u", "theta", "iters", "status"):
+        assert np.array_equal(d[k].cpu().numpy(), h[k]), k
