@@ -284,8 +284,9 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
                     m[L::M_DTHA] = -iptt * pvth;
                     m[L::M_RD] = lb_nanmax(rdm, lb_abs(m[L::M_GTH]));
                 }
-                if (cert) {  // Farkas recursion, blocked over the horizon (lanes = blocks)
-                    __syncwarp();
+            }
+            if (cert && warp == (sw + 1) % W) {  // Farkas recursion, blocked over the horizon (lanes = blocks), on ANOTHER warp:
+                {                                  // it reads the assembly's output only and runs beside the factorisation
                     if (lane < l.nb) C::farkas_p1(p, l, slot, lane);
                     __syncwarp();
                     if (lane == 0) C::farkas_p2(p, l, slot);
