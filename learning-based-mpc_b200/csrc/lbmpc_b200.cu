@@ -92,13 +92,17 @@ static int plan_slots(lbmpc_handle* h, size_t max_smem) {
 }
 
 template <int NX, int NT, int NU>
-static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io, cudaStream_t st) {
+static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_t st) {
     const HostProblem& hp = h->hp;
+    BatchIO io = io_in;
     const Params<NX, NT, NU> p = to_params<NX, NT, NU>(hp);
     int slots = (int)std::min<int64_t>(h->max_slots, (io.batch + h->num_sms - 1) / h->num_sms);
     slots = std::max(slots, 1);
     const int grid = (int)std::min<int64_t>(h->num_sms, (io.batch + slots - 1) / slots);
     const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
+    // many QPs per warp slot: the warps of a CTA start their iterations together (shared instruction fetches, see cta_tick)
+    io.lockstep = slots >= 4 && io.batch >= (int64_t)3 * grid * slots;
+    if (const char* e = getenv("LBMPC_LOCKSTEP")) io.lockstep = atoi(e) != 0;  // experiments
     cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
