@@ -337,7 +337,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
                 const double mu = m[L::M_MU];
                 const double mu_aff = (sm[0] + aaff * sm[1] + aaff * aaff * sm[2]) * p.inv_m;
                 const double sr = mu_aff / mu;
-                sigmu = fmax(sr * sr * sr * mu, 0.1 * p.tol_mu);  // no centring below the target gap (round-off at degenerate vertices)
+                sigmu = fmax(sr * sr * mu, 0.1 * p.tol_mu);  // no centring below the target gap (round-off at degenerate vertices)
                 for (int it = tid; it < nitems; it += kCtaThreads) C::corr_item(p, l, slot, it / NVB, it % NVB, sigmu);
                 if (BIG) {
                     const double t = block_sum_scatter<W, 2 * NZ>(acc, red, warp, lane, tid);  // thread a: acc[a], thread NZ + a: acc[NZ + a]

@@ -454,7 +454,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 const double mu = m[L::M_MU];
                 const double mu_aff = (s0 + aaff * s1 + aaff * aaff * s2) * p.inv_m;
                 const double sr = mu_aff / mu;
-                sigmu = fmax(sr * sr * sr * mu, 0.1 * p.tol_mu);  // no centring below the target gap (round-off at degenerate vertices)
+                sigmu = fmax(sr * sr * mu, 0.1 * p.tol_mu);  // no centring below the target gap (round-off at degenerate vertices)
                 for (int k = lane; k <= N; k += 32) C::corr_stage(p, l, slot, k, sigmu);
                 __syncwarp();
                 if (lane == 0) {

@@ -148,7 +148,7 @@ def mehrotra_dense(H, g, G, h, y0=None, tol=1e-9, tol_mu=1e-10, max_iter=60, ver
         dya, dsa, dla = solve(s * lam)
         aa = min(1.0, amax(dsa, dla))
         mu_aff = (s + aa * dsa) @ (lam + aa * dla) / mrow
-        sigmu = max((mu_aff / mu) ** 3 * mu, 0.1 * tol_mu)      # same floor as lbmpc_oracle.c: no centring below the target gap
+        sigmu = max((mu_aff / mu) ** 2 * mu, 0.1 * tol_mu)      # same floor as lbmpc_oracle.c: no centring below the target gap
         dy, ds, dl = solve(s * lam + dsa * dla - sigmu)
         a = min(1.0, 0.99 * amax(ds, dl))
         y += a * dy

@@ -17,7 +17,7 @@
  *              (adjoint recursion); stop when |r_d|_inf < tol_res max(1, 100 |lambda|_inf) (the
  *              round-off floor of r_d scales with the multipliers),
  *              |r_p|_inf < tol_res and mu < tol_mu
- *              predictor: Newton step with r_c = s.lambda ; alpha_aff ; sigma = (mu_aff/mu)^3, sigma mu >= 0.1 tol_mu
+ *              predictor: Newton step with r_c = s.lambda ; alpha_aff ; sigma = (mu_aff/mu)^2, sigma mu >= 0.1 tol_mu
  *              corrector: r_c = s.lambda + ds_a.dl_a - sigma mu ; alpha = min(1, 0.99 alpha_max)
  *              both Newton systems solved by ONE Riccati factorisation over the augmented state
  *              z = [x;theta] (backward sweep) + two backward/forward substitution sweeps
@@ -795,7 +795,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
         if (aaff > 1.0) aaff = 1.0;
         const double mu_aff = (sums[0] + aaff * sums[1] + aaff * aaff * sums[2]) / p->m_rows;
         const double sr = mu_aff / mu;
-        double sigmu = sr * sr * sr * mu;
+        double sigmu = sr * sr * mu;
         if (sigmu < 0.1 * p->tol_mu) sigmu = 0.1 * p->tol_mu; /* do not centre below the target gap: weights s/lambda beyond ~1/tol_mu
                                                                    only add round-off to the Newton steps (degenerate vertices) */
         double dummy;

@@ -101,7 +101,7 @@ def double_integrator_cases(n, seed=0):
     return mdl, X0, xref
 
 
-def drop_numerical(got, ref, max_frac=0.02):
+def drop_numerical(got, ref, max_frac=0.03):
     """Second problem shape only: a few QPs of the double integrator end at degenerate vertices (more active rows than
     variables) where the last interior-point steps are decided by round-off; either implementation may then stop with
     status 3 (numerical) one iteration before the other converges — the outcome even depends on the compiler's FMA

@@ -147,7 +147,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         const double aaff = rs.ratio > 1.0 ? 1.0 / rs.ratio : 1.0;
         const double mu_aff = (rs.s0 + aaff * rs.s1 + aaff * aaff * rs.s2) * p.inv_m;
         const double sr = mu_aff / m[L::M_MU];
-        const double sigmu = lb_max(sr * sr * sr * m[L::M_MU], 0.1 * p.tol_mu);
+        const double sigmu = lb_max(sr * sr * m[L::M_MU], 0.1 * p.tol_mu);
         m[L::M_SIGMU] = sigmu;
         for (int k = 0; k <= N; ++k) C::corr_stage(p, l, s, k, sigmu);
         for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a] + sigmu * dg[NZ + a];
