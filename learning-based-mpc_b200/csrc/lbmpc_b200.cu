@@ -58,8 +58,10 @@ struct lbmpc_handle {
     bool prof_on = false;
     // host-pointer staging
     double *s_dx0 = nullptr, *s_ref = nullptr, *s_doff = nullptr, *s_warm = nullptr, *s_uc = nullptr,
-           *s_theta = nullptr, *s_x = nullptr, *s_obj = nullptr;
-    int *s_it = nullptr, *s_st = nullptr;
+           *s_x = nullptr;
+    // theta | obj | iters | status of a call, packed back to back for the ACTUAL batch: one device-to-host copy into a
+    // pinned host block instead of four small ones, scattered to the caller's arrays after the stream synchronises
+    char *s_small = nullptr, *hs_small = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     bool timed = false;
@@ -158,6 +160,42 @@ static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream
     return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
 }
 
+struct SmallOut {
+    double *theta, *obj;
+    int *iters, *status;
+    size_t bytes;
+};
+static SmallOut small_out(char* base, size_t b, size_t nt) {
+    SmallOut o;
+    o.theta = reinterpret_cast<double*>(base);
+    o.obj = o.theta + b * nt;
+    o.iters = reinterpret_cast<int*>(o.obj + b);
+    o.status = o.iters + b;
+    o.bytes = sizeof(double) * b * (nt + 1) + sizeof(int) * 2 * b;
+    return o;
+}
+static void scatter_small(const lbmpc_handle* h, size_t b, size_t nt, double* theta, double* obj, int32_t* iters, int32_t* status) {
+    const SmallOut o = small_out(h->hs_small, b, nt);
+    memcpy(theta, o.theta, sizeof(double) * b * nt);
+    memcpy(obj, o.obj, sizeof(double) * b);
+    memcpy(iters, o.iters, sizeof(int) * b);
+    memcpy(status, o.status, sizeof(int) * b);
+}
+
+// Page-locked (pinned) caller arrays are mapped into the device's address space: the kernel then reads its 32-byte
+// initial state / writes its results through PCIe itself, while other QPs are still being solved, instead of waiting for
+// copy engines before and after the launch.  Returns the device alias of a pinned host pointer, nullptr for pageable memory.
+template <typename T>
+static T* pinned_alias(T* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? reinterpret_cast<T*>(a.devicePointer) : nullptr;
+}
+
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t n) {
     return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
@@ -247,11 +285,10 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(dmalloc(&h->s_doff, b * nx * N));
         CU_TRY(dmalloc(&h->s_warm, b * (nu * N + nt)));
         CU_TRY(dmalloc(&h->s_uc, b * nu * N));
-        CU_TRY(dmalloc(&h->s_theta, b * nt));
         CU_TRY(dmalloc(&h->s_x, b * nx * (N + 1)));
-        CU_TRY(dmalloc(&h->s_obj, b));
-        CU_TRY(dmalloc(&h->s_it, b));
-        CU_TRY(dmalloc(&h->s_st, b));
+        const size_t small = small_out(nullptr, b, nt).bytes;
+        CU_TRY(dmalloc(&h->s_small, small));
+        CU_TRY(cudaHostAlloc((void**)&h->hs_small, std::max<size_t>(small, 16), cudaHostAllocDefault));
     }
     *out = h;
     return LBMPC_OK;
@@ -282,25 +319,40 @@ int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const d
         return LBMPC_OK;
     }
     if (batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
-    CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
-    if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
+    // small per-QP inputs and all results go directly to / from pinned caller arrays; pageable ones are staged
+    const double* a_dx0 = pinned_alias(dx0);
+    const double* a_ref = pinned_alias(dx_ref);
+    double* a_uc = pinned_alias(u_or_c);
+    double* a_x = pinned_alias(x_traj);
+    double* a_th = pinned_alias(theta);
+    double* a_obj = pinned_alias(obj);
+    int32_t* a_it = pinned_alias(iters);
+    int32_t* a_st = pinned_alias(status);
+    const bool small_direct = a_th && a_obj && a_it && a_st;
+    if (!a_dx0) CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
+    if (dx_ref && !a_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
     if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, sizeof(double) * b * nx * N, cudaMemcpyHostToDevice, st));
     if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, sizeof(double) * b * (nu * N + nt), cudaMemcpyHostToDevice, st));
-    io.dx0 = h->s_dx0; io.dx_ref = dx_ref ? h->s_ref : nullptr; io.d_off = d_off ? h->s_doff : nullptr;
+    io.dx0 = a_dx0 ? a_dx0 : h->s_dx0;
+    io.dx_ref = dx_ref ? (a_ref ? a_ref : h->s_ref) : nullptr;
+    io.d_off = d_off ? h->s_doff : nullptr;
     io.warm = warm ? h->s_warm : nullptr;
-    io.uc = h->s_uc; io.theta = h->s_theta; io.xtraj = x_traj ? h->s_x : nullptr; io.obj = h->s_obj;
-    io.iters = h->s_it; io.status = h->s_st;
+    const SmallOut so = small_out(h->s_small, b, nt);
+    io.uc = a_uc ? a_uc : h->s_uc;
+    io.xtraj = x_traj ? (a_x ? a_x : h->s_x) : nullptr;
+    io.theta = small_direct ? a_th : so.theta;
+    io.obj = small_direct ? a_obj : so.obj;
+    io.iters = small_direct ? a_it : so.iters;
+    io.status = small_direct ? a_st : so.status;
     CU_TRY(cudaEventRecord(h->ev0, st));
     CU_TRY(launch_ipm_any(h, io, st));
     CU_TRY(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    CU_TRY(cudaMemcpyAsync(u_or_c, h->s_uc, sizeof(double) * b * nu * N, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(theta, h->s_theta, sizeof(double) * b * nt, cudaMemcpyDeviceToHost, st));
-    if (x_traj) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, sizeof(double) * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(obj, h->s_obj, sizeof(double) * b, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(iters, h->s_it, sizeof(int) * b, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(status, h->s_st, sizeof(int) * b, cudaMemcpyDeviceToHost, st));
+    if (!a_uc) CU_TRY(cudaMemcpyAsync(u_or_c, h->s_uc, sizeof(double) * b * nu * N, cudaMemcpyDeviceToHost, st));
+    if (!small_direct) CU_TRY(cudaMemcpyAsync(h->hs_small, h->s_small, so.bytes, cudaMemcpyDeviceToHost, st));
+    if (x_traj && !a_x) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, sizeof(double) * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (!small_direct) scatter_small(h, b, nt, theta, obj, iters, status);
     return LBMPC_OK;
 }
 
@@ -379,7 +431,8 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q
         if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, 8 * b * nx, cudaMemcpyHostToDevice, st));
         if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, 8 * b * (N + nt), cudaMemcpyHostToDevice, st));
         d_dx0 = h->s_dx0; d_ref = dx_ref ? h->s_ref : nullptr; d_X = tX; d_Y = tY; d_V = tV; d_warm = warm ? h->s_warm : nullptr;
-        d_u = h->s_uc; d_th = h->s_theta; d_xt = x_traj ? h->s_x : nullptr; d_obj = h->s_obj; d_it = h->s_it; d_st = h->s_st;
+        const SmallOut so = small_out(h->s_small, b, nt);
+        d_u = h->s_uc; d_th = so.theta; d_xt = x_traj ? h->s_x : nullptr; d_obj = so.obj; d_it = so.iters; d_st = so.status;
     }
     if (d_warm) CU_TRY(cudaMemcpy2DAsync(h->q_ulin, 8 * N, d_warm, 8 * (N + nt), 8 * N, b, cudaMemcpyDeviceToDevice, st));
     else CU_TRY(cudaMemsetAsync(h->q_ulin, 0, 8 * b * N, st));
@@ -406,13 +459,11 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q
         return LBMPC_OK;
     }
     CU_TRY(cudaMemcpyAsync(u, h->s_uc, 8 * b * N, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(theta, h->s_theta, 8 * b * nt, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h->hs_small, h->s_small, small_out(nullptr, b, nt).bytes, cudaMemcpyDeviceToHost, st));
     if (x_traj) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, 8 * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(obj, h->s_obj, 8 * b, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(iters, h->s_it, 4 * b, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(status, h->s_st, 4 * b, cudaMemcpyDeviceToHost, st));
     if (du_step) CU_TRY(cudaMemcpyAsync(du_step, h->q_step, 8 * b * sqp_iters, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    scatter_small(h, b, nt, theta, obj, iters, status);
     cudaFree(tX); cudaFree(tY); if (tV) cudaFree(tV);
     return LBMPC_OK;
 }
@@ -568,7 +619,8 @@ void lbmpc_destroy(lbmpc_handle* h) {
     free_loop(h->loop);
     cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
-    cudaFree(h->s_theta); cudaFree(h->s_x); cudaFree(h->s_obj); cudaFree(h->s_it); cudaFree(h->s_st);
+    cudaFree(h->s_x); cudaFree(h->s_small);
+    if (h->hs_small) cudaFreeHost(h->hs_small);
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

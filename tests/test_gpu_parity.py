@@ -132,6 +132,63 @@ def test_bitwise_determinism_and_permutation_invariance(models):
         assert np.array_equal(a[k][perm], c[k]), k
 
 
+def test_lockstep_tick_changes_no_result(models, monkeypatch):
+    """At many QPs per warp slot the warp kernel makes the warps of a CTA start every iteration together (cta_tick,
+    an instruction-cache measure).  It only orders the warps in time: forced off and forced on, a batch that queues
+    several QPs behind every slot gives bit-identical results, and both agree with the oracle."""
+    mdl = models["LBMPC"]
+    nb = 6000                                     # > 3 QPs per warp slot of the whole GPU: the default picks the tick
+    X0 = sample_ics(nb, seed=31)
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb)
+    monkeypatch.setenv("LBMPC_KERNEL", "warp")
+    monkeypatch.setenv("LBMPC_LOCKSTEP", "0")
+    a = sol.solve_batch(X0)
+    monkeypatch.setenv("LBMPC_LOCKSTEP", "1")
+    b = sol.solve_batch(X0)
+    monkeypatch.delenv("LBMPC_LOCKSTEP")
+    c = sol.solve_batch(X0)
+    for k in ("uc", "theta", "obj", "iters", "status", "xtraj"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+    sub = slice(0, 512)
+    ref = OracleProblem("C", "LBMPC", mdl, 50).solve_batch(X0[sub], nthreads=8)
+    assert_parity({k: v[sub] for k, v in b.items()}, ref)
+
+
+def test_pinned_host_arrays_are_accessed_in_place(models):
+    """Host-pointer mode: page-locked caller arrays are read / written by the kernel itself (no staging copies),
+    pageable ones go through the staging buffers; both give the same bits, also with a mix of the two and with the
+    optional reference input and state output."""
+    import torch
+    from lbmpc_b200.capi import _ptr
+    mdl = models["LBMPC"]
+    nb, N = 257, 50
+    X0 = sample_ics(nb, seed=5)
+    xref = mdl["LAMBDA"][:, 0][None, :] * np.random.default_rng(3).uniform(-0.05, 0.05, (nb, 1))
+    sol = solver(mdl, "C", "LBMPC", N, max_batch=nb)
+    ref = sol.solve_batch(X0, xref)                                     # numpy arrays: pageable
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    empty = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    h_x0, h_ref = pin(X0), pin(xref)
+    o = {"uc": empty((nb, N, 1), torch.float64), "theta": empty((nb, 1), torch.float64), "xtraj": empty((nb, N + 1, 4), torch.float64),
+         "obj": empty((nb,), torch.float64), "iters": empty((nb,), torch.int32), "status": empty((nb,), torch.int32)}
+
+    def call(x0, xr, theta):
+        rc = sol.lib.lbmpc_solve_batch(sol.h, nb, _ptr(x0), _ptr(xr), None, None, _ptr(o["uc"]), _ptr(theta), _ptr(o["xtraj"]),
+                                       _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]), None)
+        assert rc == 0, sol.lib.lbmpc_last_error().decode()
+    call(h_x0, h_ref, o["theta"])                                       # everything pinned
+    for k, v in o.items():
+        assert np.array_equal(v.numpy().reshape(ref[k].shape), ref[k]), k
+    for v in o.values():
+        v.zero_()
+    th_pageable = torch.zeros((nb, 1), dtype=torch.float64)             # one pageable small output: the packed staging path
+    call(torch.from_numpy(X0.copy()), h_ref, th_pageable)
+    assert np.array_equal(th_pageable.numpy().reshape(ref["theta"].shape), ref["theta"])
+    for k in ("uc", "xtraj", "obj", "iters", "status"):
+        assert np.array_equal(o[k].numpy().reshape(ref[k].shape), ref[k]), k
+
+
 def test_device_pointer_mode(models):
     """Device-resident I/O (torch tensors are only memory + stream plumbing) gives the same bits as host mode."""
     import torch
