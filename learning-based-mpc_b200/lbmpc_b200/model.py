@@ -79,11 +79,21 @@ XMIN = np.array([0.0, 1.1875, 0.1547, -20.0])
 UMAX, UMIN = 2.1547, 0.1547
 
 
-def getCONS(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, x_wp=X_WP, u_wp=U_WP):
-    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N] of getCONS.m: boxes (:15-16) + precomputed terminal set (:57-58)."""
+def getCONS(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, x_wp=X_WP, u_wp=U_WP, recompute=False):
+    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N] of getCONS.m: boxes (:15-16) + precomputed terminal set (:57-58, term_set.mat).
+    Other boxes (or recompute=True) run the invariant-set iteration the reference has commented out (:30-50) through
+    lbmpc_b200.sets — about a minute of linear programmes for the 616-row set, which it reproduces row for row."""
     F_x, h_x, F_u, h_u = _boxes(xmax, xmin, umax, umin, x_wp, u_wp)
-    d = np.load(_DATA)
-    return F_x, h_x, F_u, h_u, d["term_set_F_w_N"].copy(), d["term_set_h_w_N"].copy()
+    default = (np.allclose(xmax, XMAX) and np.allclose(xmin, XMIN) and np.allclose(umax, UMAX) and np.allclose(umin, UMIN)
+               and np.allclose(x_wp, X_WP) and np.allclose(u_wp, U_WP))
+    if default and not recompute:
+        d = np.load(_DATA)
+        return F_x, h_x, F_u, h_u, d["term_set_F_w_N"].copy(), d["term_set_h_w_N"].copy()
+    from .sets import lmpc_terminal_set
+    A, B, C, _, _ = mgcmDLTI()
+    Ks, _, _, _, _, _, _, LAMBDA, PSI, L0, P0 = matOCP(A, B, C)
+    F_w_N, h_w_N = lmpc_terminal_set(A, B, Ks, LAMBDA, PSI, F_x, h_x, F_u, h_u, L0, P0)
+    return F_x, h_x, F_u, h_u, F_w_N, h_w_N
 
 
 def pdiff(F_u, h_u, F_v, h_v):
@@ -111,14 +121,21 @@ def tightened_state_set(F_x, h_x, state_uncert):
 
 def getCONSPOLY(xmax=XMAX, xmin=XMIN, umax=UMAX, umin=UMIN, state_uncert=(0.02, 5e-4, 0.0, 0.0), x_wp=X_WP,
                 u_wp=U_WP):
-    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d] of getCONSPOLY.m for the reference's default
-    uncertainty bound; other bounds need the MPT-free set computation (lbmpc_b200.sets, when present)."""
-    if not np.allclose(state_uncert, (0.02, 5e-4, 0.0, 0.0)):
-        raise NotImplementedError("only the reference's default state_uncert ships as data")
+    """[F_x,h_x,F_u,h_u,F_w_N,h_w_N,F_x_d,h_x_d] of getCONSPOLY.m.  The reference's default uncertainty bound ships as
+    data (the values of its own MPT run, examples/DSS_NMPC.m); any other bound or box is computed here by the MPT-free
+    restatement in lbmpc_b200.sets (which reproduces the shipped sets, tests/test_sets.py)."""
     F_x, h_x, F_u, h_u = _boxes(xmax, xmin, umax, umin, x_wp, u_wp)
-    d = np.load(_DATA)
-    return (F_x, h_x, F_u, h_u, d["lbmpc_F_w_N"].copy(), d["lbmpc_h_w_N"].copy(), d["lbmpc_F_x_d"].copy(),
-            d["lbmpc_h_x_d"].copy())
+    default = (np.allclose(state_uncert, (0.02, 5e-4, 0.0, 0.0)) and np.allclose(xmax, XMAX) and np.allclose(xmin, XMIN)
+               and np.allclose(umax, UMAX) and np.allclose(umin, UMIN) and np.allclose(x_wp, X_WP) and np.allclose(u_wp, U_WP))
+    if default:
+        d = np.load(_DATA)
+        return (F_x, h_x, F_u, h_u, d["lbmpc_F_w_N"].copy(), d["lbmpc_h_w_N"].copy(), d["lbmpc_F_x_d"].copy(),
+                d["lbmpc_h_x_d"].copy())
+    from .sets import lbmpc_terminal_set
+    A, B, C, _, _ = mgcmDLTI()
+    _, _, Q, R, _, _, _, LAMBDA, PSI, L0, P0 = matOCP(A, B, C)
+    F_w_N, h_w_N, F_x_d, h_x_d = lbmpc_terminal_set(A, B, Q, R, LAMBDA, PSI, F_x, h_x, F_u, h_u, state_uncert, L0, P0)
+    return F_x, h_x, F_u, h_u, F_w_N, h_w_N, F_x_d, h_x_d
 
 
 def moore_greitzer_model(variant="LMPC"):
@@ -136,11 +153,12 @@ def moore_greitzer_model(variant="LMPC"):
     return mdl
 
 
-def double_integrator_model(lam=0.99):
+def double_integrator_model(lam=0.99, invariant=False):
     """The second problem shape of the reference (matlab/trackingMPC/RunExample.m): sampled double integrator with two
     inputs (:20-28), LQR gain, P = dare(A+BK,B,Q,R), T = 100 P (:57-62), boxes |x| <= 5, |u| <= 0.3 (:64-67), steady-state
     parametrisation null space (:40-45) and the extended admissible set X_ext of (x, theta) written out in closed form at
-    :84-93 (the MPT invariant-set iteration that follows it, :105-108, stays offline: out of scope).  nx = nu = nt = 2."""
+    :84-93.  invariant=True replaces it by the maximal positively invariant subset the reference then computes with
+    MPT (:105-108, compute_MPIS.m) — here by lbmpc_b200.sets.compute_mpis.  nx = nu = nt = 2."""
     A = np.array([[1.0, 1.0], [0.0, 1.0]])
     B = np.array([[0.0, 0.5], [1.0, 0.5]])
     Cm = np.array([[1.0, 0.0]])
@@ -158,5 +176,9 @@ def double_integrator_model(lam=0.99):
     F_w = np.block([[F_x, np.zeros((2 * n, m))], [np.zeros((2 * n, n)), F_x @ LAMBDA], [F_u @ K, F_u @ L],
                     [np.zeros((2 * m, n)), F_u @ PSI]])
     h_w = np.concatenate([h_x, lam * h_x, h_u, lam * h_u])
+    if invariant:
+        from .sets import compute_mpis, min_hrep
+        Ak = np.block([[A + B @ K, B @ L], [np.zeros((m, n)), np.eye(m)]])
+        F_w, h_w = min_hrep(*compute_mpis(F_w, h_w, Ak)[:2])
     return dict(A=A, B=B, K=K, Q=Q, R=R, P=P, T=T, Mtheta=Mtheta, LAMBDA=LAMBDA, PSI=PSI, F_x=F_x, h_x=h_x, F_u=F_u, h_u=h_u,
                 F_w_N=F_w, h_w_N=h_w, x_wp=np.zeros(n), u_wp=np.zeros(m))
