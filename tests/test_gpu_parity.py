@@ -237,6 +237,71 @@ def test_full_size_properties_config3(models):
     assert_parity({k: v[:512] for k, v in got.items()}, ref)
 
 
+def test_full_size_properties_config4(fx, models):
+    """BASELINE.json configs[3] at its full shape (C-form LBMPC, N=200, learned-oracle offsets from train_data.mat
+    windows, batch 65536 cut to 16384 to keep the test short): dynamics with the offsets hold along every optimal
+    trajectory, rows are satisfied, the result does not depend on where a QP sits in the batch, and a sample matches
+    the oracle."""
+    import torch
+    mdl = models["LBMPC"]
+    nb, N, q = 16384, 200, 100
+    data = fx["casadi_train_data__data"]
+    rng = np.random.default_rng(2)
+    offs = rng.integers(0, data.shape[1] - q, nb)
+    idx = offs[:, None] + np.arange(q)[None, :]
+    Xw = np.ascontiguousarray(data[:3][:, idx].transpose(1, 2, 0))
+    Yw = np.ascontiguousarray(data[3:7][:, idx].transpose(1, 2, 0))
+    X0 = sample_ics(nb, seed=2)
+    sol = solver(mdl, "C", "LBMPC", N, max_batch=nb)
+    d_off = sol.oracle_apply(X0, np.zeros((nb, N, 1)), Xw, Yw)
+    got = sol.solve_batch(X0, None, d_off)
+    ok = got["status"] == 0
+    assert set(np.unique(got["status"])) <= {0, 2} and 0.9 < ok.mean() < 1.0
+    u, x = got["uc"][ok][:, :, 0], got["xtraj"][ok]
+    A, B = mdl["A"], mdl["B"][:, 0]
+    xr = np.empty_like(x)
+    xr[:, 0] = X0[ok]
+    for k in range(N):
+        xr[:, k + 1] = xr[:, k] @ A.T + np.outer(u[:, k], B) + d_off[ok][:, k]
+    assert np.abs(xr - x).max() < 1e-9
+    assert (np.abs(u) <= mdl["h_u"][0] + 1e-8).all()
+    assert (x[:, 1:, :] <= mdl["h_x"][:4] + 1e-8).all() and (-x[:, 1:, :] <= mdl["h_x"][4:] + 1e-8).all()
+    z1 = np.concatenate([x[:, 1, :], got["theta"][ok]], axis=1)
+    assert (z1 @ mdl["F_w_N"].T - mdl["h_w_N"]).max() < 1e-8 and (x[:, 1, :] @ mdl["F_x_d"].T - mdl["h_x_d"]).max() < 1e-8
+    perm = rng.permutation(nb)[:2048]                             # the same QPs as a small batch (CTA-per-QP kernel)
+    sub = sol.solve_batch(X0[perm], None, d_off[perm])
+    assert np.array_equal(sub["status"], got["status"][perm]) and np.abs(sub["iters"] - got["iters"][perm]).max() <= 1
+    both = (sub["status"] == 0) & (sub["iters"] == got["iters"][perm])
+    assert np.abs(sub["obj"][both] - got["obj"][perm][both]).max() < 1e-9
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0[:128], None, d_off[:128], nthreads=8)
+    assert_parity({k: v[:128] for k, v in got.items()}, ref)
+
+
+def test_full_size_properties_config5(models):
+    """BASELINE.json configs[4] (Monte-Carlo closed loop, randomised disturbance, learned oracle) at a full per-launch
+    width: the outcome of a scenario depends on its GLOBAL index only — one 20000-scenario call and four 5000-scenario
+    calls with scenario0 offsets agree bit for bit (that is what makes the 8-GPU sharding exact) — the plant states stay
+    finite, and scenario 0 matches the CPU loop."""
+    mdl = models["LBMPC"]
+    nb, steps = 20000, 4
+    x_init = X_EQ + sample_ics(nb, seed=3)
+    wbar = np.array([0.02, 5e-4, 0.0, 0.0])
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb)
+    whole = sol.closed_loop(x_init, steps, X_EQ, U_EQ, q=100, use_oracle=True, wbar=wbar, seed=7)
+    for r in range(4):
+        sl = slice(5000 * r, 5000 * (r + 1))
+        part = sol.closed_loop(x_init[sl], steps, X_EQ, U_EQ, q=100, use_oracle=True, wbar=wbar, seed=7, scenario0=5000 * r)
+        for k in ("x", "u", "theta", "iters", "status"):
+            assert np.array_equal(part[k], whole[k][sl]), (r, k)
+    assert np.isfinite(whole["x"]).all() and set(np.unique(whole["status"])) <= {0, 2}
+    P = OracleProblem("C", "LBMPC", mdl, 50)
+    for b in (0, 1):
+        ref = P.closed_loop(X_EQ, U_EQ, x_init[b], steps, q=100, use_oracle=True, wbar=wbar, seed=7, scenario=b)
+        assert np.array_equal(ref["status"], whole["status"][b])
+        if (ref["status"] == 0).all():
+            assert np.abs(ref["x"] - whole["x"][b]).max() < 1e-7
+
+
 def test_oracle_apply_matches_l2nw(fx, models):
     """learnedModel.m:25 + oracleL2NW.m / casadiL2NW.m along the horizon, on windows of train_data.mat."""
     mdl = models["LBMPC"]
