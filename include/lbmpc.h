@@ -113,6 +113,16 @@ int lbmpc_solve_batch(lbmpc_handle *h, int64_t batch, const double *dx0, const d
                       const double *d_off, const double *warm, double *u_or_c, double *theta,
                       double *x_traj, double *obj, int32_t *iters, int32_t *status, void *stream);
 
+/* lbmpc_solve_batch with a per-stage COST SHIFT: the objective is evaluated at x_k + cost_shift_k while the dynamics and
+ * every constraint row act on x_k (cost_shift: nx x (N+1) x batch, NULL = lbmpc_solve_batch).  This is the twin-sequence
+ * problem of DMS_LBMPC_casadi.m:252-319 — learned states xl in costfunction (:252-268), nominal states x in
+ * nonlinearconstraints (:283-319) — with the oracle frozen: e_k = xl_k - x_k obeys e_{k+1} = A e_k + g_k, e_0 = 0 and does
+ * not depend on the optimisation variables (lbmpc_solve_sqp with twin = 1 builds it). */
+int lbmpc_solve_batch_shifted(lbmpc_handle *h, int64_t batch, const double *dx0, const double *dx_ref,
+                              const double *d_off, const double *cost_shift, const double *warm,
+                              double *u_or_c, double *theta, double *x_traj, double *obj, int32_t *iters,
+                              int32_t *status, void *stream);
+
 /* replaces learnedModel.m:25 + oracleL2NW.m:2-36 (mask variant casadiL2NW.m:14-28) applied along
  * the horizon: rolls the learned model x+ = A x + B u + g([x1;x2;u]) for the given input sequence
  * and returns the per-stage corrections d_k = g(.) (feed them to lbmpc_solve_batch as d_off).

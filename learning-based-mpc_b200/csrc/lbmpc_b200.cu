@@ -58,7 +58,7 @@ struct lbmpc_handle {
     bool prof_on = false;
     // host-pointer staging
     double *s_dx0 = nullptr, *s_ref = nullptr, *s_doff = nullptr, *s_warm = nullptr, *s_uc = nullptr,
-           *s_x = nullptr;
+           *s_x = nullptr, *s_csh = nullptr;
     // theta | obj | iters | status of a call, packed back to back for the ACTUAL batch: one device-to-host copy into a
     // pinned host block instead of four small ones, scattered to the caller's arrays after the stream synchronises
     char *s_small = nullptr, *hs_small = nullptr;
@@ -297,6 +297,12 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
 int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
                       const double* warm, double* u_or_c, double* theta, double* x_traj, double* obj, int32_t* iters,
                       int32_t* status, void* stream) {
+    return lbmpc_solve_batch_shifted(h, batch, dx0, dx_ref, d_off, nullptr, warm, u_or_c, theta, x_traj, obj, iters, status, stream);
+}
+
+int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
+                              const double* cost_shift, const double* warm, double* u_or_c, double* theta, double* x_traj,
+                              double* obj, int32_t* iters, int32_t* status, void* stream) {
     if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
     if (batch < 0) return fail(LBMPC_EINVAL, "negative batch");
     if (batch == 0) return LBMPC_OK;
@@ -310,7 +316,7 @@ int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const d
     io.queue = h->dqueue;
     io.prof = h->prof_on ? h->dprof : nullptr;
     if (h->dev_ptrs) {
-        io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm;
+        io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm; io.cshift = cost_shift;
         io.uc = u_or_c; io.theta = theta; io.xtraj = x_traj; io.obj = obj; io.iters = iters; io.status = status;
         CU_TRY(cudaEventRecord(h->ev0, st));
         CU_TRY(launch_ipm_any(h, io, st));
@@ -333,6 +339,11 @@ int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const d
     if (dx_ref && !a_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
     if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, sizeof(double) * b * nx * N, cudaMemcpyHostToDevice, st));
     if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, sizeof(double) * b * (nu * N + nt), cudaMemcpyHostToDevice, st));
+    if (cost_shift) {
+        if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * nx * (N + 1)));  // first use only
+        CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, sizeof(double) * b * nx * (N + 1), cudaMemcpyHostToDevice, st));
+        io.cshift = h->s_csh;
+    }
     io.dx0 = a_dx0 ? a_dx0 : h->s_dx0;
     io.dx_ref = dx_ref ? (a_ref ? a_ref : h->s_ref) : nullptr;
     io.d_off = d_off ? h->s_doff : nullptr;
@@ -619,7 +630,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     free_loop(h->loop);
     cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
-    cudaFree(h->s_x); cudaFree(h->s_small);
+    cudaFree(h->s_x); cudaFree(h->s_small); cudaFree(h->s_csh);
     if (h->hs_small) cudaFreeHost(h->hs_small);
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -282,9 +282,12 @@ struct Core {
     // g (cost gradient + G'lambda), q (Newton rhs on the bounded variables) and the Farkas input
     // (G'lambda of the box rows, g-layout, first NV fields of record R3); accumulates reductions.
     // ============================================================================================
-    static LB_HD void asm_core(const P& p, const L& l, double* s, int k, unsigned rows, const StageRows& r, RedAsm& red) {
-        double v[NV], g[NV];
+    static LB_HD void asm_core(const P& p, const L& l, double* s, int k, unsigned rows, const StageRows& r, RedAsm& red,
+                              const double* csh = nullptr) {
+        double v[NV], g[NV], e[NX];
         const bool last = k >= p.N;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) e[j] = csh ? csh[k * NX + j] : 0.0;  // cost evaluated at x + e_k (twin state sequences)
 #pragma unroll
         for (int j = 0; j < NX; ++j) v[j] = r.v[j];
 #pragma unroll
@@ -297,8 +300,9 @@ struct Core {
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int b = 0; b < NV; ++b) {
-                if (b & 1) a1 += W[a * NV + b] * v[b];
-                else a0 += W[a * NV + b] * v[b];
+                const double vb = b < NX ? v[b] + e[b < NX ? b : 0] : v[b];
+                if (b & 1) a1 += W[a * NV + b] * vb;
+                else a0 += W[a * NV + b] * vb;
             }
             g[a] = (last && a >= NZ) ? 0.0 : a0 + a1;
         }
@@ -341,7 +345,7 @@ struct Core {
         red.gth += g[NX];
     }
     // fresh QP: initial slacks and multipliers s = max(h - a v, 1), lambda = 1, then the assembly
-    static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red) {
+    static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red, const double* csh = nullptr) {
         const unsigned rows = stage_rows(p, k);
         StageRows r;
         double* r1 = s + l.r1(k);
@@ -361,10 +365,11 @@ struct Core {
                 }
             }
         }
-        asm_core(p, l, s, k, rows, r, red);
+        asm_core(p, l, s, k, rows, r, red, csh);
     }
     // running QP: apply the step parked by final_stage (ds, dl in the scratch block; dx, du), then the assembly
-    static LB_HD void update_assemble_stage(const P& p, const L& l, double* s, int k, double alpha, RedAsm& red) {
+    static LB_HD void update_assemble_stage(const P& p, const L& l, double* s, int k, double alpha, RedAsm& red,
+                                           const double* csh = nullptr) {
         const unsigned rows = stage_rows(p, k);
         StageRows r;
         load_rows(l, s, k, r);
@@ -387,7 +392,7 @@ struct Core {
                 r1[j] = r.v[j];
             }
         }
-        asm_core(p, l, s, k, rows, r, red);
+        asm_core(p, l, s, k, rows, r, red, csh);
     }
 
     // ============================================================================================
@@ -440,14 +445,15 @@ struct Core {
         if (j < NX || k < p.N) r1[j] += alpha * r3[j];
     }
     // cost gradient row a of stage k: W_type(k)[a,:] v_k (+ lin at kT)
-    static LB_HD double grad_row(const P& p, const RowTab& T, const L& l, const double* s, int k, int a) {
+    static LB_HD double grad_row(const P& p, const RowTab& T, const L& l, const double* s, int k, int a, const double* csh = nullptr) {
         const bool last = k >= p.N;
         const double* r1 = s + l.r1(k);
         const double* W = T.W[stage_type(p, k)] + a * NV;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int b = 0; b < NV; ++b) {
-            const double vb = b < NX ? r1[b] : (b < NZ ? s[l.o_misc + L::M_TH + (b - NX)] : (last ? 0.0 : r1[NX + (b - NZ)]));
+            const double vb = b < NX ? r1[b] + (csh ? csh[k * NX + (b < NX ? b : 0)] : 0.0)
+                                     : (b < NZ ? s[l.o_misc + L::M_TH + (b - NX)] : (last ? 0.0 : r1[NX + (b - NZ)]));
             if (b & 1) a1 += W[b] * vb;
             else a0 += W[b] * vb;
         }
@@ -456,23 +462,23 @@ struct Core {
         return g;
     }
     // theta rows of stage k: gradient only
-    static LB_HD void asm_theta_item(const P& p, const RowTab& T, const L& l, double* s, int k, RedAsm& red) {
+    static LB_HD void asm_theta_item(const P& p, const RowTab& T, const L& l, double* s, int k, RedAsm& red, const double* csh = nullptr) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const double g = grad_row(p, T, l, s, k, NX + t);
+            const double g = grad_row(p, T, l, s, k, NX + t, csh);
             s[l.r2(k) + L::F_G + NX + t] = g;
             s[l.r3(k) + NX + t] = 0.0;
             if (t == 0) red.gth += g;
         }
     }
     // predictor assembly of item (k, j): cost gradient row, barrier diagonal, Newton rhs, Farkas input, reductions
-    static LB_HD void asm_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedAsm& red) {
+    static LB_HD void asm_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedAsm& red, const double* csh = nullptr) {
         const bool last = k >= p.N;
         const double* r1 = s + l.r1(k);
         double* r2 = s + l.r2(k);
         double* r3 = s + l.r3(k);
         const int a = zidx(j);
-        const double g = grad_row(p, T, l, s, k, a);
+        const double g = grad_row(p, T, l, s, k, a, csh);
         const unsigned rows = stage_rows(p, k);
         const double vj = (last && j >= NX) ? 0.0 : r1[j];
         double qd = 0.0, gl = 0.0, gp = 0.0;
@@ -1518,10 +1524,10 @@ struct Core {
     }
 
     // stage: objective contribution 0.5 v'W v (+ lin'z at kT)
-    static LB_HD double objective_stage(const P& p, const L& l, const double* s, int k) {
+    static LB_HD double objective_stage(const P& p, const L& l, const double* s, int k, const double* csh = nullptr) {
         double v[NV];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)];
+        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)] + (csh ? csh[k * NX + j] : 0.0);
 #pragma unroll
         for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
         const bool last = k >= p.N;

@@ -192,6 +192,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
 
         int iters = 0, status = 1;  // LBMPC_ST_MAXITER unless a verdict is reached
         double alpha = 0.0;
+        const double* const csh = io.cshift ? io.cshift + q * (long long)((N + 1) * NX) : nullptr;
         LB_PROF(0)
         for (;;) {
             // ================= phase E+A: apply the previous step (or initialise the rows), predictor assembly =================
@@ -204,8 +205,8 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
             __syncthreads();  // the new iterate of a stage is read by all its items and by the polytope rows
             {
                 RedAsm ra{0.0, 0.0, 0.0, 0.0, 0.0};
-                for (int it = tid; it < nitems; it += kCtaThreads) C::asm_item(p, tab, l, slot, it / NVB, it % NVB, ra);
-                for (int k = tid; k <= N; k += kCtaThreads) C::asm_theta_item(p, tab, l, slot, N - k, ra);  // from the other end: spreads the work
+                for (int it = tid; it < nitems; it += kCtaThreads) C::asm_item(p, tab, l, slot, it / NVB, it % NVB, ra, csh);
+                for (int k = tid; k <= N; k += kCtaThreads) C::asm_theta_item(p, tab, l, slot, N - k, ra, csh);  // from the other end: spreads the work
                 double acc[NOUT];
                 if (BIG) {
 #pragma unroll
@@ -379,7 +380,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
         // ---- results ----
         {
             double J = 0.0;
-            for (int k = tid; k <= N; k += kCtaThreads) J += C::objective_stage(p, l, slot, k);
+            for (int k = tid; k <= N; k += kCtaThreads) J += C::objective_stage(p, l, slot, k, csh);
             double sm[1] = {J}, mx[1] = {0.0};
             block_reduce<W, 1, 1>(sm, mx, red, warp, lane);
             for (int k = tid; k < N; k += kCtaThreads) {

@@ -38,6 +38,7 @@ struct BatchIO {
     int *iters, *status;
     unsigned long long* queue;  // global work counter (zeroed before launch)
     unsigned long long* prof;   // optional (may be null): per-phase SM cycles of CTA 0, see lbmpc_debug_phase_cycles
+    const double* cshift;       // optional NX x (N+1) per QP: the cost is evaluated at x_k + cshift_k (twin state sequences)
     int lockstep;               // warp kernel: the warps of a CTA start every iteration together (see cta_tick)
 };
 
@@ -306,6 +307,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
 
         int iters = 0, status = 1;  // LBMPC_ST_MAXITER unless a verdict is reached
         double alpha = 0.0;
+        const double* const csh = io.cshift ? io.cshift + q * (long long)((N + 1) * NX) : nullptr;
         LB_PROF(0)
         for (;;) {
             if (io.lockstep) cta_tick(true);
@@ -316,9 +318,9 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             {
                 RedAsm ra{0.0, 0.0, 0.0, 0.0, 0.0};
                 if (iters > 0) {
-                    for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra);
+                    for (int k = lane; k <= N; k += 32) C::update_assemble_stage(p, l, slot, k, alpha, ra, csh);
                 } else {
-                    for (int k = lane; k <= N; k += 32) C::init_assemble_stage(p, l, slot, k, ra);
+                    for (int k = lane; k <= N; k += 32) C::init_assemble_stage(p, l, slot, k, ra, csh);
                     for (int i = lane; i < p.ng; i += 32) C::init_rows_gen(p, l, slot, Gs, hgs, i);
                 }
                 __syncwarp();  // x_kg of the new iterate is read by the polytope rows
@@ -497,7 +499,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         // ---- results ----
         {
             double J = 0.0;
-            for (int k = lane; k <= N; k += 32) J += C::objective_stage(p, l, slot, k);
+            for (int k = lane; k <= N; k += 32) J += C::objective_stage(p, l, slot, k, csh);
             J = warp_sum(J);
             for (int k = lane; k < N; k += 32) {
 #pragma unroll

@@ -101,6 +101,8 @@ def load_library(path=None):
     lib.lbmpc_create.restype = C.c_int
     lib.lbmpc_solve_batch.argtypes = [vp, C.c_int64] + [vp] * 10 + [vp]
     lib.lbmpc_solve_batch.restype = C.c_int
+    lib.lbmpc_solve_batch_shifted.argtypes = [vp, C.c_int64] + [vp] * 11 + [vp]
+    lib.lbmpc_solve_batch_shifted.restype = C.c_int
     lib.lbmpc_oracle_apply.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [vp]
     lib.lbmpc_oracle_apply.restype = C.c_int
     lib.lbmpc_solve_sqp.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
@@ -207,25 +209,27 @@ class Solver:
             raise LbmpcError(f"{what} failed ({rc}): {self.lib.lbmpc_last_error().decode()}")
 
     # -- host-pointer API -----------------------------------------------------------------------
-    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, want_x=True, stream=None, out=None):
+    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, want_x=True, stream=None, out=None, cost_shift=None):
+        """lbmpc_solve_batch; with cost_shift (batch,N+1,nx) lbmpc_solve_batch_shifted: objective at x_k + cost_shift_k."""
         if self.device_pointers:
-            return self._solve_device(dx0, dx_ref, d_off, warm, want_x, stream, out)
+            return self._solve_device(dx0, dx_ref, d_off, warm, want_x, stream, out, cost_shift)
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
         dx0 = np.ascontiguousarray(dx0, np.float64).reshape(-1, nx)
         nb = dx0.shape[0]
         c = lambda a, shp: None if a is None else np.ascontiguousarray(a, np.float64).reshape(shp)
         dx_ref, d_off, warm = c(dx_ref, (nb, nx)), c(d_off, (nb, N, nx)), c(warm, (nb, N * nu + nt))
+        cost_shift = c(cost_shift, (nb, N + 1, nx))
         o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)),
                  xtraj=np.empty((nb, N + 1, nx)) if want_x else None, obj=np.empty(nb),
                  iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32))
-        rc = self.lib.lbmpc_solve_batch(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(warm), _ptr(o["uc"]),
-                                        _ptr(o["theta"]), _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]),
-                                        _ptr(o["status"]), None)
+        rc = self.lib.lbmpc_solve_batch_shifted(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
+                                                _ptr(o["uc"]), _ptr(o["theta"]), _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]),
+                                                _ptr(o["status"]), None)
         self._check(rc, "lbmpc_solve_batch")
         return o
 
     # -- device-pointer API (torch tensors; torch is plumbing for device memory and streams) ----
-    def _solve_device(self, dx0, dx_ref, d_off, warm, want_x, stream, out):
+    def _solve_device(self, dx0, dx_ref, d_off, warm, want_x, stream, out, cost_shift=None):
         import torch
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
         nb = dx0.shape[0]
@@ -238,9 +242,9 @@ class Solver:
                        iters=torch.empty(nb, dtype=torch.int32, device=dev),
                        status=torch.empty(nb, dtype=torch.int32, device=dev))
         st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
-        rc = self.lib.lbmpc_solve_batch(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(warm),
-                                        _ptr(out["uc"]), _ptr(out["theta"]), _ptr(out.get("xtraj")), _ptr(out["obj"]),
-                                        _ptr(out["iters"]), _ptr(out["status"]), C.c_void_p(st))
+        rc = self.lib.lbmpc_solve_batch_shifted(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
+                                                _ptr(out["uc"]), _ptr(out["theta"]), _ptr(out.get("xtraj")), _ptr(out["obj"]),
+                                                _ptr(out["iters"]), _ptr(out["status"]), C.c_void_p(st))
         self._check(rc, "lbmpc_solve_batch")
         return out
 

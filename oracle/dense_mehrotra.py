@@ -17,12 +17,13 @@ Only tests/ may import this module.
 import numpy as np
 
 
-def condensed_qp(form, variant, mdl, N, dx0, dx_ref=None, delta=0.01, d_off=None):
+def condensed_qp(form, variant, mdl, N, dx0, dx_ref=None, delta=0.01, d_off=None, cost_shift=None):
     """Return (H, g, c0, G, h, meta) with J(y) = 0.5 y'Hy + g'y + c0 and rows G y <= h.
 
     form    'F' (fmincon scripts, y=[c;theta]) or 'C' (CasADi scripts, y=[du;theta])
     variant 'LMPC' (terminal set on last state) or 'LBMPC' (robust rows on x_1)
     mdl     dict with A,B,K,Q,R,P,T,LAMBDA,PSI,F_x,h_x,F_u,h_u,F_w_N,h_w_N[,F_x_d,h_x_d]
+    cost_shift (N+1, n): the objective sees x_k + cost_shift_k, the rows see x_k (twin sequences, DMS_LBMPC_casadi.m:252-319)
     """
     A, B, K = mdl["A"], mdl["B"], mdl["K"]
     n, m = B.shape
@@ -67,10 +68,11 @@ def condensed_qp(form, variant, mdl, N, dx0, dx_ref=None, delta=0.01, d_off=None
         stages, sc = range(N), delta                 # k=1..N, delta-scaled (…casadi.m:233-237)
     else:
         stages, sc = range(N - 2), 1.0               # "if k < N-1" (costLMPC.m:30)
+    ek = (lambda k: 0.0) if cost_shift is None else (lambda k: np.asarray(cost_shift, float)[k])
     for k in stages:
-        add_quad(Xmap[k] - Lam @ Th, Xoff[k], Q, sc)
+        add_quad(Xmap[k] - Lam @ Th, Xoff[k] + ek(k), Q, sc)
         add_quad(Umap[k] - Psi @ Th, Uoff[k], R, sc)
-    add_quad(Xmap[N] - Lam @ Th, Xoff[N], P, 1.0)    # terminal cost on x_N
+    add_quad(Xmap[N] - Lam @ Th, Xoff[N] + ek(N), P, 1.0)    # terminal cost on x_N
     add_quad(Lam @ Th, -dx_ref, T, 1.0)              # (LAMBDA*theta - xs)'T(.)
     rows, rhs = [], []
 

@@ -354,6 +354,7 @@ typedef struct {
     double P0tt_inv[MAXNT * MAXNT];
     double *dx, *du, dth[MAXNT];
     double lin[MAXNZ], cconst;
+    const double *csh;                       /* (N+1)*nx or NULL: the cost is evaluated at x_k + csh_k (twin sequences) */
     double flops;
 } lbo_ws;
 
@@ -415,7 +416,7 @@ static void assemble(const lbo_problem *p, lbo_ws *w, int corr, double sigmu, do
         for (int k = 0; k <= N; ++k) {
             const double *W = p->W[p->wtype[k]];
             double v[MAXNV];
-            for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j];
+            for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (w->csh ? w->csh[k * nx + j] : 0.0);
             for (int j = 0; j < p->nt; ++j) v[nx + j] = w->th[j];
             for (int j = 0; j < nu; ++j) v[nz + j] = (k < N) ? w->u[k * nu + j] : 0.0;
             int lim = (k < N) ? nv : nz;
@@ -819,7 +820,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
     for (int k = 0; k <= N; ++k) {
         const double *W = p->W[p->wtype[k]];
         double v[MAXNV];
-        for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j];
+        for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (w->csh ? w->csh[k * nx + j] : 0.0);
         for (int j = 0; j < nt; ++j) v[nx + j] = w->th[j];
         for (int j = 0; j < nu; ++j) v[nz + j] = (k < N) ? w->u[k * nu + j] : 0.0;
         int lim = (k < N) ? nv : nz;
@@ -850,8 +851,18 @@ int lbo_solve(const lbo_problem *p, const double *dx0, const double *dx_ref, con
     return rc;
 }
 
+int lbo_solve_shifted(const lbo_problem *p, const double *dx0, const double *dx_ref, const double *d_off,
+                      const double *cost_shift, const double *warm, double *uc, double *theta, double *xtraj,
+                      double *obj, int *iters, int *status, double *stats) {
+    lbo_ws *w = ws_alloc(p);
+    w->csh = cost_shift;
+    int rc = solve_ws(p, w, dx0, dx_ref, d_off, warm, uc, theta, xtraj, obj, iters, status, stats);
+    ws_free(w);
+    return rc;
+}
+
 typedef struct {
-    const lbo_problem *p; long batch; const double *dx0, *dx_ref, *d_off, *warm;
+    const lbo_problem *p; long batch; const double *dx0, *dx_ref, *d_off, *warm, *csh;
     double *uc, *theta, *xtraj, *obj; int *iters, *status; long *next;
 } lbo_batch_job;
 
@@ -864,12 +875,14 @@ static void *batch_worker(void *arg) {
         long b0 = __atomic_fetch_add(j->next, 4, __ATOMIC_RELAXED);
         if (b0 >= j->batch) break;
         long b1 = b0 + 4 < j->batch ? b0 + 4 : j->batch;
-        for (long b = b0; b < b1; ++b)
+        for (long b = b0; b < b1; ++b) {
+            w->csh = j->csh ? j->csh + b * (long)(N + 1) * nx : NULL;
             solve_ws(p, w, j->dx0 + b * nx, j->dx_ref ? j->dx_ref + b * nx : NULL,
                       j->d_off ? j->d_off + b * (long)nx * N : NULL,
                       j->warm ? j->warm + b * (long)(N * nu + nt) : NULL, j->uc + b * (long)N * nu,
                       j->theta + b * nt, j->xtraj ? j->xtraj + b * (long)(N + 1) * nx : NULL,
                       j->obj + b, j->iters + b, j->status + b, NULL);
+        }
     }
     ws_free(w);
     return NULL;
@@ -879,8 +892,14 @@ static void *batch_worker(void *arg) {
 int lbo_solve_batch(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
                     const double *d_off, const double *warm, double *uc, double *theta,
                     double *xtraj, double *obj, int *iters, int *status, int nthreads) {
+    return lbo_solve_batch_shifted(p, batch, dx0, dx_ref, d_off, NULL, warm, uc, theta, xtraj, obj, iters, status, nthreads);
+}
+
+int lbo_solve_batch_shifted(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                            const double *d_off, const double *cost_shift, const double *warm, double *uc,
+                            double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads) {
     long next = 0;
-    lbo_batch_job job = {p, batch, dx0, dx_ref, d_off, warm, uc, theta, xtraj, obj, iters, status, &next};
+    lbo_batch_job job = {p, batch, dx0, dx_ref, d_off, warm, cost_shift, uc, theta, xtraj, obj, iters, status, &next};
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     pthread_t th[256];

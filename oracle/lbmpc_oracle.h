@@ -95,6 +95,17 @@ int lbo_solve_batch(const lbo_problem *p, long batch, const double *dx0, const d
                     const double *d_off, const double *warm, double *uc, double *theta,
                     double *xtraj, double *obj, int *iters, int *status, int nthreads);
 
+/* Same with a per-stage COST SHIFT: the objective is evaluated at x_k + cost_shift_k (nx*(N+1), [k][i]; NULL = 0) while
+ * the dynamics and every constraint row act on x_k.  This is the twin-sequence problem of DMS_LBMPC_casadi.m:252-319
+ * (learned states xl in costfunction :252-268, nominal states x in nonlinearconstraints :283-319) with the oracle frozen:
+ * xl_k - x_k = e_k obeys e_{k+1} = A e_k + g_k, e_0 = 0, independent of the optimisation variables. */
+int lbo_solve_shifted(const lbo_problem *p, const double *dx0, const double *dx_ref, const double *d_off,
+                      const double *cost_shift, const double *warm, double *uc, double *theta, double *xtraj,
+                      double *obj, int *iters, int *status, double *stats);
+int lbo_solve_batch_shifted(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                            const double *d_off, const double *cost_shift, const double *warm, double *uc,
+                            double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads);
+
 /* Nadaraya-Watson oracle g(xi), xi=[dx1;dx2;du]  (oracleL2NW.m:26-36).  X 3*q, Y 4*q row-major
  * ([i][j] = component i of sample j), valid q or NULL (mask variant casadiL2NW.m:18-21). */
 void lbo_oracle_l2nw(const double *X, const double *Y, const double *valid, int q, int nin,

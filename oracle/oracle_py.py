@@ -110,31 +110,33 @@ class OracleProblem:
     def num_rows(self):
         return lib().lbo_num_rows(self.h)
 
-    def solve(self, dx0, dx_ref=None, d_off=None, warm=None):
+    def solve(self, dx0, dx_ref=None, d_off=None, warm=None, cost_shift=None):
         out = self.solve_batch(np.asarray(dx0, float).reshape(1, -1),
                                None if dx_ref is None else np.asarray(dx_ref, float).reshape(1, -1),
                                None if d_off is None else np.asarray(d_off, float).reshape(1, self.N, self.nx),
-                               None if warm is None else np.asarray(warm, float).reshape(1, -1), nthreads=1, stats=True)
+                               None if warm is None else np.asarray(warm, float).reshape(1, -1), nthreads=1, stats=True,
+                               cost_shift=None if cost_shift is None else np.asarray(cost_shift, float).reshape(1, self.N + 1, self.nx))
         return {k: v[0] for k, v in out.items()}
 
-    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, nthreads=1, stats=False):
-        """dx0 (batch,nx); d_off (batch,N,nx); warm (batch,N*nu+nt).  Returns dict of arrays."""
+    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, nthreads=1, stats=False, cost_shift=None):
+        """dx0 (batch,nx); d_off (batch,N,nx); warm (batch,N*nu+nt); cost_shift (batch,N+1,nx): the objective is evaluated at
+        x_k + cost_shift_k (lbo_solve_shifted).  Returns dict of arrays."""
         L = lib()
         dx0 = _d(dx0)
         nb = dx0.shape[0]
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
-        dx_ref, d_off, warm = _d(dx_ref), _d(d_off), _d(warm)
+        dx_ref, d_off, warm, cost_shift = _d(dx_ref), _d(d_off), _d(warm), _d(cost_shift)
         uc = np.empty((nb, N, nu)); th = np.empty((nb, nt)); xt = np.empty((nb, N + 1, nx)); obj = np.empty(nb)
         it = np.empty(nb, np.int32); st = np.empty(nb, np.int32)
         out = dict(uc=uc, theta=th, xtraj=xt, obj=obj, iters=it, status=st)
         if stats and nb == 1:
             s = np.zeros(6)
-            L.lbo_solve(self.h, _p(dx0), _p(dx_ref), _p(d_off), _p(warm), _p(uc), _p(th), _p(xt), _p(obj),
-                        it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), _p(s))
+            L.lbo_solve_shifted(self.h, _p(dx0), _p(dx_ref), _p(d_off), _p(cost_shift), _p(warm), _p(uc), _p(th), _p(xt), _p(obj),
+                                it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), _p(s))
             out["stats"] = s.reshape(1, 6)
         else:
-            L.lbo_solve_batch(self.h, C.c_long(nb), _p(dx0), _p(dx_ref), _p(d_off), _p(warm), _p(uc), _p(th), _p(xt),
-                              _p(obj), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), C.c_int(nthreads))
+            L.lbo_solve_batch_shifted(self.h, C.c_long(nb), _p(dx0), _p(dx_ref), _p(d_off), _p(cost_shift), _p(warm), _p(uc),
+                                      _p(th), _p(xt), _p(obj), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), C.c_int(nthreads))
         return out
 
     def oracle_offsets(self, dx0, du, X, Y, valid=None, bandwidth=0.5, lam=0.001):

@@ -11,7 +11,7 @@
 using namespace lbmpc;
 
 template <int NX, int NT, int NU>
-static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off,
+static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off, const double* csh,
                      const double* warm, double* uc, double* theta, double* xtraj, double* obj, int* iters,
                      int* status) {
     using C = Core<NX, NT, NU>;
@@ -62,8 +62,8 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
         RedAsm ra{0, 0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) {
-            if (it == 0) C::init_assemble_stage(p, l, s, k, ra);
-            else C::update_assemble_stage(p, l, s, k, alpha, ra);
+            if (it == 0) C::init_assemble_stage(p, l, s, k, ra, csh);
+            else C::update_assemble_stage(p, l, s, k, alpha, ra, csh);
         }
         double acc[NH + 2 * NZ];
         std::memset(acc, 0, sizeof acc);
@@ -164,9 +164,9 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // the box rows / x / u step is applied at the top of the next pass (update_assemble_stage)
     }
     if (it == p.max_iter)  // ran out of iterations: apply the last step so that the outputs are the last iterate
-        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra); }
+        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra, csh); }
     double J = m[L::M_CCONST];
-    for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k);
+    for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k, csh);
     for (int k = 0; k < N; ++k)
         for (int i = 0; i < NU; ++i) {
             double v = s[l.i_u(i, k)];
@@ -187,8 +187,8 @@ extern "C" const char* emul_last_error() { return g_err.c_str(); }
 
 // same argument conventions as lbmpc_create + lbmpc_solve_batch (column-major, one column per QP)
 extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg, long batch, const double* dx0,
-                                const double* dx_ref, const double* d_off, const double* warm, double* uc,
-                                double* theta, double* xtraj, double* obj, int* iters, int* status) {
+                                const double* dx_ref, const double* d_off, const double* cost_shift, const double* warm,
+                                double* uc, double* theta, double* xtraj, double* obj, int* iters, int* status) {
     HostProblem hp;
     int rc = build_problem(mdl, cfg, hp, g_err);
     if (rc) return rc;
@@ -197,12 +197,13 @@ extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg,
         const double* x0 = dx0 + b * nx;
         const double* xr = dx_ref ? dx_ref + b * nx : nullptr;
         const double* dk = d_off ? d_off + b * (long)nx * N : nullptr;
+        const double* cs = cost_shift ? cost_shift + b * (long)nx * (N + 1) : nullptr;
         const double* wm = warm ? warm + b * (long)(nu * N + nt) : nullptr;
         double* xt = xtraj ? xtraj + b * (long)nx * (N + 1) : nullptr;
         if (nx == 4 && nt == 1 && nu == 1)
-            solve_one<4, 1, 1>(hp, x0, xr, dk, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
+            solve_one<4, 1, 1>(hp, x0, xr, dk, cs, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
         else if (nx == 2 && nt == 2 && nu == 2)
-            solve_one<2, 2, 2>(hp, x0, xr, dk, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
+            solve_one<2, 2, 2>(hp, x0, xr, dk, cs, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
         else { g_err = "emul: unsupported dims"; return LBMPC_ESHAPE; }
     }
     return 0;

@@ -11,7 +11,7 @@ from lbmpc_b200 import capi
 from oracle_py import OracleProblem
 
 
-def emul_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None):
+def emul_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None, cost_shift=None):
     m, keep = capi.pack_model(mdl)
     cfg = capi.make_config(form, variant, N)
     dx0 = np.ascontiguousarray(dx0, float)
@@ -21,8 +21,8 @@ def emul_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=No
              iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32))
     p = capi._ptr
     c = lambda a: None if a is None else np.ascontiguousarray(a, float)
-    dx_ref, d_off, warm = c(dx_ref), c(d_off), c(warm)
-    rc = lib.emul_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), p(dx0), p(dx_ref), p(d_off), p(warm), p(o["uc"]),
+    dx_ref, d_off, warm, cost_shift = c(dx_ref), c(d_off), c(warm), c(cost_shift)
+    rc = lib.emul_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), p(dx0), p(dx_ref), p(d_off), p(cost_shift), p(warm), p(o["uc"]),
                               p(o["theta"]), p(o["xtraj"]), p(o["obj"]), p(o["iters"]), p(o["status"]))
     assert rc == 0, lib.emul_last_error()
     return o
@@ -50,6 +50,24 @@ def test_core_inputs_ref_offsets_warm(emul_lib, models):
     got = emul_solve(emul_lib, mdl, "C", "LBMPC", N, X0, xref, doff, warm)
     ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, xref, doff, warm)
     assert_parity(got, ref)
+
+
+def test_core_cost_shift_twin_sequences(emul_lib, models):
+    """Objective evaluated at x_k + e_k, rows and dynamics on x_k (DMS_LBMPC_casadi.m:252-319 with the oracle frozen):
+    device math vs the oracle, both forms, with the other optional inputs present."""
+    rng = np.random.default_rng(17)
+    for form, variant, N in (("C", "LBMPC", 30), ("F", "LMPC", 20)):
+        mdl = models[variant]
+        nb = 24
+        X0 = sample_ics(nb, seed=N)
+        e = 2e-3 * rng.standard_normal((nb, N + 1, 4)).cumsum(axis=1)
+        e[:, 0] = 0.0
+        xref = (mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.05, 0.05, (nb, 1)))
+        got = emul_solve(emul_lib, mdl, form, variant, N, X0, xref, None, None, e)
+        ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, xref, cost_shift=e)
+        assert_parity(got, ref)
+        plain = OracleProblem(form, variant, mdl, N).solve_batch(X0, xref)
+        assert np.abs(plain["uc"] - ref["uc"]).max() > 1e-5                       # the shift does change the problem
 
 
 def test_long_horizon(emul_lib, models):

@@ -365,6 +365,35 @@ def test_both_solver_kernels_against_oracle(models, monkeypatch, kernel, form, N
 
 
 @pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
+    """lbmpc_solve_batch_shifted: objective at x_k + e_k, rows and dynamics on x_k (DMS_LBMPC_casadi.m:252-319 with the
+    oracle frozen), both kernels, host and device pointers, against the oracle; a zero shift changes nothing."""
+    import torch
+    monkeypatch.setenv("LBMPC_KERNEL", kernel)
+    rng = np.random.default_rng(17)
+    for form, variant, N, nb in (("C", "LBMPC", 50, 200), ("F", "LMPC", 20, 40)):
+        mdl = models[variant]
+        X0 = sample_ics(nb, seed=N + 1)
+        e = 2e-3 * rng.standard_normal((nb, N + 1, 4)).cumsum(axis=1)
+        e[:, 0] = 0.0
+        xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.05, 0.05, (nb, 1))
+        sol = solver(mdl, form, variant, N, max_batch=nb)
+        got = sol.solve_batch(X0, xref, cost_shift=e)
+        ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, xref, cost_shift=e, nthreads=8)
+        assert_parity(got, ref)
+        zero, plain = sol.solve_batch(X0, xref, cost_shift=0 * e), sol.solve_batch(X0, xref)
+        for k in ("uc", "theta", "obj", "iters", "status"):
+            assert np.array_equal(zero[k], plain[k]), k
+        assert np.abs(plain["uc"] - got["uc"]).max() > 1e-5
+        dsol = solver(mdl, form, variant, N, device_pointers=True)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dev = dsol.solve_batch(t(X0), t(xref), cost_shift=t(e))
+        torch.cuda.synchronize()
+        for k in ("uc", "theta", "obj", "iters", "status"):
+            assert np.array_equal(dev[k].cpu().numpy(), got[k]), k
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
 def test_iteration_cap_bad_inputs_and_options(models, monkeypatch, kernel):
     """Verdicts other than optimal / infeasible: the iteration cap (status 1, outputs = last iterate) and non-finite
     inputs (status 3) come out like the oracle's; a caller-supplied Farkas radius and tolerances are honoured."""

@@ -62,6 +62,23 @@ def test_cform_closed_loop_tracks_saved_trajectory(fx, models):
     assert np.abs(out["x"][1] - ref[1]).max() < 1e-7
 
 
+def test_oracle_cost_shift_vs_dense_formulation(models):
+    """Twin-sequence problem (cost on x_k + e_k, rows on x_k): Riccati oracle vs the condensed dense statement."""
+    rng = np.random.default_rng(23)
+    for form, variant, N in (("C", "LBMPC", 20), ("C", "LMPC", 12), ("F", "LBMPC", 15)):
+        mdl = models[variant]
+        dx0 = sample_ics(1, seed=N)[0] * 0.5
+        e = 3e-3 * rng.standard_normal((N + 1, 4)).cumsum(axis=0)
+        e[0] = 0.0
+        r = OracleProblem(form, variant, mdl, N).solve(dx0, cost_shift=e)
+        H, g, c0, G, h, _ = condensed_qp(form, variant, mdl, N, dx0, cost_shift=e)
+        y, s, lam, info = mehrotra_dense(H, g, G, h)
+        assert r["status"] == 0 and info["status"] == 0
+        obj = 0.5 * y @ H @ y + g @ y + c0
+        assert abs(obj - r["obj"]) <= 1e-9 * max(1.0, abs(obj))
+        assert np.abs(y[:N] - r["uc"][:, 0]).max() < 1e-7 and abs(y[N] - r["theta"][0]) < 1e-7
+
+
 @pytest.mark.parametrize("form", ["F", "C"])
 @pytest.mark.parametrize("variant", ["LMPC", "LBMPC"])
 @pytest.mark.parametrize("N", [5, 20, 50])
