@@ -149,9 +149,12 @@ int lbmpc_closed_loop(lbmpc_handle *h, int64_t batch, int32_t steps, int32_t q, 
  * L2NW oracle inside the optimisation, a non-convex NLP) as a SEQUENCE of QPs.  Outer iteration j = 0..sqp_iters-1:
  *     d_k = g([x1;x2;u]_k ; X, Y) along the learned-model rollout of the previous inputs (u^-1 = warm or 0)   [lbmpc_oracle_apply]
  *     one QP with the frozen offsets d_k, started from the previous solution                                   [lbmpc_solve_batch]
+ * twin = 0: ONE state sequence, the frozen d_k enter the dynamics (LBMPC_casadi.m / costLBMPC.m).  twin = 1: the twin
+ * sequences of DMS_LBMPC_casadi.m:252-319 — the cost sees the learned states x_k + e_k (e_{k+1} = A e_k + d_k, e_0 = 0), the
+ * constraint rows and the dynamics the nominal states x_k (lbmpc_solve_batch_shifted); x_traj returns the nominal sequence.
  * Outputs are those of the last QP; du_step (batch x sqp_iters, may be NULL) = |u^j - u^{j-1}|_inf per outer iteration.
  * C-form handles on the 4-state model; array conventions as in lbmpc_solve_batch / lbmpc_oracle_apply. */
-int lbmpc_solve_sqp(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t q, double bandwidth, double lambda,
+int lbmpc_solve_sqp(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t q, double bandwidth, double lambda,
                     const double *dx0, const double *dx_ref, const double *X, const double *Y, const double *valid,
                     const double *warm, double *u, double *theta, double *x_traj, double *obj, int32_t *iters,
                     int32_t *status, double *du_step, void *stream);

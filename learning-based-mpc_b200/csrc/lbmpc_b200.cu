@@ -69,7 +69,7 @@ struct lbmpc_handle {
     // outer-iteration (SQP) scratch, grown on demand
     int64_t sqp_batch = 0;
     int sqp_iters = 0;
-    double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr;
+    double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr, *q_csh = nullptr;
 };
 
 template <int NX, int NT, int NU>
@@ -403,7 +403,7 @@ int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwid
     return LBMPC_OK;
 }
 
-int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q, double bandwidth, double lambda,
+int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t q, double bandwidth, double lambda,
                     const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
                     const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
                     int32_t* status, double* du_step, void* stream) {
@@ -425,8 +425,11 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q
         h->q_ulin = h->q_warm = h->q_doff = h->q_step = nullptr;
         CU_TRY(dmalloc(&h->q_ulin, b * N)); CU_TRY(dmalloc(&h->q_warm, b * (N + nt)));
         CU_TRY(dmalloc(&h->q_doff, b * nx * N)); CU_TRY(dmalloc(&h->q_step, b * (size_t)sqp_iters));
+        cudaFree(h->q_csh);
+        h->q_csh = nullptr;
         h->sqp_batch = batch; h->sqp_iters = sqp_iters;
     }
+    if (twin && !h->q_csh) CU_TRY(dmalloc(&h->q_csh, (size_t)h->sqp_batch * nx * (N + 1)));
     // device views of the inputs / outputs
     const double *d_dx0 = dx0, *d_ref = dx_ref, *d_X = X, *d_Y = Y, *d_V = valid, *d_warm = warm;
     double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
@@ -456,6 +459,13 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t q
         BatchIO io{};
         io.batch = batch; io.queue = h->dqueue; io.prof = nullptr;
         io.dx0 = d_dx0; io.dx_ref = d_ref; io.d_off = h->q_doff; io.warm = j == 0 ? d_warm : h->q_warm;
+        if (twin) {  // cost on the learned sequence x + e, rows and dynamics on the nominal one
+            twin_shift_kernel<4><<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(batch, hp.N, h->dA, h->q_doff, h->q_csh);
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+            io.d_off = nullptr;
+            io.cshift = h->q_csh;
+        }
         io.uc = d_u; io.theta = d_th; io.xtraj = d_xt; io.obj = d_obj; io.iters = d_it; io.status = d_st;
         CU_TRY(launch_ipm_any(h, io, st));
         sqp_update_kernel<<<ug, 128, 0, st>>>(batch, hp.N, hp.nt, d_u, d_th, h->q_ulin, h->q_warm, du_step ? h->q_step : nullptr,
@@ -632,7 +642,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_x); cudaFree(h->s_small); cudaFree(h->s_csh);
     if (h->hs_small) cudaFreeHost(h->hs_small);
-    cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step);
+    cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

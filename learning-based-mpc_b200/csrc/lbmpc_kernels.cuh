@@ -767,6 +767,39 @@ sqp_update_kernel(long long batch, int N, int nt, const double* __restrict__ uc,
 }
 
 // ---------------------------------------------------------------------------------------------
+// twin state sequences (DMS_LBMPC_casadi.m:283-319): gap between the learned and the nominal state sequence for frozen
+// oracle corrections d_k:  e_0 = 0, e_{k+1} = A e_k + d_k   (thread per QP; feeds BatchIO::cshift)
+// ---------------------------------------------------------------------------------------------
+template <int NX>
+__global__ void __launch_bounds__(128)
+twin_shift_kernel(long long batch, int N, const double* __restrict__ A, const double* __restrict__ d_off, double* __restrict__ csh) {
+    const long long qp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qp >= batch) return;
+    double a[NX * NX], e[NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) a[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) e[i] = 0.0;
+    const double* d = d_off + qp * (long long)N * NX;
+    double* o = csh + qp * (long long)(N + 1) * NX;
+    for (int k = 0;; ++k) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) o[k * NX + i] = e[i];
+        if (k == N) break;
+        double n[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = d[k * NX + i];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += a[i * NX + j] * e[j];
+            n[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] = n[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64-FMA peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
 // 8 independent register-resident DFMA chains per thread.
 // ---------------------------------------------------------------------------------------------

@@ -105,7 +105,7 @@ def load_library(path=None):
     lib.lbmpc_solve_batch_shifted.restype = C.c_int
     lib.lbmpc_oracle_apply.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [vp]
     lib.lbmpc_oracle_apply.restype = C.c_int
-    lib.lbmpc_solve_sqp.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
+    lib.lbmpc_solve_sqp.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
     lib.lbmpc_solve_sqp.restype = C.c_int
     lib.lbmpc_closed_loop.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double,
                                       vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp]
@@ -273,9 +273,11 @@ class Solver:
         self._check(rc, "lbmpc_oracle_apply")
         return d
 
-    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, want_x=True):
+    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, want_x=True,
+                  twin=False):
         """Learned-oracle problem as a sequence of QPs (lbmpc_solve_sqp): X (batch,q,3), Y (batch,q,nx) data windows.
-        Host arrays.  Returns the last QP's solution plus du_step (batch, sqp_iters)."""
+        Host arrays.  twin: cost on the learned state sequence, rows on the nominal one (DMS_LBMPC_casadi.m).  Returns the last
+        QP's solution plus du_step (batch, sqp_iters)."""
         if self.device_pointers:
             raise LbmpcError("solve_sqp is exposed for host-pointer handles")
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
@@ -288,7 +290,7 @@ class Solver:
         o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)), xtraj=np.empty((nb, N + 1, nx)) if want_x else None,
                  obj=np.empty(nb), iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32),
                  du_step=np.empty((nb, sqp_iters)))
-        rc = self.lib.lbmpc_solve_sqp(self.h, nb, int(sqp_iters), int(q), float(bandwidth), float(lam), _ptr(dx0), _ptr(dx_ref),
+        rc = self.lib.lbmpc_solve_sqp(self.h, nb, int(sqp_iters), int(bool(twin)), int(q), float(bandwidth), float(lam), _ptr(dx0), _ptr(dx_ref),
                                       _ptr(X), _ptr(Y), _ptr(valid), _ptr(warm), _ptr(o["uc"]), _ptr(o["theta"]),
                                       _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]),
                                       _ptr(o["du_step"]), None)

@@ -172,7 +172,7 @@ static void cmd_solve_sqp(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     mwSize d3[3];
     mxArray *uc, *th, *x, *f, *it, *st, *ds;
     if (nrhs < 10)
-        mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm)");
+        mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm, twin)");
     e = lookup(get_handle(prhs[1]));
     its = (int)mxGetScalar(prhs[2]);
     if ((int)mxGetM(prhs[6]) != e->nx) mexErrMsgIdAndTxt("lbmpc:args", "dx0 must be nx x batch");
@@ -185,7 +185,7 @@ static void cmd_solve_sqp(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     it = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
     st = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
     ds = mxCreateDoubleMatrix((mwSize)(its > 0 ? its : 1), (mwSize)batch, mxREAL);
-    rc = lbmpc_solve_sqp(e->h, batch, its, (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), mxGetScalar(prhs[5]),
+    rc = lbmpc_solve_sqp(e->h, batch, its, nrhs > 12 ? (int)mxGetScalar(prhs[12]) : 0, (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), mxGetScalar(prhs[5]),
                          dptr(prhs[6]), dptr(prhs[7]), dptr(prhs[8]), dptr(prhs[9]), nrhs > 10 ? dptr(prhs[10]) : NULL,
                          nrhs > 11 ? dptr(prhs[11]) : NULL, mxGetPr(uc), mxGetPr(th), mxGetPr(x), mxGetPr(f),
                          (int32_t *)mxGetData(it), (int32_t *)mxGetData(st), mxGetPr(ds), NULL);

@@ -147,7 +147,7 @@ class OracleProblem:
                                  C.c_double(bandwidth), C.c_double(lam), _p(d))
         return d
 
-    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001):
+    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, twin=False, A=None):
         """CPU mirror of lbmpc_solve_sqp (include/lbmpc.h): oracle offsets along the previous inputs, then one QP, repeated.
         X (batch,q,3), Y (batch,q,nx), valid (batch,q) or None."""
         dx0 = np.ascontiguousarray(dx0, float).reshape(-1, self.nx)
@@ -160,7 +160,13 @@ class OracleProblem:
             for j in range(sqp_iters):
                 d = self.oracle_offsets(dx0[b], ulin, np.ascontiguousarray(X[b].T), np.ascontiguousarray(Y[b].T),
                                         None if valid is None else valid[b], bandwidth, lam)
-                o = self.solve_batch(dx0[b:b + 1], xr, d[None], w)
+                if twin:   # cost on x + e with e_{k+1} = A e_k + d_k, rows and dynamics on x
+                    e = np.zeros((N + 1, self.nx))
+                    for k in range(N):
+                        e[k + 1] = A @ e[k] + d[k]
+                    o = self.solve_batch(dx0[b:b + 1], xr, None, w, cost_shift=e[None])
+                else:
+                    o = self.solve_batch(dx0[b:b + 1], xr, d[None], w)
                 u = o["uc"][0, :, 0]
                 steps[b, j] = np.abs(u - ulin).max()
                 ulin = u.copy()

@@ -442,6 +442,18 @@ def test_sqp_outer_loop_matches_oracle_and_contracts(fx, models):
     one = sol.solve_batch(X0, d_off=sol.oracle_apply(X0, np.zeros((nb, N, 1)), Xw, Yw))  # first outer iteration = plain RTI step
     first = sol.solve_sqp(X0, Xw, Yw, sqp_iters=1)
     assert np.array_equal(one["uc"], first["uc"])
+    # twin state sequences (DMS_LBMPC_casadi.m:252-319): cost on the learned states, rows on the nominal ones
+    tw = sol.solve_sqp(X0, Xw, Yw, sqp_iters=its, twin=True)
+    tref = OracleProblem("C", "LBMPC", mdl, N).solve_sqp(X0, Xw, Yw, sqp_iters=its, twin=True, A=mdl["A"])
+    assert_parity(tw, tref)
+    okt = tref["status"] == 0
+    assert np.abs(tw["du_step"][okt] - tref["du_step"][okt]).max() < 1e-7
+    xn = tw["xtraj"][okt]                                               # the returned states are the NOMINAL sequence
+    u = tw["uc"][okt][:, :, 0]
+    for k in range(N):
+        assert np.abs(xn[:, k + 1] - (xn[:, k] @ mdl["A"].T + np.outer(u[:, k], mdl["B"][:, 0]))).max() < 1e-9
+    both = ok & okt
+    assert 1e-6 < np.abs(tw["uc"][both] - got["uc"][both]).max() < 0.5  # a different problem, not a different planet
 
 
 @pytest.mark.parametrize("form", ["F", "C"])
