@@ -127,7 +127,7 @@ s.close()
 del Xw, Yw, d_off
 
 # ---- config 5: Monte-Carlo closed loop, per-GPU share of 1 M scenarios (125 k), T = 20 steps ----
-nb, T = 125000, 20
+nb, T = 125000, 100
 s = lbmpc_b200.Solver(lbmpc_b200.moore_greitzer_model("LBMPC"), "C", "LBMPC", 50, max_batch=nb)
 x_init = X_EQ[None, :] + sample_initial_states(nb, 3)
 wbar = np.array([0.02, 5e-4, 0.0, 0.0])
