@@ -125,7 +125,7 @@ static void cmd_solve(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
     mwSize d3[3];
     mxArray *uc, *th, *x, *f, *it, *st;
     int rc;
-    if (nrhs < 3) mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve', h, dx0, dx_ref, d_off, warm)");
+    if (nrhs < 3) mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve', h, dx0, dx_ref, d_off, warm, cost_shift)");
     e = lookup(get_handle(prhs[1]));
     if ((int)mxGetM(prhs[2]) != e->nx) mexErrMsgIdAndTxt("lbmpc:args", "dx0 must be nx x batch");
     batch = (int64_t)mxGetN(prhs[2]);
@@ -136,10 +136,11 @@ static void cmd_solve(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
     f = mxCreateDoubleMatrix(1, (mwSize)batch, mxREAL);
     it = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
     st = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
-    rc = lbmpc_solve_batch(e->h, batch, dptr(prhs[2]), nrhs > 3 ? dptr(prhs[3]) : NULL,
-                           nrhs > 4 ? dptr(prhs[4]) : NULL, nrhs > 5 ? dptr(prhs[5]) : NULL, mxGetPr(uc),
-                           mxGetPr(th), mxGetPr(x), mxGetPr(f), (int32_t *)mxGetData(it), (int32_t *)mxGetData(st),
-                           NULL);
+    /* cost_shift (nx x (N+1) x batch, optional): objective at x_k + cost_shift_k — twin sequences, DMS_LBMPC_casadi.m */
+    rc = lbmpc_solve_batch_shifted(e->h, batch, dptr(prhs[2]), nrhs > 3 ? dptr(prhs[3]) : NULL,
+                                   nrhs > 4 ? dptr(prhs[4]) : NULL, nrhs > 6 ? dptr(prhs[6]) : NULL,
+                                   nrhs > 5 ? dptr(prhs[5]) : NULL, mxGetPr(uc), mxGetPr(th), mxGetPr(x), mxGetPr(f),
+                                   (int32_t *)mxGetData(it), (int32_t *)mxGetData(st), NULL);
     if (rc != LBMPC_OK) fail_rc("lbmpc_solve_batch", rc);
     plhs[0] = mxCreateStructMatrix(1, 1, 6, names);
     mxSetField(plhs[0], 0, "u_or_c", uc); mxSetField(plhs[0], 0, "theta", th); mxSetField(plhs[0], 0, "x", x);

@@ -118,6 +118,15 @@ def test_gateway_matches_c_abi(gw, models):
     assert np.array_equal(uc, ref["uc"].reshape(16, 50)) and np.array_equal(th.ravel(), ref["theta"].ravel())
     assert np.array_equal(f, ref["obj"])
     assert np.array_equal(np.transpose(x, (2, 1, 0)), ref["xtraj"].reshape(16, 51, 4))
+    # optional 7th argument: per-stage cost shift (nx x (N+1) x batch in MATLAB's column-major layout)
+    e = 2e-3 * np.random.default_rng(1).standard_normal((16, 51, 4)).cumsum(axis=1)
+    e[:, 0] = 0.0
+    e_mx = gw.mexstub_double(np.ascontiguousarray(e).ctypes.data, 4 * 51, 16)
+    rc, out, msg = _call(gw, 1, gw.mxCreateString(b"solve"), h, _dbl(gw, dx0.T), empty, empty, empty, e_mx)
+    assert rc == 0, msg
+    ref_s = lbmpc_b200.Solver(mdl, "C", "LBMPC", 50, max_batch=16).solve_batch(dx0, cost_shift=e)
+    assert np.array_equal(get("u_or_c", np.float64, (50, 16)).T, ref_s["uc"].reshape(16, 50))
+    assert not np.array_equal(ref_s["uc"], ref["uc"])
     rc, _, msg = _call(gw, 0, gw.mxCreateString(b"destroy"), h)
     assert rc == 0, msg
     rc, _, msg = _call(gw, 1, gw.mxCreateString(b"solve"), h, _dbl(gw, dx0.T))
