@@ -62,6 +62,7 @@ struct lbmpc_handle {
     // theta | obj | iters | status of a call, packed back to back for the ACTUAL batch: one device-to-host copy into a
     // pinned host block instead of four small ones, scattered to the caller's arrays after the stream synchronises
     char *s_small = nullptr, *hs_small = nullptr;
+    char* hs_bounce = nullptr;  // pinned + mapped: inputs / outputs of small host-pointer calls (kBounceBytes)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     bool timed = false;
@@ -159,6 +160,8 @@ static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream
     }
     return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
 }
+
+constexpr size_t kBounceBytes = 512 * 1024;
 
 struct SmallOut {
     double *theta, *obj;
@@ -289,6 +292,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         const size_t small = small_out(nullptr, b, nt).bytes;
         CU_TRY(dmalloc(&h->s_small, small));
         CU_TRY(cudaHostAlloc((void**)&h->hs_small, std::max<size_t>(small, 16), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc((void**)&h->hs_bounce, kBounceBytes, cudaHostAllocMapped));
     }
     *out = h;
     return LBMPC_OK;
@@ -325,7 +329,11 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
         return LBMPC_OK;
     }
     if (batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
-    // small per-QP inputs and all results go directly to / from pinned caller arrays; pageable ones are staged
+    // Where the caller's arrays live decides how they travel:
+    //  * page-locked arrays: the kernel reads / writes them in place (pinned_alias);
+    //  * pageable arrays of a SMALL call (a closed-loop step, a handful of QPs): bounced through a pinned, mapped block of
+    //    the handle — a host memcpy each way, no copy-engine operation at all, so the call costs one launch + one sync;
+    //  * pageable arrays of a large call: device staging buffers and cudaMemcpyAsync (small outputs packed into one copy).
     const double* a_dx0 = pinned_alias(dx0);
     const double* a_ref = pinned_alias(dx_ref);
     double* a_uc = pinned_alias(u_or_c);
@@ -335,13 +343,65 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
     int32_t* a_it = pinned_alias(iters);
     int32_t* a_st = pinned_alias(status);
     const bool small_direct = a_th && a_obj && a_it && a_st;
-    if (!a_dx0) CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
-    if (dx_ref && !a_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, sizeof(double) * b * nx, cudaMemcpyHostToDevice, st));
-    if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, sizeof(double) * b * nx * N, cudaMemcpyHostToDevice, st));
-    if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, sizeof(double) * b * (nu * N + nt), cudaMemcpyHostToDevice, st));
+    const size_t nb_x = sizeof(double) * b * nx, nb_doff = sizeof(double) * b * nx * N, nb_warm = sizeof(double) * b * (nu * N + nt),
+                 nb_uc = sizeof(double) * b * nu * N, nb_xt = sizeof(double) * b * nx * (N + 1);
+    const SmallOut so_sz = small_out(nullptr, b, nt);
+    const size_t bounce_need = (a_dx0 ? 0 : nb_x) + ((dx_ref && !a_ref) ? nb_x : 0) + (d_off ? nb_doff : 0) + (warm ? nb_warm : 0) +
+                               (a_uc ? 0 : nb_uc) + ((x_traj && !a_x) ? nb_xt : 0) + (small_direct ? 0 : so_sz.bytes) + 64;
+    if (h->hs_bounce && bounce_need <= kBounceBytes) {
+        char* cur = h->hs_bounce;  // mapped: the same address is valid on the device (unified addressing)
+        auto in = [&](const double* src, size_t bytes) -> const double* {
+            char* dst = cur;
+            memcpy(dst, src, bytes);
+            cur += (bytes + 15) & ~(size_t)15;
+            return reinterpret_cast<const double*>(dst);
+        };
+        auto out = [&](size_t bytes) -> char* {
+            char* dst = cur;
+            cur += (bytes + 15) & ~(size_t)15;
+            return dst;
+        };
+        io.dx0 = a_dx0 ? a_dx0 : in(dx0, nb_x);
+        io.dx_ref = dx_ref ? (a_ref ? a_ref : in(dx_ref, nb_x)) : nullptr;
+        io.d_off = d_off ? in(d_off, nb_doff) : nullptr;
+        io.warm = warm ? in(warm, nb_warm) : nullptr;
+        if (cost_shift) {  // read in every iteration: keep it in device memory
+            if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * nx * (N + 1)));
+            CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_xt, cudaMemcpyHostToDevice, st));
+            io.cshift = h->s_csh;
+        }
+        char* b_uc = a_uc ? nullptr : out(nb_uc);
+        char* b_xt = (x_traj && !a_x) ? out(nb_xt) : nullptr;
+        char* b_small = small_direct ? nullptr : out(so_sz.bytes);
+        const SmallOut so = small_out(b_small, b, nt);
+        io.uc = a_uc ? a_uc : reinterpret_cast<double*>(b_uc);
+        io.xtraj = x_traj ? (a_x ? a_x : reinterpret_cast<double*>(b_xt)) : nullptr;
+        io.theta = small_direct ? a_th : so.theta;
+        io.obj = small_direct ? a_obj : so.obj;
+        io.iters = small_direct ? a_it : so.iters;
+        io.status = small_direct ? a_st : so.status;
+        CU_TRY(cudaEventRecord(h->ev0, st));
+        CU_TRY(launch_ipm_any(h, io, st));
+        CU_TRY(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+        CU_TRY(cudaStreamSynchronize(st));
+        if (b_uc) memcpy(u_or_c, b_uc, nb_uc);
+        if (b_xt) memcpy(x_traj, b_xt, nb_xt);
+        if (b_small) {
+            memcpy(theta, so.theta, sizeof(double) * b * nt);
+            memcpy(obj, so.obj, sizeof(double) * b);
+            memcpy(iters, so.iters, sizeof(int) * b);
+            memcpy(status, so.status, sizeof(int) * b);
+        }
+        return LBMPC_OK;
+    }
+    if (!a_dx0) CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, nb_x, cudaMemcpyHostToDevice, st));
+    if (dx_ref && !a_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, nb_x, cudaMemcpyHostToDevice, st));
+    if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, nb_doff, cudaMemcpyHostToDevice, st));
+    if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, nb_warm, cudaMemcpyHostToDevice, st));
     if (cost_shift) {
         if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * nx * (N + 1)));  // first use only
-        CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, sizeof(double) * b * nx * (N + 1), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_xt, cudaMemcpyHostToDevice, st));
         io.cshift = h->s_csh;
     }
     io.dx0 = a_dx0 ? a_dx0 : h->s_dx0;
@@ -359,9 +419,9 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
     CU_TRY(launch_ipm_any(h, io, st));
     CU_TRY(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    if (!a_uc) CU_TRY(cudaMemcpyAsync(u_or_c, h->s_uc, sizeof(double) * b * nu * N, cudaMemcpyDeviceToHost, st));
+    if (!a_uc) CU_TRY(cudaMemcpyAsync(u_or_c, h->s_uc, nb_uc, cudaMemcpyDeviceToHost, st));
     if (!small_direct) CU_TRY(cudaMemcpyAsync(h->hs_small, h->s_small, so.bytes, cudaMemcpyDeviceToHost, st));
-    if (x_traj && !a_x) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, sizeof(double) * b * nx * (N + 1), cudaMemcpyDeviceToHost, st));
+    if (x_traj && !a_x) CU_TRY(cudaMemcpyAsync(x_traj, h->s_x, nb_xt, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     if (!small_direct) scatter_small(h, b, nt, theta, obj, iters, status);
     return LBMPC_OK;
@@ -642,6 +702,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_x); cudaFree(h->s_small); cudaFree(h->s_csh);
     if (h->hs_small) cudaFreeHost(h->hs_small);
+    if (h->hs_bounce) cudaFreeHost(h->hs_bounce);
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
