@@ -1,6 +1,8 @@
-"""Single-QP latency through the C ABI (host pointers): time of the lbmpc_solve_batch call itself vs the kernel time, for pageable\nand page-locked caller arrays.  usage: python tools/latency_one.py"""
-import sys, time, numpy as np
-sys.path.insert(0,'learning-based-mpc_b200')
+"""Single-QP latency through the C ABI (host pointers): time of the lbmpc_solve_batch call itself vs the kernel time, for pageable
+and page-locked caller arrays.  usage: python tools/latency_one.py"""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'learning-based-mpc_b200'))
 import lbmpc_b200
 from lbmpc_b200.capi import _ptr
 mdl = lbmpc_b200.moore_greitzer_model("LBMPC")
