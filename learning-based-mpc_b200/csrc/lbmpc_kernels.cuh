@@ -541,7 +541,7 @@ constexpr int kOracleMaxPerLane = 16;  // q <= 512
 
 // PER = data points held in registers per lane (4: q <= 128, the reference's q = 10/50/100; 16: q <= 512)
 template <int NX, int NU, int PER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N, long long batch, int q,
               double inv_h2, double lambda, const double* __restrict__ dx0, const double* __restrict__ du,
               long long du_ld, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ valid,
