@@ -119,11 +119,12 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_
 static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     if (h->cta_blocks_per_sm[0] <= 0) return 0;
     if (const char* e = getenv("LBMPC_KERNEL")) return e[0] == 'c' ? 4 : 0;   // warp | cta (tests, experiments)
-    // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins up to ~5 QPs per SM (1.2x at 1 and at 5
-    // QPs/SM); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
-    // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, even at 28.
-    const int per_sm = h->cta_big ? 24 : std::min(5, h->cta_blocks_per_sm[0] + 1);
-    if (batch <= (int64_t)h->num_sms * per_sm) return 4;
+    // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
+    // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
+    // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, 1.1x at 24 and is
+    // still level at 440 QPs/SM: always picked.
+    if (h->cta_big) return 4;
+    if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return 4;
     // long horizons: shared memory holds only 1-2 QPs per SM either way, so the four warps of a CTA are free (N = 200: 1.18x)
     if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return 4;
     return 0;

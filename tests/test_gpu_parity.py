@@ -365,6 +365,20 @@ def test_both_solver_kernels_against_oracle(models, monkeypatch, kernel, form, N
 
 
 @pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_both_solver_kernels_large_polytope(models, monkeypatch, kernel):
+    """616-row terminal set (tracking LMPC): the warp kernel stages the polytope in shared memory with a bulk TMA copy and
+    sums its Hessian by warp reductions, the CTA kernel reads it from global memory / L2 and block-reduces.  The engine
+    picks the CTA kernel for this set at every batch size, so the warp path is forced here to stay covered."""
+    monkeypatch.setenv("LBMPC_KERNEL", kernel)
+    mdl = models["LMPC"]
+    for form, N, nb in (("C", 50, 200), ("F", 20, 64)):
+        X0 = sample_ics(nb, seed=N + 3)
+        xref = mdl["LAMBDA"][:, 0][None, :] * np.random.default_rng(N).uniform(-0.05, 0.05, (nb, 1))
+        got = solver(mdl, form, "LMPC", N, max_batch=nb).solve_batch(X0, xref)
+        assert_parity(got, OracleProblem(form, "LMPC", mdl, N).solve_batch(X0, xref, nthreads=8))
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
 def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
     """lbmpc_solve_batch_shifted: objective at x_k + e_k, rows and dynamics on x_k (DMS_LBMPC_casadi.m:252-319 with the
     oracle frozen), both kernels, host and device pointers, against the oracle; a zero shift changes nothing."""
