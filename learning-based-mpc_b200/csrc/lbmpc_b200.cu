@@ -447,7 +447,11 @@ int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwid
         CU_TRY(cudaGetLastError());
         return LBMPC_OK;
     }
-    double *ddx0, *ddu, *dX, *dY, *dV = nullptr, *dd;
+    double *ddx0 = nullptr, *ddu = nullptr, *dX = nullptr, *dY = nullptr, *dV = nullptr, *dd = nullptr;
+    struct TmpGuard {  // staging of a host-pointer call: released on every exit path
+        double *&a, *&b, *&c, *&d, *&e, *&f;
+        ~TmpGuard() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); cudaFree(e); cudaFree(f); }
+    } tmp_guard{ddx0, ddu, dX, dY, dV, dd};
     CU_TRY(dmalloc(&ddx0, b * 4)); CU_TRY(dmalloc(&ddu, b * N)); CU_TRY(dmalloc(&dX, b * 3 * q));
     CU_TRY(dmalloc(&dY, b * 4 * q)); CU_TRY(dmalloc(&dd, b * 4 * N));
     if (valid) CU_TRY(dmalloc(&dV, b * q));
@@ -460,7 +464,6 @@ int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwid
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(d_off, dd, 8 * b * 4 * N, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    cudaFree(ddx0); cudaFree(ddu); cudaFree(dX); cudaFree(dY); cudaFree(dd); if (dV) cudaFree(dV);
     return LBMPC_OK;
 }
 
@@ -496,6 +499,10 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
     double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
     int *d_it = iters, *d_st = status;
     double *tX = nullptr, *tY = nullptr, *tV = nullptr;
+    struct TmpGuard {  // the data-window staging of a host-pointer call is released on every exit path
+        double *&a, *&b, *&c;
+        ~TmpGuard() { cudaFree(a); cudaFree(b); cudaFree(c); }
+    } tmp_guard{tX, tY, tV};
     if (!h->dev_ptrs) {
         CU_TRY(dmalloc(&tX, b * 3 * q)); CU_TRY(dmalloc(&tY, b * 4 * q));
         if (valid) CU_TRY(dmalloc(&tV, b * q));
@@ -546,7 +553,6 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
     if (du_step) CU_TRY(cudaMemcpyAsync(du_step, h->q_step, 8 * b * sqp_iters, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     scatter_small(h, b, nt, theta, obj, iters, status);
-    cudaFree(tX); cudaFree(tY); if (tV) cudaFree(tV);
     return LBMPC_OK;
 }
 
