@@ -108,7 +108,11 @@ int lbmpc_create(const lbmpc_model *model, const lbmpc_config *cfg, int device, 
  *   x_traj   nx x (N+1) x batch or NULL  OUT predicted states (delta coordinates)
  *   obj      batch OUT objective J (costLMPC.m / `res.f`)
  *   iters, status  batch OUT
- *   stream   cudaStream_t (may be NULL = default stream) */
+ *   stream   cudaStream_t (may be NULL = default stream)
+ * Host-pointer handles (pointers_on_device = 0): the call returns when the results are in the caller's arrays.  Page-locked
+ * arrays (cudaHostAlloc / cudaHostRegister) are read and written in place by the kernel; pageable arrays of a small call
+ * (<= 512 KB in total, e.g. one closed-loop step) go through a pinned mapped block of the handle, those of a large call
+ * through device staging buffers sized by max_batch.  The three routes give bit-identical results. */
 int lbmpc_solve_batch(lbmpc_handle *h, int64_t batch, const double *dx0, const double *dx_ref,
                       const double *d_off, const double *warm, double *u_or_c, double *theta,
                       double *x_traj, double *obj, int32_t *iters, int32_t *status, void *stream);
