@@ -187,6 +187,9 @@ def test_pinned_host_arrays_are_accessed_in_place(models):
     assert np.array_equal(th_pageable.numpy().reshape(ref["theta"].shape), ref["theta"])
     for k in ("uc", "xtraj", "obj", "iters", "status"):
         assert np.array_equal(o[k].numpy().reshape(ref[k].shape), ref[k]), k
+    small = sol.solve_batch(X0[:16], xref[:16])                        # pageable and small: the pinned bounce block, no copies
+    for k in ("uc", "theta", "xtraj", "obj", "iters", "status"):
+        assert np.array_equal(small[k], ref[k][:16]), k
 
 
 def test_device_pointer_mode(models):
