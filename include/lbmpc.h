@@ -14,6 +14,10 @@
  *  - all matrices are COLUMN-major doubles (MATLAB layout), dimensions passed explicitly;
  *  - batch arrays are "one column per QP": dx0 is nx x batch, u_or_c is (nu*N) x batch, ...;
  *  - the caller owns every array; the handle owns device scratch sized at create;
+ *  - a handle is NOT re-entrant: at most ONE call may be in flight per handle (work-queue counter, timing events and
+ *    staging buffers are per handle).  Device-pointer calls are asynchronous on `stream`; issue the next call of the same
+ *    handle on the SAME stream (stream order serialises them) or synchronise first.  Use one handle per host thread /
+ *    stream for concurrent solves;
  *  - return value 0 = ok, negative = error (text via lbmpc_last_error()); per-QP outcome only
  *    through status[];
  *  - there is NO CPU fallback: every call fails with LBMPC_ECUDA if no sm_100 device is usable.
@@ -48,6 +52,14 @@ extern "C" {
 #define LBMPC_ST_MAXITER 1
 #define LBMPC_ST_INFEASIBLE 2
 #define LBMPC_ST_NUMERICAL 3
+
+/* thread mapping of the solve kernel (lbmpc_set_kernel).  AUTO picks by batch size and problem shape. */
+#define LBMPC_KERNEL_AUTO 0
+#define LBMPC_KERNEL_WARP 1        /* one warp per QP, iterate in shared memory (throughput at moderate batches)      */
+#define LBMPC_KERNEL_CTA 2         /* one 4-warp CTA per QP (latency: few QPs per SM, 616-row sets, long horizons)    */
+#define LBMPC_KERNEL_STREAM 3      /* one THREAD per QP, iterate streamed from HBM (large batches, any horizon)       */
+#define LBMPC_KERNEL_STREAM_MIXED 4 /* STREAM with the direction / factor records stored in FP32 ("f32+f64": iterate,
+                                      residuals and all arithmetic stay FP64; reported separately, never the default) */
 
 typedef struct lbmpc_handle lbmpc_handle;
 
@@ -162,6 +174,14 @@ int lbmpc_solve_sqp(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t t
                     const double *dx0, const double *dx_ref, const double *X, const double *Y, const double *valid,
                     const double *warm, double *u, double *theta, double *x_traj, double *obj, int32_t *iters,
                     int32_t *status, double *du_step, void *stream);
+
+/* Force a thread mapping (LBMPC_KERNEL_*) and the lock-step tick of the warp kernel (lockstep: -1 auto, 0 off, 1 on).
+ * Every mapping runs the same algorithm: results agree to round-off (tests/test_gpu_parity.py forces each one).
+ * The environment variables LBMPC_KERNEL=warp|cta|stream|mixed and LBMPC_LOCKSTEP=0|1 set the same two values ONCE, when
+ * the handle is created. */
+int lbmpc_set_kernel(lbmpc_handle *h, int32_t kernel, int32_t lockstep);
+/* mapping the last solve call used (LBMPC_KERNEL_WARP / _CTA / _STREAM / _STREAM_MIXED; 0 before the first call) */
+int lbmpc_last_kernel(const lbmpc_handle *h);
 
 /* introspection used by the host mirrors, tests and bench */
 int lbmpc_num_rows(const lbmpc_handle *h);            /* inequality rows m of one QP                     */

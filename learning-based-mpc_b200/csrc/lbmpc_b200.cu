@@ -17,6 +17,7 @@
 #include "lbmpc_kernels.cuh"
 #include "lbmpc_kernel_cta.cuh"
 #include "lbmpc_problem.hpp"
+#include "lbmpc_stream.cuh"
 
 using namespace lbmpc;
 
@@ -53,7 +54,10 @@ struct lbmpc_handle {
     bool dev_ptrs = false;
     int64_t max_batch = 0;
     double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
-    unsigned long long* dqueue = nullptr;
+    unsigned long long* dqueue = nullptr;   // ring of kQueueRing work counters: every launch takes the next one, so a launch
+                                            // that is still running never sees its counter reset by the following call
+    int64_t queue_next = 0;
+    int last_kernel = 0;
     unsigned long long* dprof = nullptr;  // 8 counters, enabled by lbmpc_debug_phase_cycles
     bool prof_on = false;
     // host-pointer staging
@@ -71,7 +75,18 @@ struct lbmpc_handle {
     int64_t sqp_batch = 0;
     int sqp_iters = 0;
     double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr, *q_csh = nullptr;
+    // kernel choice (lbmpc_set_kernel; LBMPC_KERNEL / LBMPC_LOCKSTEP / LBMPC_STREAM_* are read ONCE, in lbmpc_create)
+    int force_kernel = LBMPC_KERNEL_AUTO, force_lockstep = -1;
+    // stream kernel (one thread per QP, iterate in HBM): workspace of the resident warps
+    int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM
+    int64_t st_min_batch = 0;          // auto choice: batches at least this large take the stream kernel
+    double* st_ws64 = nullptr;
+    void* st_wsft = nullptr;
+    size_t st_ws64_bytes = 0, st_wsft_bytes = 0;
 };
+
+constexpr int kQueueRing = 64;
+static unsigned long long* next_queue(lbmpc_handle* h) { return h->dqueue + (h->queue_next++ % kQueueRing); }
 
 template <int NX, int NT, int NU>
 static int plan_slots(lbmpc_handle* h, size_t max_smem) {
@@ -105,39 +120,106 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_
     const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
     // many QPs per warp slot: the warps of a CTA start their iterations together (shared instruction fetches, see cta_tick)
     io.lockstep = slots >= 4 && io.batch >= (int64_t)3 * grid * slots;
-    if (const char* e = getenv("LBMPC_LOCKSTEP")) io.lockstep = atoi(e) != 0;  // experiments
-    cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
+    if (h->force_lockstep >= 0) io.lockstep = h->force_lockstep;
+    io.queue = next_queue(h);
+    cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
     h->launches += 1;
+    h->last_kernel = LBMPC_KERNEL_WARP;
     return cudaGetLastError();
 }
 
 // Few QPs per SM: the launch lasts as long as its slowest QP, so the latency variant (one CTA per QP) wins; many QPs
 // per SM: the warp-per-QP kernel keeps more QPs resident.  LBMPC_KERNEL=warp|cta overrides (experiments).
-// returns 0: warp-per-QP kernel, 4 / 2: CTA-per-QP kernel with that many warps per QP
+// returns LBMPC_KERNEL_WARP / _CTA / _STREAM / _STREAM_MIXED
 static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
-    if (h->cta_blocks_per_sm[0] <= 0) return 0;
-    if (const char* e = getenv("LBMPC_KERNEL")) return e[0] == 'c' ? 4 : 0;   // warp | cta (tests, experiments)
+    const bool cta_ok = h->shape == 0 && h->cta_blocks_per_sm[0] > 0, stream_ok = h->shape == 0 && h->st_ctas_per_sm > 0;
+    if (h->force_kernel == LBMPC_KERNEL_WARP) return LBMPC_KERNEL_WARP;
+    if (h->force_kernel == LBMPC_KERNEL_CTA) return cta_ok ? LBMPC_KERNEL_CTA : LBMPC_KERNEL_WARP;
+    if (h->force_kernel == LBMPC_KERNEL_STREAM || h->force_kernel == LBMPC_KERNEL_STREAM_MIXED)
+        return stream_ok ? h->force_kernel : LBMPC_KERNEL_WARP;
+    // many QPs per SM: one thread per QP with the iterate streamed from HBM (no shared-memory residency limit)
+    if (stream_ok && h->st_min_batch > 0 && batch >= h->st_min_batch) return LBMPC_KERNEL_STREAM;
+    if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
     // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, 1.1x at 24 and is
     // still level at 440 QPs/SM: always picked.
-    if (h->cta_big) return 4;
-    if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return 4;
+    if (h->cta_big) return LBMPC_KERNEL_CTA;
+    if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return LBMPC_KERNEL_CTA;
     // long horizons: shared memory holds only 1-2 QPs per SM either way, so the four warps of a CTA are free (N = 200: 1.18x)
-    if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return 4;
-    return 0;
+    if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return LBMPC_KERNEL_CTA;
+    return LBMPC_KERNEL_WARP;
 }
-static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, int warps) {
+static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io_in, cudaStream_t st) {
     const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
-    const int per_sm = h->cta_blocks_per_sm[warps == 4 ? 0 : 1];
-    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * per_sm, io.batch);
-    cudaError_t e = cudaMemsetAsync(h->dqueue, 0, sizeof(unsigned long long), st);
+    BatchIO io = io_in;
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * h->cta_blocks_per_sm[0], io.batch);
+    io.queue = next_queue(h);
+    cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (h->cta_big) ipm_kernel_cta<4, 1, 1, 4, true><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
     else ipm_kernel_cta<4, 1, 1, 4, false><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
     h->launches += 1;
+    h->last_kernel = LBMPC_KERNEL_CTA;
+    return cudaGetLastError();
+}
+
+// ---- stream kernel: one thread per QP, workspace of the resident warps in HBM ----
+static cudaError_t stream_workspace(lbmpc_handle* h, int64_t warps, const StreamLayout<4>& l, bool mixed) {
+    const size_t need64 = (size_t)warps * l.n64 * 32 * sizeof(double);
+    const size_t needft = (size_t)warps * l.nft * 32 * (mixed ? sizeof(float) : sizeof(double));
+    if (need64 > h->st_ws64_bytes) {  // grown only when a call brings a larger layout than the one sized at create
+        cudaFree(h->st_ws64);
+        h->st_ws64 = nullptr; h->st_ws64_bytes = 0;
+        cudaError_t e = cudaMalloc((void**)&h->st_ws64, need64);
+        if (e != cudaSuccess) return e;
+        h->st_ws64_bytes = need64;
+    }
+    if (needft > h->st_wsft_bytes) {
+        cudaFree(h->st_wsft);
+        h->st_wsft = nullptr; h->st_wsft_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->st_wsft, needft);
+        if (e != cudaSuccess) return e;
+        h->st_wsft_bytes = needft;
+    }
+    return cudaSuccess;
+}
+static int64_t stream_warps(const lbmpc_handle* h, int64_t batch) {
+    const int64_t ctas = std::min<int64_t>((int64_t)h->num_sms * h->st_ctas_per_sm, (batch + 127) / 128);
+    return std::max<int64_t>(ctas, 1) * 4;
+}
+static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed) {
+    const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
+    const StreamLayout<4> l(p.N, p.ng, io.cshift != nullptr, jac != nullptr);
+    const int64_t warps = stream_warps(h, io.batch);
+    cudaError_t e = stream_workspace(h, warps, l, mixed);
+    if (e != cudaSuccess) return e;
+    unsigned long long* queue = next_queue(h);
+    e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)(warps / 4);
+    auto fill = [&](auto& s) {
+        s.batch = io.batch; s.dx0 = io.dx0; s.dx_ref = io.dx_ref; s.d_off = io.d_off; s.warm = io.warm; s.cshift = io.cshift;
+        s.jac = jac; s.uc = io.uc; s.theta = io.theta; s.xtraj = io.xtraj; s.obj = io.obj; s.iters = io.iters; s.status = io.status;
+        s.queue = queue; s.ws64 = h->st_ws64;
+    };
+    if (mixed) {
+        StreamIO<float> s{};
+        fill(s);
+        s.wsft = (float*)h->st_wsft;
+        if (jac) ipm_stream_kernel<4, true, float><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
+        else ipm_stream_kernel<4, false, float><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
+    } else {
+        StreamIO<double> s{};
+        fill(s);
+        s.wsft = (double*)h->st_wsft;
+        if (jac) ipm_stream_kernel<4, true, double><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
+        else ipm_stream_kernel<4, false, double><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
+    }
+    h->launches += 1;
+    h->last_kernel = mixed ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM;
     return cudaGetLastError();
 }
 
@@ -154,10 +236,12 @@ static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int
     h->launches += 1;
 }
 
-static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st) {
+static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, const double* jac = nullptr) {
     if (h->shape == 0) {
-        const int w = pick_kernel(h, io.batch);
-        if (w) return launch_ipm_cta(h, io, st, w);
+        const int w = jac ? (h->force_kernel == LBMPC_KERNEL_STREAM_MIXED ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM)
+                          : pick_kernel(h, io.batch);  // per-stage dynamics (LTV) exist in the stream mapping only
+        if (w == LBMPC_KERNEL_CTA) return launch_ipm_cta(h, io, st);
+        if (w == LBMPC_KERNEL_STREAM || w == LBMPC_KERNEL_STREAM_MIXED) return launch_ipm_stream(h, io, jac, st, w == LBMPC_KERNEL_STREAM_MIXED);
     }
     return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
 }
@@ -273,7 +357,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(dmalloc(&h->dhg, (size_t)hp.ngp));
     CU_TRY(dmalloc(&h->dA, (size_t)hp.nx * hp.nx));
     CU_TRY(dmalloc(&h->dB, (size_t)hp.nx * hp.nu));
-    CU_TRY(dmalloc(&h->dqueue, 1));
+    CU_TRY(dmalloc(&h->dqueue, kQueueRing));
     CU_TRY(dmalloc(&h->dprof, 16));
     CU_TRY(cudaMemset(h->dprof, 0, 16 * sizeof(unsigned long long)));
     CU_TRY(cudaMemcpy(h->dG, hp.G.data(), sizeof(double) * nz * hp.ngp, cudaMemcpyHostToDevice));
@@ -282,6 +366,21 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(cudaMemcpy(h->dB, hp.B.data(), sizeof(double) * hp.nx * hp.nu, cudaMemcpyHostToDevice));
     CU_TRY(cudaEventCreate(&h->ev0));
     CU_TRY(cudaEventCreate(&h->ev1));
+    if (h->shape == 0) {  // stream mapping: resident CTAs per SM, workspace for the largest batch of this handle
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->st_ctas_per_sm, ipm_stream_kernel<4, false, double>, 128, 0));
+        h->st_min_batch = (int64_t)h->num_sms * 64;  // >= 64 QPs (2 warps) per SM; below that the shared-memory kernels win
+        if (const char* e = getenv("LBMPC_STREAM_CTAS")) h->st_ctas_per_sm = std::max(1, std::min(h->st_ctas_per_sm, atoi(e)));
+        if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
+        if (h->max_batch >= h->st_min_batch) {
+            const StreamLayout<4> l(hp.N, hp.ng, false, false);
+            CU_TRY(stream_workspace(h, stream_warps(h, h->max_batch), l, false));
+        }
+    }
+    // experiment / test overrides, read once
+    if (const char* e = getenv("LBMPC_KERNEL"))
+        h->force_kernel = e[0] == 'c' ? LBMPC_KERNEL_CTA : e[0] == 's' ? LBMPC_KERNEL_STREAM : e[0] == 'm' ? LBMPC_KERNEL_STREAM_MIXED
+                        : e[0] == 'w' ? LBMPC_KERNEL_WARP : LBMPC_KERNEL_AUTO;
+    if (const char* e = getenv("LBMPC_LOCKSTEP")) h->force_lockstep = atoi(e) != 0;
     if (!h->dev_ptrs) {
         const size_t b = (size_t)h->max_batch, N = hp.N, nx = hp.nx, nu = hp.nu, nt = hp.nt;
         CU_TRY(dmalloc(&h->s_dx0, b * nx));
@@ -647,6 +746,17 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
     return LBMPC_OK;
 }
 
+int lbmpc_set_kernel(lbmpc_handle* h, int32_t kernel, int32_t lockstep) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (kernel < LBMPC_KERNEL_AUTO || kernel > LBMPC_KERNEL_STREAM_MIXED) return fail(LBMPC_EINVAL, "kernel must be one of LBMPC_KERNEL_*");
+    if ((kernel == LBMPC_KERNEL_CTA || kernel >= LBMPC_KERNEL_STREAM) && h->shape != 0)
+        return fail(LBMPC_ESHAPE, "the CTA and stream mappings are compiled for the (4,1,1) Moore-Greitzer shape");
+    h->force_kernel = kernel;
+    h->force_lockstep = lockstep < 0 ? -1 : (lockstep != 0);
+    return LBMPC_OK;
+}
+int lbmpc_last_kernel(const lbmpc_handle* h) { return h ? h->last_kernel : 0; }
+
 int lbmpc_num_rows(const lbmpc_handle* h) { return h ? h->hp.m_rows : 0; }
 int lbmpc_slots_per_cta(const lbmpc_handle* h) { return h ? h->max_slots : 0; }
 int64_t lbmpc_kernel_launches(const lbmpc_handle* h) { return h ? h->launches : 0; }
@@ -711,6 +821,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     if (h->hs_small) cudaFreeHost(h->hs_small);
     if (h->hs_bounce) cudaFreeHost(h->hs_bounce);
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh);
+    cudaFree(h->st_ws64); cudaFree(h->st_wsft);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

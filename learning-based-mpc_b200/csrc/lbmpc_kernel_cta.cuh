@@ -235,7 +235,6 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
             }
             __syncthreads();
             LB_PROF(1)
-            if (iters >= p.max_iter) break;
 
             // ================= phase B (warp 0): factorisation + dual residual + affine backward substitution; Farkas =================
             const bool cert = m[L::M_LAM] >= p.inf_trigger;
@@ -309,6 +308,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
                 status = v;
                 break;
             }
+            if (iters >= p.max_iter) break;  // the last allowed iterate has been tested: LBMPC_ST_MAXITER
             // ================= phase B2: block transfer matrices (all warps), affine forward substitution (warp 0) =================
             for (int t = tid; t < l.nb * NX; t += kCtaThreads) C::bwd_p1_T(p, l, slot, zero_rec, t);
             if (tid >= kCtaThreads - l.nb) C::fwd_p1(p, l, slot, kCtaThreads - 1 - tid, true);  // the last warp: off the T tasks' lanes

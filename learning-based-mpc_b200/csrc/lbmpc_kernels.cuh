@@ -351,7 +351,6 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
             }
             LB_PROF2(15)
             LB_PROF(1)
-            if (iters >= p.max_iter) break;
 
             // =================================================================================
             // phase B: Riccati factorisation + dual residual (one warp, one dot product per lane and
@@ -433,6 +432,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
                 status = v;
                 break;
             }
+            if (iters >= p.max_iter) break;  // the last allowed iterate has been tested: LBMPC_ST_MAXITER
             if constexpr (kCoop) affine_forward<NX, NT, NU>(p, l, slot, zero_rec, lane);
             else solve_sweeps<NX, NT, NU>(p, l, slot, zero_rec, lane, true, true);
             LB_PROF(3)

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "liblbmpc_b200.so")
 FORM = {"F": 0, "C": 1}
 VARIANT = {"LMPC": 0, "LBMPC": 1}
 ST_OPTIMAL, ST_MAXITER, ST_INFEASIBLE, ST_NUMERICAL = 0, 1, 2, 3
+KERNEL = {"auto": 0, "warp": 1, "cta": 2, "stream": 3, "mixed": 4}     # LBMPC_KERNEL_* (include/lbmpc.h)
+KERNEL_NAME = {v: k for k, v in KERNEL.items()}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -110,6 +112,10 @@ def load_library(path=None):
     lib.lbmpc_closed_loop.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double,
                                       vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp]
     lib.lbmpc_closed_loop.restype = C.c_int
+    lib.lbmpc_set_kernel.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.lbmpc_set_kernel.restype = C.c_int
+    lib.lbmpc_last_kernel.argtypes = [vp]
+    lib.lbmpc_last_kernel.restype = C.c_int
     lib.lbmpc_num_rows.argtypes = [vp]
     lib.lbmpc_slots_per_cta.argtypes = [vp]
     lib.lbmpc_kernel_launches.argtypes = [vp]
@@ -163,7 +169,7 @@ class Solver:
     """
 
     def __init__(self, mdl, form, variant, N, delta=0.01, device=0, max_batch=1024, device_pointers=False,
-                 tol_res=0.0, tol_mu=0.0, inf_radius=0.0, max_iter=0, lib=None):
+                 tol_res=0.0, tol_mu=0.0, inf_radius=0.0, max_iter=0, lib=None, kernel=None, lockstep=None):
         self.lib = lib or load_library()
         self._model, self._keep = pack_model(mdl)
         self._cfg = make_config(form, variant, N, delta, tol_res, tol_mu, inf_radius, max_iter, max_batch,
@@ -176,6 +182,19 @@ class Solver:
         if rc != 0:
             raise LbmpcError(f"lbmpc_create failed ({rc}): {self.lib.lbmpc_last_error().decode()}")
         self.h = h
+        if kernel is not None or lockstep is not None:
+            self.set_kernel(kernel or "auto", lockstep)
+
+    def set_kernel(self, kernel="auto", lockstep=None):
+        """lbmpc_set_kernel: force a thread mapping ("auto" | "warp" | "cta" | "stream" | "mixed") and the warp kernel's
+        lock-step tick (None = auto)."""
+        self._check(self.lib.lbmpc_set_kernel(self.h, KERNEL[kernel], -1 if lockstep is None else int(bool(lockstep))),
+                    "lbmpc_set_kernel")
+
+    @property
+    def last_kernel(self):
+        """mapping the last solve call used: "warp" | "cta" | "stream" | "mixed" ("auto" before the first call)"""
+        return KERNEL_NAME[int(self.lib.lbmpc_last_kernel(self.h))]
 
     # -- introspection --------------------------------------------------------------------------
     @property

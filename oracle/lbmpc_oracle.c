@@ -775,7 +775,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
     }
     int st = LBO_ST_MAXITER, it = 0;
     double rp_inf = 0, rd_inf = 0, mu = 0, lam_inf = 0, hlam = 0;
-    for (it = 0; it < p->max_iter; ++it) {
+    for (it = 0;; ++it) {
         assemble(p, w, 0, 0.0, &rp_inf, &mu, &lam_inf, &hlam);
         double cert[2] = {0, 0};
         const int want_cert = lam_inf >= p->inf_trigger;
@@ -790,6 +790,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
         if (want_cert && hlam + cert[1] < 0.0 && cert[0] * p->inf_scale <= -(hlam + cert[1])) {
             st = LBO_ST_INFEASIBLE; break;
         }
+        if (it >= p->max_iter) break; /* the iterate of the last allowed iteration has been tested: LBO_ST_MAXITER */
         forward(p, w);
         double sums[3];
         double aaff = rows_step(p, w, 0, 0.0, 0.0, sums);

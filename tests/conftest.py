@@ -35,7 +35,7 @@ def emul_lib():
     out_dir = os.path.join(ROOT, "tests", "emul", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libemul.so")
-    deps = [src] + [os.path.join(ROOT, "learning-based-mpc_b200", "csrc", f) for f in ("lbmpc_core.cuh", "lbmpc_problem.hpp")]
+    deps = [src] + [os.path.join(ROOT, "learning-based-mpc_b200", "csrc", f) for f in ("lbmpc_core.cuh", "lbmpc_problem.hpp", "lbmpc_stream.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-x", "c++", src, "-o", so])
     lib = ctypes.CDLL(so)

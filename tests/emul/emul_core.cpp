@@ -58,7 +58,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         for (int b = l.nb - 1; b >= 0; --b) C::fwd_p3(p, l, s, b, aff);
     };
     int it = 0, st = 1;
-    for (it = 0; it < p.max_iter; ++it) {
+    for (it = 0;; ++it) {
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
         RedAsm ra{0, 0, 0, 0, 0};
         for (int k = 0; k <= N; ++k) {
@@ -130,6 +130,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         // ---- phase B2: verdict, affine substitution sweeps ----
         const int v = C::verdict(p, m, cert);
         if (v >= 0) { st = v; break; }
+        if (it >= p.max_iter) break;                     // the last allowed iterate has been tested: status 1
         if constexpr (NT == 1 && NU == 1 && NX <= 4) {   // affine backward substitution rode on the factor sweep
             for (int t = 0; t < l.nb * NX; ++t) C::bwd_p1_T(p, l, s, zero_rec.data(), t);
             for (int b = 0; b < l.nb; ++b) C::fwd_p1(p, l, s, b, true);
@@ -163,8 +164,6 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
         // the box rows / x / u step is applied at the top of the next pass (update_assemble_stage)
     }
-    if (it == p.max_iter)  // ran out of iterations: apply the last step so that the outputs are the last iterate
-        for (int k = 0; k <= N; ++k) { RedAsm ra{0, 0, 0, 0, 0}; C::update_assemble_stage(p, l, s, k, alpha, ra, csh); }
     double J = m[L::M_CCONST];
     for (int k = 0; k <= N; ++k) J += C::objective_stage(p, l, s, k, csh);
     for (int k = 0; k < N; ++k)
@@ -206,5 +205,45 @@ extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg,
             solve_one<2, 2, 2>(hp, x0, xr, dk, cs, wm, uc + b * (long)nu * N, theta + b * nt, xt, obj + b, iters + b, status + b);
         else { g_err = "emul: unsupported dims"; return LBMPC_ESHAPE; }
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream mapping (csrc/lbmpc_stream.cuh): one thread per QP, workspace in "HBM".  The per-lane passes
+// compiled for the host with lane stride LS (1, or 32 with the QP in lane `lane`: the device layout).
+// mode bit 0: float storage of the direction / factor records (mixed mode); jac: LTV Jacobians or NULL
+// ------------------------------------------------------------------------------------------------
+#include "../../learning-based-mpc_b200/csrc/lbmpc_stream.cuh"
+
+template <bool LTV, typename FT, int LS>
+static void stream_batch(const HostProblem& hp, StreamIO<FT> io, int lane) {
+    using S = Stream<4, LTV, FT, LS>;
+    const Params<4, 1, 1> p = to_params<4, 1, 1>(hp);
+    const StreamLayout<4> l(p.N, p.ng, io.cshift != nullptr, LTV);
+    std::vector<double> w64((size_t)l.n64 * LS, std::nan(""));   // uninitialised device memory: must never leak into results
+    std::vector<FT> wft((size_t)l.nft * LS, (FT)std::nan(""));
+    for (long long q = 0; q < io.batch; ++q)
+        S::solve_one(p, l, io, q, hp.G.data(), hp.hg.data(), w64.data() + lane, wft.data() + lane);
+}
+
+extern "C" int emul_stream_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg, long batch, int mode, int lane_stride,
+                                       const double* dx0, const double* dx_ref, const double* d_off, const double* cost_shift,
+                                       const double* jac, const double* warm, double* uc, double* theta, double* xtraj,
+                                       double* obj, int* iters, int* status) {
+    HostProblem hp;
+    int rc = build_problem(mdl, cfg, hp, g_err);
+    if (rc) return rc;
+    if (!(hp.nx == 4 && hp.nt == 1 && hp.nu == 1)) { g_err = "emul stream: (4,1,1) only"; return LBMPC_ESHAPE; }
+    auto run = [&](auto ft, auto ltv) {
+        using FT = decltype(ft);
+        StreamIO<FT> io{};
+        io.batch = batch; io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm; io.cshift = cost_shift; io.jac = jac;
+        io.uc = uc; io.theta = theta; io.xtraj = xtraj; io.obj = obj; io.iters = iters; io.status = status;
+        if (lane_stride == 32) stream_batch<decltype(ltv)::value, FT, 32>(hp, io, 13);
+        else stream_batch<decltype(ltv)::value, FT, 1>(hp, io, 0);
+    };
+    const bool f32 = mode & 1;
+    if (jac) { if (f32) run(float(), std::true_type()); else run(double(), std::true_type()); }
+    else     { if (f32) run(float(), std::false_type()); else run(double(), std::false_type()); }
     return 0;
 }

@@ -1,0 +1,76 @@
+"""The stream mapping (learning-based-mpc_b200/csrc/lbmpc_stream.cuh: one thread per QP, iterate streamed from HBM, four
+fused passes per iteration) compiled for the host and checked against the oracle.  No-GPU half of the parity gate for
+that kernel; the GPU half is tests/test_gpu_parity.py (kernel forced with Solver(kernel="stream"))."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, sample_ics
+from lbmpc_b200 import capi
+from oracle_py import OracleProblem
+
+
+def stream_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None, cost_shift=None, jac=None, mode=0, stride=1):
+    m, keep = capi.pack_model(mdl)
+    cfg = capi.make_config(form, variant, N)
+    dx0 = np.ascontiguousarray(dx0, float)
+    nb = dx0.shape[0]
+    o = dict(uc=np.empty((nb, N, 1)), theta=np.empty((nb, 1)), xtraj=np.empty((nb, N + 1, 4)), obj=np.empty(nb),
+             iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32))
+    p = capi._ptr
+    c = lambda a: None if a is None else np.ascontiguousarray(a, float)
+    dx_ref, d_off, warm, cost_shift, jac = c(dx_ref), c(d_off), c(warm), c(cost_shift), c(jac)
+    rc = lib.emul_stream_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), C.c_int(mode), C.c_int(stride), p(dx0), p(dx_ref),
+                                     p(d_off), p(cost_shift), p(jac), p(warm), p(o["uc"]), p(o["theta"]), p(o["xtraj"]),
+                                     p(o["obj"]), p(o["iters"]), p(o["status"]))
+    assert rc == 0, lib.emul_last_error()
+    return o
+
+
+@pytest.mark.parametrize("form", ["F", "C"])
+@pytest.mark.parametrize("variant", ["LMPC", "LBMPC"])
+@pytest.mark.parametrize("N", [3, 20, 50])
+def test_stream_matches_oracle(emul_lib, models, form, variant, N):
+    mdl = models[variant]
+    X0 = sample_ics(96, seed=N)
+    got = stream_solve(emul_lib, mdl, form, variant, N, X0)
+    ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, nthreads=4)
+    assert_parity(got, ref)
+
+
+def test_stream_device_lane_stride(emul_lib, models):
+    """Lane stride 32 (the device layout, QP in lane 13, workspace pre-filled with NaN): bit-identical to stride 1."""
+    mdl = models["LBMPC"]
+    X0 = sample_ics(16, seed=5)
+    a = stream_solve(emul_lib, mdl, "C", "LBMPC", 30, X0)
+    b = stream_solve(emul_lib, mdl, "C", "LBMPC", 30, X0, stride=32)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_stream_inputs_ref_offsets_warm_shift(emul_lib, models):
+    mdl = models["LBMPC"]
+    N, nb = 40, 24
+    rng = np.random.default_rng(11)
+    X0 = sample_ics(nb, seed=2)
+    xref = (mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.1, 0.1, (nb, 1)))
+    doff = 1e-4 * rng.standard_normal((nb, N, 4))
+    warm = np.concatenate([0.05 * rng.standard_normal((nb, N)), 0.01 * rng.standard_normal((nb, 1))], axis=1)
+    got = stream_solve(emul_lib, mdl, "C", "LBMPC", N, X0, xref, doff, warm)
+    ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, xref, doff, warm)
+    assert_parity(got, ref)
+    e = 2e-3 * rng.standard_normal((nb, N + 1, 4)).cumsum(axis=1)
+    e[:, 0] = 0.0
+    for form, variant in (("C", "LBMPC"), ("F", "LMPC")):
+        got = stream_solve(emul_lib, models[variant], form, variant, N, X0, xref, None, None, e)
+        ref = OracleProblem(form, variant, models[variant], N).solve_batch(X0, xref, cost_shift=e)
+        assert_parity(got, ref)
+
+
+def test_stream_long_horizon(emul_lib, models):
+    mdl = models["LBMPC"]
+    X0 = sample_ics(8, seed=4)
+    got = stream_solve(emul_lib, mdl, "C", "LBMPC", 200, X0)
+    ref = OracleProblem("C", "LBMPC", mdl, 200).solve_batch(X0)
+    assert_parity(got, ref)

@@ -132,7 +132,7 @@ def test_bitwise_determinism_and_permutation_invariance(models):
         assert np.array_equal(a[k][perm], c[k]), k
 
 
-def test_lockstep_tick_changes_no_result(models, monkeypatch):
+def test_lockstep_tick_changes_no_result(models):
     """At many QPs per warp slot the warp kernel makes the warps of a CTA start every iteration together (cta_tick,
     an instruction-cache measure).  It only orders the warps in time: forced off and forced on, a batch that queues
     several QPs behind every slot gives bit-identical results, and both agree with the oracle."""
@@ -140,13 +140,13 @@ def test_lockstep_tick_changes_no_result(models, monkeypatch):
     nb = 6000                                     # > 3 QPs per warp slot of the whole GPU: the default picks the tick
     X0 = sample_ics(nb, seed=31)
     sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb)
-    monkeypatch.setenv("LBMPC_KERNEL", "warp")
-    monkeypatch.setenv("LBMPC_LOCKSTEP", "0")
+    sol.set_kernel("warp", lockstep=False)
     a = sol.solve_batch(X0)
-    monkeypatch.setenv("LBMPC_LOCKSTEP", "1")
+    sol.set_kernel("warp", lockstep=True)
     b = sol.solve_batch(X0)
-    monkeypatch.delenv("LBMPC_LOCKSTEP")
+    sol.set_kernel("warp")
     c = sol.solve_batch(X0)
+    assert sol.last_kernel == "warp"
     for k in ("uc", "theta", "obj", "iters", "status", "xtraj"):
         assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(a[k], c[k]), k
@@ -349,44 +349,43 @@ def test_closed_loop_matches_oracle(models):
                 assert np.abs(got["u"][b] - ref["u"]).max() < 1e-6
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta"])
+@pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])
 @pytest.mark.parametrize("form,N,nb", [("C", 50, 300), ("F", 50, 64), ("C", 20, 33), ("C", 200, 9)])
-def test_both_solver_kernels_against_oracle(models, monkeypatch, kernel, form, N, nb):
-    """The engine has two kernels for the 4-state shape: one warp per QP (throughput) and one CTA per QP (latency, picked
-    for small batches).  Both are forced here (LBMPC_KERNEL) on the same inputs, with reference / offsets / warm start."""
-    monkeypatch.setenv("LBMPC_KERNEL", kernel)
+def test_both_solver_kernels_against_oracle(models, kernel, form, N, nb):
+    """The engine has three thread mappings for the 4-state shape: one warp per QP (moderate batches), one CTA per QP
+    (latency, picked for small batches) and one thread per QP with the iterate streamed from HBM (large batches).  Each
+    is forced here (lbmpc_set_kernel) on the same inputs, with reference / offsets / warm start."""
     mdl = models["LBMPC"]
     rng = np.random.default_rng(11)
     X0 = sample_ics(nb, seed=N + nb)
     xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.05, 0.05, (nb, 1))
     d_off = 2e-4 * rng.standard_normal((nb, N, 4))
     warm = np.concatenate([0.02 * rng.standard_normal((nb, N)), 0.01 * rng.standard_normal((nb, 1))], axis=1)
-    sol = solver(mdl, form, "LBMPC", N, max_batch=nb)
+    sol = solver(mdl, form, "LBMPC", N, max_batch=nb, kernel=kernel)
     P = OracleProblem(form, "LBMPC", mdl, N)
     assert_parity(sol.solve_batch(X0), P.solve_batch(X0, nthreads=8))
+    assert sol.last_kernel == kernel
     assert_parity(sol.solve_batch(X0, xref, d_off, warm), P.solve_batch(X0, xref, d_off, warm, nthreads=8))
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta"])
-def test_both_solver_kernels_large_polytope(models, monkeypatch, kernel):
+@pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])
+def test_both_solver_kernels_large_polytope(models, kernel):
     """616-row terminal set (tracking LMPC): the warp kernel stages the polytope in shared memory with a bulk TMA copy and
     sums its Hessian by warp reductions, the CTA kernel reads it from global memory / L2 and block-reduces.  The engine
     picks the CTA kernel for this set at every batch size, so the warp path is forced here to stay covered."""
-    monkeypatch.setenv("LBMPC_KERNEL", kernel)
     mdl = models["LMPC"]
     for form, N, nb in (("C", 50, 200), ("F", 20, 64)):
         X0 = sample_ics(nb, seed=N + 3)
         xref = mdl["LAMBDA"][:, 0][None, :] * np.random.default_rng(N).uniform(-0.05, 0.05, (nb, 1))
-        got = solver(mdl, form, "LMPC", N, max_batch=nb).solve_batch(X0, xref)
+        got = solver(mdl, form, "LMPC", N, max_batch=nb, kernel=kernel).solve_batch(X0, xref)
         assert_parity(got, OracleProblem(form, "LMPC", mdl, N).solve_batch(X0, xref, nthreads=8))
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta"])
-def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
+@pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])
+def test_cost_shift_twin_sequences(models, kernel):
     """lbmpc_solve_batch_shifted: objective at x_k + e_k, rows and dynamics on x_k (DMS_LBMPC_casadi.m:252-319 with the
     oracle frozen), both kernels, host and device pointers, against the oracle; a zero shift changes nothing."""
     import torch
-    monkeypatch.setenv("LBMPC_KERNEL", kernel)
     rng = np.random.default_rng(17)
     for form, variant, N, nb in (("C", "LBMPC", 50, 200), ("F", "LMPC", 20, 40)):
         mdl = models[variant]
@@ -394,7 +393,7 @@ def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
         e = 2e-3 * rng.standard_normal((nb, N + 1, 4)).cumsum(axis=1)
         e[:, 0] = 0.0
         xref = mdl["LAMBDA"][:, 0][None, :] * rng.uniform(-0.05, 0.05, (nb, 1))
-        sol = solver(mdl, form, variant, N, max_batch=nb)
+        sol = solver(mdl, form, variant, N, max_batch=nb, kernel=kernel)
         got = sol.solve_batch(X0, xref, cost_shift=e)
         ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, xref, cost_shift=e, nthreads=8)
         assert_parity(got, ref)
@@ -402,7 +401,7 @@ def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
         for k in ("uc", "theta", "obj", "iters", "status"):
             assert np.array_equal(zero[k], plain[k]), k
         assert np.abs(plain["uc"] - got["uc"]).max() > 1e-5
-        dsol = solver(mdl, form, variant, N, device_pointers=True)
+        dsol = solver(mdl, form, variant, N, device_pointers=True, kernel=kernel)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
         dev = dsol.solve_batch(t(X0), t(xref), cost_shift=t(e))
         torch.cuda.synchronize()
@@ -410,14 +409,13 @@ def test_cost_shift_twin_sequences(models, monkeypatch, kernel):
             assert np.array_equal(dev[k].cpu().numpy(), got[k]), k
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta"])
-def test_iteration_cap_bad_inputs_and_options(models, monkeypatch, kernel):
+@pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])
+def test_iteration_cap_bad_inputs_and_options(models, kernel):
     """Verdicts other than optimal / infeasible: the iteration cap (status 1, outputs = last iterate) and non-finite
     inputs (status 3) come out like the oracle's; a caller-supplied Farkas radius and tolerances are honoured."""
-    monkeypatch.setenv("LBMPC_KERNEL", kernel)
     mdl = models["LBMPC"]
     X0 = sample_ics(40, seed=9)
-    sol = solver(mdl, "C", "LBMPC", 50, max_batch=40, max_iter=4)
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=40, max_iter=4, kernel=kernel)
     P = OracleProblem("C", "LBMPC", mdl, 50)
     P.set_options(max_iter=4)
     got, ref = sol.solve_batch(X0), P.solve_batch(X0, nthreads=4)
@@ -426,7 +424,7 @@ def test_iteration_cap_bad_inputs_and_options(models, monkeypatch, kernel):
     bad = X0.copy()
     bad[3, 1] = np.nan
     bad[7, 0] = np.inf
-    sol2 = solver(mdl, "C", "LBMPC", 50, max_batch=40, tol_res=1e-7, tol_mu=1e-8, inf_radius=500.0)
+    sol2 = solver(mdl, "C", "LBMPC", 50, max_batch=40, tol_res=1e-7, tol_mu=1e-8, inf_radius=500.0, kernel=kernel)
     P2 = OracleProblem("C", "LBMPC", mdl, 50)
     P2.set_options(tol_res=1e-7, tol_mu=1e-8, inf_radius=500.0)
     got, ref = sol2.solve_batch(bad), P2.solve_batch(bad, nthreads=4)
