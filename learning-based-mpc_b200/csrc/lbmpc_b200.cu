@@ -78,7 +78,9 @@ struct lbmpc_handle {
     // kernel choice (lbmpc_set_kernel; LBMPC_KERNEL / LBMPC_LOCKSTEP / LBMPC_STREAM_* are read ONCE, in lbmpc_create)
     int force_kernel = LBMPC_KERNEL_AUTO, force_lockstep = -1;
     // stream kernel (one thread per QP, iterate in HBM): workspace of the resident warps
-    int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM
+    int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM (default layout)
+    int st_warps_cap = 0;              // 8: never use the 12-warp variant (LBMPC_STREAM_WARPS, experiments)
+    int max_smem_optin = 0;
     int64_t st_min_batch = 0;          // auto choice: batches at least this large take the stream kernel
     double* st_ws64 = nullptr;
     void* st_wsft = nullptr;
@@ -186,41 +188,37 @@ static cudaError_t stream_workspace(lbmpc_handle* h, int64_t warps, const Stream
     }
     return cudaSuccess;
 }
-static int64_t stream_warps(const lbmpc_handle* h, int64_t batch) {
-    const int64_t ctas = std::min<int64_t>((int64_t)h->num_sms * h->st_ctas_per_sm, (batch + 127) / 128);
-    return std::max<int64_t>(ctas, 1) * 4;
+template <bool LTV, typename FT, int WARPS>
+static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, size_t smem) {
+    const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
+    const bool cs = io.cshift != nullptr;
+    const StreamLayout<4> l(p.N, p.ng, cs, LTV);
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(h->num_sms, (io.batch + 32 * WARPS - 1) / (32 * WARPS)));
+    cudaError_t e = stream_workspace(h, ctas * WARPS, l, sizeof(FT) == 4);
+    if (e != cudaSuccess) return e;
+    StreamIO<FT> s{};
+    s.batch = io.batch; s.dx0 = io.dx0; s.dx_ref = io.dx_ref; s.d_off = io.d_off; s.warm = io.warm; s.cshift = io.cshift;
+    s.jac = jac; s.uc = io.uc; s.theta = io.theta; s.xtraj = io.xtraj; s.obj = io.obj; s.iters = io.iters; s.status = io.status;
+    s.queue = next_queue(h);
+    s.ws64 = h->st_ws64;
+    s.wsft = (FT*)h->st_wsft;
+    e = cudaMemsetAsync(s.queue, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    ipm_stream_kernel<4, LTV, FT, WARPS><<<(unsigned)ctas, 32 * WARPS, smem, st>>>(p, s, h->dG, h->dhg);
+    h->launches += 1;
+    h->last_kernel = sizeof(FT) == 4 ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM;
+    return cudaGetLastError();
+}
+// warps per CTA (= per SM): 12 when their double buffers fit shared memory, else 8
+template <bool LTV, typename FT>
+static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st) {
+    const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV);
+    const bool w12 = 12 * per_warp <= (size_t)h->max_smem_optin && h->st_warps_cap != 8;
+    return w12 ? launch_stream_w<LTV, FT, 12>(h, io, jac, st, 12 * per_warp) : launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp);
 }
 static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed) {
-    const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
-    const StreamLayout<4> l(p.N, p.ng, io.cshift != nullptr, jac != nullptr);
-    const int64_t warps = stream_warps(h, io.batch);
-    cudaError_t e = stream_workspace(h, warps, l, mixed);
-    if (e != cudaSuccess) return e;
-    unsigned long long* queue = next_queue(h);
-    e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
-    const int grid = (int)(warps / 4);
-    auto fill = [&](auto& s) {
-        s.batch = io.batch; s.dx0 = io.dx0; s.dx_ref = io.dx_ref; s.d_off = io.d_off; s.warm = io.warm; s.cshift = io.cshift;
-        s.jac = jac; s.uc = io.uc; s.theta = io.theta; s.xtraj = io.xtraj; s.obj = io.obj; s.iters = io.iters; s.status = io.status;
-        s.queue = queue; s.ws64 = h->st_ws64;
-    };
-    if (mixed) {
-        StreamIO<float> s{};
-        fill(s);
-        s.wsft = (float*)h->st_wsft;
-        if (jac) ipm_stream_kernel<4, true, float><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
-        else ipm_stream_kernel<4, false, float><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
-    } else {
-        StreamIO<double> s{};
-        fill(s);
-        s.wsft = (double*)h->st_wsft;
-        if (jac) ipm_stream_kernel<4, true, double><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
-        else ipm_stream_kernel<4, false, double><<<grid, 128, 0, st>>>(p, s, h->dG, h->dhg);
-    }
-    h->launches += 1;
-    h->last_kernel = mixed ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM;
-    return cudaGetLastError();
+    if (mixed) return jac ? launch_stream_t<true, float>(h, io, jac, st) : launch_stream_t<false, float>(h, io, jac, st);
+    return jac ? launch_stream_t<true, double>(h, io, jac, st) : launch_stream_t<false, double>(h, io, jac, st);
 }
 
 static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int q, double inv_h2, double lambda,
@@ -367,13 +365,21 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(cudaEventCreate(&h->ev0));
     CU_TRY(cudaEventCreate(&h->ev1));
     if (h->shape == 0) {  // stream mapping: resident CTAs per SM, workspace for the largest batch of this handle
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->st_ctas_per_sm, ipm_stream_kernel<4, false, double>, 128, 0));
+        h->max_smem_optin = max_smem;
+        const int smem8 = 8 * (int)StreamSmem<4, double>::warp_bytes(true, true);
+        auto optin = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, std::max(smem8, max_smem))); };
+        CU_TRY(optin(ipm_stream_kernel<4, false, double, 8>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 8>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, float, 8>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 8>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, double, 12>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 12>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, float, 12>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 12>));
+        h->st_ctas_per_sm = 1;
         h->st_min_batch = (int64_t)h->num_sms * 64;  // >= 64 QPs (2 warps) per SM; below that the shared-memory kernels win
-        if (const char* e = getenv("LBMPC_STREAM_CTAS")) h->st_ctas_per_sm = std::max(1, std::min(h->st_ctas_per_sm, atoi(e)));
+        if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
-        if (h->max_batch >= h->st_min_batch) {
+        if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use
             const StreamLayout<4> l(hp.N, hp.ng, false, false);
-            CU_TRY(stream_workspace(h, stream_warps(h, h->max_batch), l, false));
+            const int64_t ctas = std::min<int64_t>(h->num_sms, (h->max_batch + 255) / 256);
+            CU_TRY(stream_workspace(h, ctas * 12, l, false));
         }
     }
     // experiment / test overrides, read once

@@ -40,22 +40,32 @@
 #pragma once
 
 #include "lbmpc_core.cuh"
+#ifdef __CUDACC__
+#include "lbmpc_kernels.cuh"  // mbarrier / 1-D bulk copy helpers
+#endif
 
 namespace lbmpc {
 
 template <int NX>
 struct StreamLayout {
     static constexpr int NZ = NX + 1, NV = NX + 2, NVB = NX + 1, NH = NZ * (NZ + 1) / 2;
-    static constexpr int F_X = 0, F_U = NX, F_S = NVB, F_LB = 3 * NVB, RS_IT = 5 * NVB;
-    static constexpr int D_DA = 0, D_DV = NVB, D_RL = 2 * NVB, D_RI = D_RL + NZ, D_KAP = D_RI + 1, D_QC = D_KAP + 1,
-                         D_T2 = D_QC + NV, RS_D = D_T2 + NVB;
+    // FP64 record: iterate x u s lambda, then the step [dx du] that the next pass BU applies (FP64 in every mode: the
+    // iterate stays on the dynamics x+ = A x + B u + d exactly only if the applied step does)
+    static constexpr int F_X = 0, F_U = NX, F_S = NVB, F_LB = 3 * NVB, F_DV = 5 * NVB, RS_IT = 6 * NVB, RS_IT0 = 5 * NVB;
+    // FT record; order chosen so that what a pass reads of a stage is ONE contiguous range: BU [DA], F2 [DA .. KAP],
+    // F1 [RL .. KAP], B2 [RL .. T2]
+    static constexpr int D_DA = 0, D_RL = NVB, D_RI = D_RL + NZ, D_KAP = D_RI + 1, D_T2 = D_KAP + 1, RS_D = D_T2 + NVB;
+    // second FP64 record: the sigma-independent part of the corrector right-hand side (a residual: FP64 in every mode)
+    static constexpr int RS_Q = NV;
+    static constexpr int kPolyChunk = 16;  // polytope rows fetched per pipeline item
     static constexpr int NJ = NX * 3;  // LTV: Jacobian of the learned term w.r.t. xi = [x1; x2; u] per stage
-    int N, ng, o_it, o_cs, o_j, o_sg, o_lg, n64, nft;  // offsets / sizes in elements (per QP)
+    int N, ng, o_it, o_q, o_cs, o_j, o_sg, o_lg, n64, nft;  // offsets / sizes in elements (per QP)
     LB_HD StreamLayout(int N_, int ng_, bool cs, bool ltv) {
         N = N_;
         ng = ng_;
         int o = 0;
         o_it = o; o += RS_IT * (N + 1);
+        o_q = o;  o += RS_Q * (N + 1);
         o_cs = o; o += cs ? NX * (N + 1) : 0;
         o_j = o;  o += ltv ? NJ * N : 0;
         o_sg = o; o += ng;
@@ -90,14 +100,91 @@ struct StreamIO {  // batch-major caller arrays (include/lbmpc.h)
     FT* wsft;      // ... and nft * 32 FT
 };
 
+enum StreamPass : int { PASS_BU = 0, PASS_F1 = 1, PASS_B2 = 2, PASS_F2 = 3 };
+constexpr int kStreamNone = -(1 << 30);  // pipeline item: nothing to fetch
+
+// what one pass reads of a stage: the FP64 iterate record (all passes but B2) and ONE contiguous element range of the
+// direction / factor record; cost shift in the two passes that evaluate the cost gradient
+template <int NX>
+struct StreamNeeds {
+    using SL = StreamLayout<NX>;
+    static LB_HD int it(int pass) { return pass == PASS_B2 ? 0 : (pass == PASS_BU ? SL::RS_IT : SL::RS_IT0); }  // leading elements of the FP64 record
+    static LB_HD int d_lo(int pass) { return (pass == PASS_BU || pass == PASS_F2) ? SL::D_DA : SL::D_RL; }
+    static LB_HD int d_hi(int pass) { return pass == PASS_BU ? SL::D_RL : (pass == PASS_B2 ? SL::RS_D : SL::D_T2); }
+    static LB_HD bool cs(int pass) { return pass == PASS_BU || pass == PASS_F1; }
+};
+
+// read-only view of the pipeline item a pass is working on (stride LS between elements):
+//   it[e]  element e of the stage's iterate record        d[e]  element e of its direction / factor record (pass range only)
+//   cs[j]  cost shift of the stage                        jac[i] LTV Jacobian of the stage
+//   sg[i], lg[i]  slack / multiplier of polytope row i (absolute row index, valid inside the fetched chunk)
+template <typename P64, typename PFT>
+struct StreamView {
+    P64 it;
+    PFT d;
+    P64 q, cs, jac, sg, lg;
+};
+#ifdef __CUDACC__
+// 32-bit shared-space addresses (ld.shared with immediate offsets instead of generic loads)
+struct StreamSh64 { unsigned a; };
+template <typename FT> struct StreamShFT { unsigned a; };
+#endif
+
+// Direct pipe: every read goes to the workspace itself (host emulation; LS = 1 or 32)
+template <int NX, typename FT, int LS>
+struct StreamPipeDirect {
+    using SL = StreamLayout<NX>;
+    const SL* l;
+    const double* w64;
+    const FT* wft;
+    int ring[2], n_issue, n_wait;
+    LB_HD StreamPipeDirect(const SL& l_, const double* w64_, const FT* wft_) : l(&l_), w64(w64_), wft(wft_), n_issue(0), n_wait(0) {}
+    LB_HD void start(int) {}
+    LB_HD void issue(int item) {
+        if (item == kStreamNone) return;
+        ring[n_issue++ & 1] = item;
+    }
+    using View = StreamView<const double*, const FT*>;
+    LB_HD View acquire() {
+        const int item = ring[n_wait++ & 1];
+        View v;
+        const int k = item >= 0 ? item : 0;
+        v.it = w64 + (l->o_it + k * SL::RS_IT) * LS;
+        v.d = wft + k * SL::RS_D * LS;
+        v.q = w64 + (l->o_q + k * SL::RS_Q) * LS;
+        v.cs = w64 + (l->o_cs + k * NX) * LS;
+        v.jac = w64 + (l->o_j + k * SL::NJ) * LS;
+        v.sg = w64 + l->o_sg * LS;
+        v.lg = w64 + l->o_lg * LS;
+        return v;
+    }
+};
+
 template <int NX, bool LTV, typename FT, int LS>
 struct Stream {
     using P = Params<NX, 1, 1>;
     using SL = StreamLayout<NX>;
     using Lane = StreamLane<NX>;
     using C = Core<NX, 1, 1>;
-    static constexpr int NZ = NX + 1, NV = NX + 2, NVB = NX + 1, NH = SL::NH;
+    static constexpr int NZ = NX + 1, NV = NX + 2, NVB = NX + 1, NH = SL::NH, CH = SL::kPolyChunk;
 
+#ifdef __CUDACC__
+    static __device__ __forceinline__ double ld(StreamSh64 p, int e) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p.a + 8u * (unsigned)(e * LS)) : "memory");
+        return v;
+    }
+    static __device__ __forceinline__ double ldf(StreamShFT<double> p, int e) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p.a + 8u * (unsigned)(e * LS)) : "memory");
+        return v;
+    }
+    static __device__ __forceinline__ double ldf(StreamShFT<float> p, int e) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(p.a + 4u * (unsigned)(e * LS)) : "memory");
+        return (double)v;
+    }
+#endif
     static LB_HD double ld(const double* p, int e) { return p[e * LS]; }
     static LB_HD void st(double* p, int e, double v) { p[e * LS] = v; }
     static LB_HD double ldf(const FT* p, int e) { return (double)p[e * LS]; }
@@ -107,29 +194,31 @@ struct Stream {
     struct AB {  // dynamics of the stage being processed
         double A[NX * NX], B[NX];
     };
-    // LTI: the constant bank; LTV: A_k = A + [J(:,1:2) 0 0], B_k = B + J(:,3), J read from the workspace
-    static LB_HD void load_ab(const P& p, const SL& l, const double* w64, int k, AB& ab) {
+    // LTI: the constant bank; LTV: A_k = A + [J(:,1:2) 0 0], B_k = B + J(:,3), J = Jacobian of the stage (jac[c*3+b])
+    template <typename PJ>
+    static LB_HD void load_ab(const P& p, PJ jac, AB& ab) {
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
 #pragma unroll
             for (int b = 0; b < NX; ++b) {
                 double v = p.A[c * NX + b];
-                if (LTV && b < 2) v += ld(w64, l.o_j + k * SL::NJ + c * 3 + b);
+                if (LTV && b < 2) v += ld(jac, c * 3 + b);
                 ab.A[c * NX + b] = v;
             }
             double v = p.B[c];
-            if (LTV) v += ld(w64, l.o_j + k * SL::NJ + c * 3 + 2);
+            if (LTV) v += ld(jac, c * 3 + 2);
             ab.B[c] = v;
         }
     }
 
     // cost gradient g = W_type(k) [x + e; theta; u] (u part dropped at the last stage), objective piece 0.5 v'g (+ lin'z at kT)
-    static LB_HD void cost_grad(const P& p, const SL& l, const Lane& ln, const double* w64, int k, const double* v,
-                                bool has_cs, double* g, double* Jacc) {
+    template <typename PC>
+    static LB_HD void cost_grad(const P& p, const Lane& ln, PC cs, int k, const double* v, bool has_cs, double* g,
+                                double* Jacc) {
         const bool last = k >= p.N;
         double vv[NV];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) vv[j] = v[j] + (has_cs ? ld(w64, l.o_cs + k * NX + j) : 0.0);
+        for (int j = 0; j < NX; ++j) vv[j] = v[j] + (has_cs ? ld(cs, j) : 0.0);
         vv[NX] = ln.th;
         vv[NZ] = last ? 0.0 : v[NX];
         const double* W = p.W[C::stage_type(p, k)];
@@ -204,7 +293,7 @@ struct Stream {
             for (int j = 0; j < NX; ++j) st(it, SL::F_X + j, x[j]);
             if (k == N) break;
             AB ab;
-            load_ab(p, l, w64, k, ab);
+            load_ab(p, w64 + (l.o_j + k * SL::NJ) * LS, ab);
             double u = io.warm ? io.warm[q * (N + 1) + k] : 0.0;
 #pragma unroll
             for (int j = 0; j < NX; ++j) u += p.Kinit[j] * x[j];
@@ -223,12 +312,18 @@ struct Stream {
         }
     }
 
+    // next pipeline item after stage k's own record in a backward / forward pass
+    static LB_HD int next_bwd(int k) { return k > 0 ? k - 1 : kStreamNone; }
+    static LB_HD int next_fwd(int k, int N) { return k < N ? k + 1 : kStreamNone; }
+
     // ============================================================================================
     // pass BU.  Returns the verdict (LBMPC_ST_*) or -1 to continue.
     // ============================================================================================
+    template <class Pipe>
     static LB_HD int pass_bu(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                             double* w64, FT* wft, bool has_cs) {
+                             double* w64, FT* wft, bool has_cs, Pipe& pp) {
         const int N = p.N;
+        const int nch = (p.ng + CH - 1) / CH;
         const bool fresh = ln.fresh;
         const double alpha = fresh ? 0.0 : ln.alpha, sigmu = ln.sigmu;
         const double th_old = ln.th;
@@ -242,24 +337,31 @@ struct Stream {
         for (int a = 0; a < NH; ++a) HG[a] = 0.0;
 #pragma unroll
         for (int a = 0; a < NZ; ++a) gGl[a] = dG[a] = 0.0;
+        pp.start(PASS_BU);
+        pp.issue(N);
         for (int k = N; k >= 0; --k) {
+            const bool atkg = k == p.kg;
+            pp.issue((atkg && nch > 0) ? -1 : next_bwd(k));
+            const auto vw = pp.acquire();
             double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
             FT* d = wft + k * SL::RS_D * LS;
             const unsigned rows = C::stage_rows(p, k);
             const bool last = k >= N;
+            AB ab;
+            load_ab(p, vw.jac, ab);
             // ---- apply the step / initialise the rows, then the predictor assembly at the new iterate ----
             double vo[NVB], vn[NVB], dva[NVB], dv[NVB];
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
                 const bool ex = j < NX || !last;
-                vo[j] = ex ? ld(it, j) : 0.0;
-                dva[j] = (ex && !fresh) ? ldf(d, SL::D_DA + j) : 0.0;
-                dv[j] = (ex && !fresh) ? ldf(d, SL::D_DV + j) : 0.0;
+                vo[j] = ex ? ld(vw.it, j) : 0.0;
+                dva[j] = (ex && !fresh) ? ldf(vw.d, SL::D_DA + j) : 0.0;
+                dv[j] = (ex && !fresh) ? ld(vw.it, SL::F_DV + j) : 0.0;
                 vn[j] = vo[j] + alpha * dv[j];
                 if (ex) st(it, j, vn[j]);
             }
             double g[NV];
-            cost_grad(p, l, ln, w64, k, vn, has_cs, g, &J);
+            cost_grad(p, ln, vw.cs, k, vn, has_cs, g, &J);
             double qd[NVB], q[NVB], gl[NVB];
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
@@ -271,8 +373,8 @@ struct Stream {
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     double S = 1.0, Lm = 0.0;
                     if (act) {
-                        S = ld(it, SL::F_S + r);
-                        Lm = ld(it, SL::F_LB + r);
+                        S = ld(vw.it, SL::F_S + r);
+                        Lm = ld(vw.it, SL::F_LB + r);
                     }
                     const double slack_o = side == 0 ? p.hi[j] - vo[j] : vo[j] - p.lo[j];
                     const double rp_o = S - slack_o, is = lb_rcp(S), w = Lm * is;
@@ -305,51 +407,55 @@ struct Stream {
                 q[j] = g[a] + gpj;  // Newton right-hand side on the bounded variables
                 g[a] += glj;        // cost gradient + G'lambda (dual residual input)
             }
-            // ---- polytope block ----
-            if (k == p.kg) {
+            // ---- polytope block (chunks of CH rows through the pipeline) ----
+            if (atkg) {
                 double zo[NZ], zn[NZ], dza[NZ], dz[NZ];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
                     zo[a] = vo[a]; zn[a] = vn[a]; dza[a] = dva[a]; dz[a] = dv[a];
                 }
                 zo[NX] = th_old; zn[NX] = th; dza[NX] = ln.dtha; dz[NX] = ln.dth;
-                for (int i = 0; i < p.ng; ++i) {
-                    double gi[NZ], so = hg[i], sn = hg[i], adva = 0.0, adv = 0.0;
+                for (int c = 0; c < nch; ++c) {
+                    pp.issue(c + 1 < nch ? -(c + 2) : next_bwd(k));
+                    const auto pw = pp.acquire();
+                    const int i1 = (c + 1) * CH < p.ng ? (c + 1) * CH : p.ng;
+                    for (int i = c * CH; i < i1; ++i) {
+                        double gi[NZ], so = hg[i], sn = hg[i], adva = 0.0, adv = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        gi[a] = G[a * p.ngp + i];
-                        so -= gi[a] * zo[a];
-                        sn -= gi[a] * zn[a];
-                        adva += gi[a] * dza[a];
-                        adv += gi[a] * dz[a];
-                    }
-                    const double S = ld(w64, l.o_sg + i), Lm = ld(w64, l.o_lg + i);
-                    const double rp_o = S - so, is = lb_rcp(S), w = Lm * is;
-                    const double dsa = -rp_o - adva, dla = -Lm - w * dsa;
-                    const double ds = -rp_o - adv;
-                    const double rc = S * Lm + dsa * dla - sigmu;
-                    const double dl = (-rc - Lm * ds) * is;
-                    const double Sn = fresh ? (so > 1.0 ? so : 1.0) : S + alpha * ds;
-                    const double Ln = fresh ? 1.0 : Lm + alpha * dl;
-                    st(w64, l.o_sg + i, Sn);
-                    st(w64, l.o_lg + i, Ln);
-                    const double rp = Sn - sn, wn = Ln * lb_rcp(Sn), t = wn * rp;
-                    rpm = lb_nanmax(rpm, lb_abs(rp));
-                    sl += Sn * Ln;
-                    lam = lb_max(lam, Ln);
-                    hl += Ln * sn;
-                    int idx = 0;
+                        for (int a = 0; a < NZ; ++a) {
+                            gi[a] = G[a * p.ngp + i];
+                            so -= gi[a] * zo[a];
+                            sn -= gi[a] * zn[a];
+                            adva += gi[a] * dza[a];
+                            adv += gi[a] * dz[a];
+                        }
+                        const double S = ld(pw.sg, i), Lm = ld(pw.lg, i);
+                        const double rp_o = S - so, is = lb_rcp(S), w = Lm * is;
+                        const double dsa = -rp_o - adva, dla = -Lm - w * dsa;
+                        const double ds = -rp_o - adv;
+                        const double rc = S * Lm + dsa * dla - sigmu;
+                        const double dl = (-rc - Lm * ds) * is;
+                        const double Sn = fresh ? (so > 1.0 ? so : 1.0) : S + alpha * ds;
+                        const double Ln = fresh ? 1.0 : Lm + alpha * dl;
+                        st(w64, l.o_sg + i, Sn);
+                        st(w64, l.o_lg + i, Ln);
+                        const double rp = Sn - sn, wn = Ln * lb_rcp(Sn), t = wn * rp;
+                        rpm = lb_nanmax(rpm, lb_abs(rp));
+                        sl += Sn * Ln;
+                        lam = lb_max(lam, Ln);
+                        hl += Ln * sn;
+                        int idx = 0;
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        const double wa = wn * gi[a];
+                        for (int a = 0; a < NZ; ++a) {
+                            const double wa = wn * gi[a];
 #pragma unroll
-                        for (int b = a; b < NZ; ++b) HG[idx++] += wa * gi[b];
-                        gGl[a] += gi[a] * Ln;
-                        dG[a] += gi[a] * (t - Ln);
+                            for (int b = a; b < NZ; ++b) HG[idx++] += wa * gi[b];
+                            gGl[a] += gi[a] * Ln;
+                            dG[a] += gi[a] * (t - Ln);
+                        }
                     }
                 }
             }
-            const bool atkg = k == p.kg;
             if (last) {
                 // ---- terminal stage: P = Wzz + Qd (+HG); pv = q | g_theta; pi = g; pc = G'lambda ----
                 const double* W = p.W[C::stage_type(p, N)];
@@ -369,8 +475,6 @@ struct Stream {
                 continue;
             }
             // ---- Riccati step: P (stage k+1) -> P (stage k), factors RL = L / Rt, Ri = 1 / Rt ----
-            AB ab;
-            load_ab(p, l, w64, k, ab);
             const double* W = p.W[C::stage_type(p, k)];
             double M[NZ][NX], L[NZ], Rt;
 #pragma unroll
@@ -498,39 +602,48 @@ struct Stream {
     // ============================================================================================
     // pass F1: affine forward substitution, affine row directions, sigma
     // ============================================================================================
+    template <class Pipe>
     static LB_HD void pass_f1(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                              const double* w64, FT* wft, bool has_cs) {
+                              double* w64, FT* wft, bool has_cs, Pipe& pp) {
         const int N = p.N;
+        const int nch = (p.ng + CH - 1) / CH;
         double dxa[NX], ratio = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NX; ++j) dxa[j] = 0.0;
 #pragma unroll
         for (int a = 0; a < NZ; ++a) ln.dG1[a] = ln.dG2[a] = 0.0;
+        pp.start(PASS_F1);
+        pp.issue(0);
         for (int k = 0; k <= N; ++k) {
-            const double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
+            const bool atkg = k == p.kg;
+            pp.issue((atkg && nch > 0) ? -1 : next_fwd(k, N));
+            const auto vw = pp.acquire();
             FT* d = wft + k * SL::RS_D * LS;
             const unsigned rows = C::stage_rows(p, k);
             const bool last = k >= N;
+            AB ab;
+            load_ab(p, vw.jac, ab);
             double v[NVB], dva[NVB];
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
-                v[j] = ld(it, j);
+                v[j] = ld(vw.it, j);
                 dva[j] = dxa[j];
             }
-            v[NX] = last ? 0.0 : ld(it, NX);
+            v[NX] = last ? 0.0 : ld(vw.it, NX);
             dva[NX] = 0.0;
             if (!last) {
-                double acc = ldf(d, SL::D_RL + NX) * ln.dtha;
+                double acc = ldf(vw.d, SL::D_RL + NX) * ln.dtha;
 #pragma unroll
-                for (int c = 0; c < NX; ++c) acc += ldf(d, SL::D_RL + c) * dxa[c];
-                dva[NX] = ldf(d, SL::D_KAP) - acc;
+                for (int c = 0; c < NX; ++c) acc += ldf(vw.d, SL::D_RL + c) * dxa[c];
+                dva[NX] = ldf(vw.d, SL::D_KAP) - acc;
             }
 #pragma unroll
             for (int j = 0; j < NVB; ++j)
                 if (j < NX || !last) stf(d, SL::D_DA + j, dva[j]);
             double g[NV];
-            cost_grad(p, l, ln, w64, k, v, has_cs, g, nullptr);
-            stf(d, SL::D_QC + NX, g[NX]);
+            cost_grad(p, ln, vw.cs, k, v, has_cs, g, nullptr);
+            double* qr = w64 + (l.o_q + k * SL::RS_Q) * LS;
+            st(qr, NX, g[NX]);
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
                 double t1 = 0.0, t2 = 0.0;
@@ -541,8 +654,8 @@ struct Stream {
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     double S = 1.0, Lm = 0.0;
                     if (act) {
-                        S = ld(it, SL::F_S + r);
-                        Lm = ld(it, SL::F_LB + r);
+                        S = ld(vw.it, SL::F_S + r);
+                        Lm = ld(vw.it, SL::F_LB + r);
                     }
                     const double slack = side == 0 ? p.hi[j] - v[j] : v[j] - p.lo[j];
                     const double rp = act ? S - slack : 0.0, is = lb_rcp(S), w = Lm * is;
@@ -556,11 +669,11 @@ struct Stream {
                     t2 += act ? sgn * is : 0.0;
                 }
                 if (j < NX || !last) {
-                    stf(d, SL::D_QC + C::zidx(j), g[C::zidx(j)] + t1);
+                    st(qr, C::zidx(j), g[C::zidx(j)] + t1);
                     stf(d, SL::D_T2 + j, t2);
                 }
             }
-            if (k == p.kg) {
+            if (atkg) {
                 double dza[NZ], z[NZ];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
@@ -569,32 +682,35 @@ struct Stream {
                 }
                 dza[NX] = ln.dtha;
                 z[NX] = ln.th;
-                for (int i = 0; i < p.ng; ++i) {
-                    double gi[NZ], slack = hg[i], adva = 0.0;
+                for (int c = 0; c < nch; ++c) {
+                    pp.issue(c + 1 < nch ? -(c + 2) : next_fwd(k, N));
+                    const auto pw = pp.acquire();
+                    const int i1 = (c + 1) * CH < p.ng ? (c + 1) * CH : p.ng;
+                    for (int i = c * CH; i < i1; ++i) {
+                        double gi[NZ], slack = hg[i], adva = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        gi[a] = G[a * p.ngp + i];
-                        slack -= gi[a] * z[a];
-                        adva += gi[a] * dza[a];
-                    }
-                    const double S = ld(w64, l.o_sg + i), Lm = ld(w64, l.o_lg + i);
-                    const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
-                    const double dsa = -rp - adva, dla = -Lm - w * dsa, rr = dsa * is;
-                    ratio = lb_max(ratio, lb_max(-rr, 1.0 + rr));
-                    s0 += S * Lm;
-                    s1 += S * dla + Lm * dsa;
-                    s2 += dsa * dla;
-                    const double t1 = w * rp - dsa * dla * is - Lm;
+                        for (int a = 0; a < NZ; ++a) {
+                            gi[a] = G[a * p.ngp + i];
+                            slack -= gi[a] * z[a];
+                            adva += gi[a] * dza[a];
+                        }
+                        const double S = ld(pw.sg, i), Lm = ld(pw.lg, i);
+                        const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
+                        const double dsa = -rp - adva, dla = -Lm - w * dsa, rr = dsa * is;
+                        ratio = lb_max(ratio, lb_max(-rr, 1.0 + rr));
+                        s0 += S * Lm;
+                        s1 += S * dla + Lm * dsa;
+                        s2 += dsa * dla;
+                        const double t1 = w * rp - dsa * dla * is - Lm;
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        ln.dG1[a] += gi[a] * t1;
-                        ln.dG2[a] += gi[a] * is;
+                        for (int a = 0; a < NZ; ++a) {
+                            ln.dG1[a] += gi[a] * t1;
+                            ln.dG2[a] += gi[a] * is;
+                        }
                     }
                 }
             }
             if (!last) {
-                AB ab;
-                load_ab(p, l, w64, k, ab);
                 double xn[NX];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
@@ -617,37 +733,42 @@ struct Stream {
     // ============================================================================================
     // pass B2: corrector backward substitution from the stored right-hand side pieces
     // ============================================================================================
-    static LB_HD void pass_b2(const P& p, const SL& l, Lane& ln, const double* w64, FT* wft) {
+    template <class Pipe>
+    static LB_HD void pass_b2(const P& p, const SL& l, Lane& ln, FT* wft, Pipe& pp) {
         const int N = p.N;
         const double sigmu = ln.sigmu;
         double pv[NZ], kgt[NZ];
 #pragma unroll
         for (int a = 0; a < NZ; ++a) kgt[a] = ln.gGl[a] + ln.dG1[a] + sigmu * ln.dG2[a];
-        {
-            const FT* d = wft + N * SL::RS_D * LS;
+        pp.start(PASS_B2);
+        pp.issue(N);
+        for (int k = N; k >= 0; --k) {
+            pp.issue(next_bwd(k));
+            const auto vw = pp.acquire();
+            if (k == N) {
 #pragma unroll
-            for (int a = 0; a < NZ; ++a)
-                pv[a] = ldf(d, SL::D_QC + a) + (a < NX ? sigmu * ldf(d, SL::D_T2 + a) : 0.0) + (p.kg == N ? kgt[a] : 0.0);
-        }
-        for (int k = N - 1; k >= 0; --k) {
+                for (int a = 0; a < NZ; ++a)
+                    pv[a] = ld(vw.q, a) + (a < NX ? sigmu * ldf(vw.d, SL::D_T2 + a) : 0.0) + (p.kg == N ? kgt[a] : 0.0);
+                continue;
+            }
             FT* d = wft + k * SL::RS_D * LS;
             AB ab;
-            load_ab(p, l, w64, k, ab);
-            double rt = ldf(d, SL::D_QC + NZ) + sigmu * ldf(d, SL::D_T2 + NX);
+            load_ab(p, vw.jac, ab);
+            double rt = ld(vw.q, NZ) + sigmu * ldf(vw.d, SL::D_T2 + NX);
 #pragma unroll
             for (int c = 0; c < NX; ++c) rt += ab.B[c] * pv[c];
-            stf(d, SL::D_KAP, -ldf(d, SL::D_RI) * rt);
+            stf(d, SL::D_KAP, -ldf(vw.d, SL::D_RI) * rt);
             double pvn[NZ];
 #pragma unroll
             for (int a = 0; a < NZ; ++a) {
-                double v = ldf(d, SL::D_QC + a) + (a < NX ? sigmu * ldf(d, SL::D_T2 + a) : 0.0);
+                double v = ld(vw.q, a) + (a < NX ? sigmu * ldf(vw.d, SL::D_T2 + a) : 0.0);
                 if (a < NX) {
 #pragma unroll
                     for (int c = 0; c < NX; ++c) v += ab.A[c * NX + a] * pv[c];
                 } else {
                     v += pv[NX];
                 }
-                v -= ldf(d, SL::D_RL + a) * rt;
+                v -= ldf(vw.d, SL::D_RL + a) * rt;
                 if (k == p.kg) v += kgt[a];
                 pvn[a] = v;
             }
@@ -660,37 +781,45 @@ struct Stream {
     // ============================================================================================
     // pass F2: corrector forward substitution, final row directions, step length
     // ============================================================================================
+    template <class Pipe>
     static LB_HD void pass_f2(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                              const double* w64, FT* wft) {
+                              double* w64, FT* wft, Pipe& pp) {
         const int N = p.N;
+        const int nch = (p.ng + CH - 1) / CH;
         const double sigmu = ln.sigmu;
         double dx[NX], ratio = 0.0;
 #pragma unroll
         for (int j = 0; j < NX; ++j) dx[j] = 0.0;
+        pp.start(PASS_F2);
+        pp.issue(0);
         for (int k = 0; k <= N; ++k) {
-            const double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
-            FT* d = wft + k * SL::RS_D * LS;
+            const bool atkg = k == p.kg;
+            pp.issue((atkg && nch > 0) ? -1 : next_fwd(k, N));
+            const auto vw = pp.acquire();
+            double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
             const unsigned rows = C::stage_rows(p, k);
             const bool last = k >= N;
+            AB ab;
+            load_ab(p, vw.jac, ab);
             double v[NVB], dva[NVB], dv[NVB];
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
-                v[j] = ld(it, j);
-                dva[j] = ldf(d, SL::D_DA + j);
+                v[j] = ld(vw.it, j);
+                dva[j] = ldf(vw.d, SL::D_DA + j);
                 dv[j] = dx[j];
             }
-            v[NX] = last ? 0.0 : ld(it, NX);
-            dva[NX] = last ? 0.0 : ldf(d, SL::D_DA + NX);
+            v[NX] = last ? 0.0 : ld(vw.it, NX);
+            dva[NX] = last ? 0.0 : ldf(vw.d, SL::D_DA + NX);
             dv[NX] = 0.0;
             if (!last) {
-                double acc = ldf(d, SL::D_RL + NX) * ln.dth;
+                double acc = ldf(vw.d, SL::D_RL + NX) * ln.dth;
 #pragma unroll
-                for (int c = 0; c < NX; ++c) acc += ldf(d, SL::D_RL + c) * dx[c];
-                dv[NX] = ldf(d, SL::D_KAP) - acc;
+                for (int c = 0; c < NX; ++c) acc += ldf(vw.d, SL::D_RL + c) * dx[c];
+                dv[NX] = ldf(vw.d, SL::D_KAP) - acc;
             }
 #pragma unroll
             for (int j = 0; j < NVB; ++j)
-                if (j < NX || !last) stf(d, SL::D_DV + j, dv[j]);
+                if (j < NX || !last) st(it, SL::F_DV + j, dv[j]);
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
 #pragma unroll
@@ -700,8 +829,8 @@ struct Stream {
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     double S = 1.0, Lm = 1.0;
                     if (act) {
-                        S = ld(it, SL::F_S + r);
-                        Lm = ld(it, SL::F_LB + r);
+                        S = ld(vw.it, SL::F_S + r);
+                        Lm = ld(vw.it, SL::F_LB + r);
                     }
                     const double slack = side == 0 ? p.hi[j] - v[j] : v[j] - p.lo[j];
                     const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
@@ -712,7 +841,7 @@ struct Stream {
                     ratio = lb_max(ratio, act ? lb_max(-ds * is, -dl * lb_rcp(Lm)) : 0.0);
                 }
             }
-            if (k == p.kg) {
+            if (atkg) {
                 double dza[NZ], dz[NZ], z[NZ];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
@@ -723,27 +852,30 @@ struct Stream {
                 dza[NX] = ln.dtha;
                 dz[NX] = ln.dth;
                 z[NX] = ln.th;
-                for (int i = 0; i < p.ng; ++i) {
-                    double slack = hg[i], adva = 0.0, adv = 0.0;
+                for (int c = 0; c < nch; ++c) {
+                    pp.issue(c + 1 < nch ? -(c + 2) : next_fwd(k, N));
+                    const auto pw = pp.acquire();
+                    const int i1 = (c + 1) * CH < p.ng ? (c + 1) * CH : p.ng;
+                    for (int i = c * CH; i < i1; ++i) {
+                        double slack = hg[i], adva = 0.0, adv = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) {
-                        const double gia = G[a * p.ngp + i];
-                        slack -= gia * z[a];
-                        adva += gia * dza[a];
-                        adv += gia * dz[a];
+                        for (int a = 0; a < NZ; ++a) {
+                            const double gia = G[a * p.ngp + i];
+                            slack -= gia * z[a];
+                            adva += gia * dza[a];
+                            adv += gia * dz[a];
+                        }
+                        const double S = ld(pw.sg, i), Lm = ld(pw.lg, i);
+                        const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
+                        const double dsa = -rp - adva, dla = -Lm - w * dsa;
+                        const double ds = -rp - adv;
+                        const double rc = S * Lm + dsa * dla - sigmu;
+                        const double dl = (-rc - Lm * ds) * is;
+                        ratio = lb_max(ratio, lb_max(-ds * is, -dl * lb_rcp(Lm)));
                     }
-                    const double S = ld(w64, l.o_sg + i), Lm = ld(w64, l.o_lg + i);
-                    const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
-                    const double dsa = -rp - adva, dla = -Lm - w * dsa;
-                    const double ds = -rp - adv;
-                    const double rc = S * Lm + dsa * dla - sigmu;
-                    const double dl = (-rc - Lm * ds) * is;
-                    ratio = lb_max(ratio, lb_max(-ds * is, -dl * lb_rcp(Lm)));
                 }
             }
             if (!last) {
-                AB ab;
-                load_ab(p, l, w64, k, ab);
                 double xn[NX];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
@@ -793,17 +925,18 @@ struct Stream {
                                 double* w64, FT* wft) {
         Lane ln;
         const bool has_cs = io.cshift != nullptr;
+        StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
         init_qp(p, l, ln, io, q, w64, has_cs);
         for (;;) {
-            int st = pass_bu(p, l, ln, G, hg, w64, wft, has_cs);
+            int st = pass_bu(p, l, ln, G, hg, w64, wft, has_cs, pp);
             if (st < 0 && ln.iters >= p.max_iter) st = 1;
             if (st >= 0) {
                 finish(p, l, ln, io, w64, st);
                 return;
             }
-            pass_f1(p, l, ln, G, hg, w64, wft, has_cs);
-            pass_b2(p, l, ln, w64, wft);
-            pass_f2(p, l, ln, G, hg, w64, wft);
+            pass_f1(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            pass_b2(p, l, ln, wft, pp);
+            pass_f2(p, l, ln, G, hg, w64, wft, pp);
             ln.iters += 1;
             ln.fresh = false;
         }
@@ -812,21 +945,153 @@ struct Stream {
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
-// the kernel: persistent lanes, QPs from a global queue (warp-aggregated atomics)
+// TMA pipe: the records a pass reads are fetched one pipeline item (a stage, or a chunk of polytope rows) AHEAD of the
+// arithmetic with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) into a double buffer in shared memory private to the
+// warp, completion on an mbarrier per buffer.  One elected lane issues the copies of an item (<= 4 contiguous ranges,
+// 4.6 - 13 KB); every lane then reads its own column of the buffer.  This takes the HBM latency (~600 cycles per
+// dependent access, and an in-order warp would pay it ~10 times per stage) off the critical path without spending
+// registers on prefetched operands.
 // ---------------------------------------------------------------------------------------------
+template <int NX, typename FT>
+struct StreamSmem {  // byte offsets inside one buffer
+    using SL = StreamLayout<NX>;
+    static constexpr int kLine = 32 * (int)sizeof(double), kLineF = 32 * (int)sizeof(FT);
+    static constexpr int off_it = 0, off_d = SL::RS_IT * kLine;                      // B2 has no iterate record: its range starts at 0
+    static constexpr int off_cs = off_d + (SL::D_T2 - SL::D_DA) * kLineF;             // after the widest range next to an iterate record (F2)
+    static constexpr int off_q = (SL::RS_D - SL::D_RL) * kLineF;                      // B2: after its FT range
+    static_assert(off_q + SL::RS_Q * kLine <= off_cs, "layout");
+    static __host__ __device__ int off_j(bool cs) { return off_cs + (cs ? NX * kLine : 0); }
+    static __host__ __device__ int buf_bytes(bool cs, bool ltv) {
+        int b = off_j(cs) + (ltv ? SL::NJ * kLine : 0);
+        const int b2 = off_q + SL::RS_Q * kLine, poly = 2 * SL::kPolyChunk * kLine;
+        b = b > b2 ? b : b2;
+        b = b > poly ? b : poly;
+        return (b + 127) & ~127;
+    }
+    static __host__ __device__ size_t warp_bytes(bool cs, bool ltv) { return 2 * (size_t)buf_bytes(cs, ltv) + 128; }  // + two mbarriers
+};
+
 template <int NX, bool LTV, typename FT>
-__global__ void __launch_bounds__(128, 2)
+struct StreamPipeTma {
+    using SL = StreamLayout<NX>;
+    using SM = StreamSmem<NX, FT>;
+    using ND = StreamNeeds<NX>;
+    const SL* l;
+    const double* w64g;   // warp base (lane 0) of the FP64 workspace
+    const FT* wftg;
+    unsigned char* buf;   // two buffers
+    uint64_t* bar;        // two mbarriers
+    int lane, pass, bufb, ring[2];
+    unsigned n_issue, n_wait;
+    bool has_cs;
+    __device__ void start(int pass_) { pass = pass_; }
+    __device__ void issue(int item) {
+        if (item == kStreamNone) return;
+        const unsigned b = n_issue & 1u;
+        ring[b] = item;
+        ++n_issue;
+        __syncwarp();  // every lane is done reading buffer b (item n_issue - 2) and has fenced its global stores
+        if (lane == 0) {
+            unsigned char* dst = buf + b * bufb;
+            uint64_t* br = bar + b;
+            if (item >= 0) {
+                const int k = item, dlo = ND::d_lo(pass), dn = ND::d_hi(pass) - dlo;
+                const int it = ND::it(pass);
+                const bool cs = has_cs && ND::cs(pass), jj = LTV && k < l->N;
+                const bool qq = pass == PASS_B2;
+                const uint32_t bytes = it * SM::kLine + dn * SM::kLineF + (cs ? NX * SM::kLine : 0) + (jj ? SL::NJ * SM::kLine : 0) +
+                                       (qq ? SL::RS_Q * SM::kLine : 0);
+                mbar_expect_tx(br, bytes);
+                if (qq) tma_bulk_g2s(dst + SM::off_q, w64g + (size_t)(l->o_q + k * SL::RS_Q) * 32, SL::RS_Q * SM::kLine, br);
+                if (it) tma_bulk_g2s(dst + SM::off_it, w64g + (size_t)(l->o_it + k * SL::RS_IT) * 32, it * SM::kLine, br);
+                tma_bulk_g2s(dst + (it ? SM::off_d : 0), wftg + (size_t)(k * SL::RS_D + dlo) * 32, dn * SM::kLineF, br);
+                if (cs) tma_bulk_g2s(dst + SM::off_cs, w64g + (size_t)(l->o_cs + k * NX) * 32, NX * SM::kLine, br);
+                if (jj) tma_bulk_g2s(dst + SM::off_j(has_cs), w64g + (size_t)(l->o_j + k * SL::NJ) * 32, SL::NJ * SM::kLine, br);
+            } else {
+                const int c = -(item + 1), i0 = c * SL::kPolyChunk;
+                const int n = l->ng - i0 < SL::kPolyChunk ? l->ng - i0 : SL::kPolyChunk;
+                mbar_expect_tx(br, 2u * n * SM::kLine);
+                tma_bulk_g2s(dst, w64g + (size_t)(l->o_sg + i0) * 32, n * SM::kLine, br);
+                tma_bulk_g2s(dst + SL::kPolyChunk * SM::kLine, w64g + (size_t)(l->o_lg + i0) * 32, n * SM::kLine, br);
+            }
+        }
+    }
+    using View = StreamView<StreamSh64, StreamShFT<FT>>;
+    __device__ View acquire() {
+        const unsigned b = n_wait & 1u, parity = (n_wait >> 1) & 1u;
+        ++n_wait;
+        mbar_wait(bar + b, parity);
+        const int item = ring[b];
+        const unsigned src = smem_u32(buf + b * bufb) + 8u * (unsigned)lane;  // this lane's column (FP64 lines)
+        View v;
+        if (item >= 0) {
+            const bool it = ND::it(pass) != 0;
+            v.it.a = src + SM::off_it;
+            v.d.a = smem_u32(buf + b * bufb) + (unsigned)sizeof(FT) * (unsigned)lane + (it ? SM::off_d : 0) - (unsigned)(ND::d_lo(pass) * SM::kLineF);
+            v.q.a = src + SM::off_q;
+            v.cs.a = src + SM::off_cs;
+            v.jac.a = src + SM::off_j(has_cs);
+            v.sg = v.lg = v.it;
+        } else {
+            const int i0 = -(item + 1) * SL::kPolyChunk;
+            v.sg.a = src - (unsigned)(i0 * SM::kLine);
+            v.lg.a = src + SL::kPolyChunk * SM::kLine - (unsigned)(i0 * SM::kLine);
+            v.it = v.q = v.cs = v.jac = v.sg;
+            v.d.a = src;
+        }
+        return v;
+    }
+};
+
+// generic-proxy stores to the workspace (this pass) -> async-proxy reads (bulk copies of the next pass)
+__device__ __forceinline__ void stream_pass_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: persistent lanes, QPs from a global queue (warp-aggregated atomics).  Every lane of a warp runs every pass
+// (the bulk-copy pipeline is warp-collective); a lane without a QP computes on whatever its workspace column holds and
+// its results are never looked at.
+// ---------------------------------------------------------------------------------------------
+// Instruction cache: one iteration is ~4.5 k instructions per stage in four loop bodies (72 KB of SASS); warps that sit in
+// different passes evict each other's lines (ncu, 8 free-running warps per SM: 1.7 of 6.6 stall cycles per issue are
+// instruction fetches and two warps per scheduler issue no more than one).  Every warp executes every pass with the same
+// trip counts, so a CTA-wide barrier in front of each pass keeps the warps of an SM on the same lines at almost no cost
+// (cta_tick, lbmpc_kernels.cuh: it also counts the warps that still have work, so that the CTA leaves together).
+// WARPS per CTA (one CTA per SM): 8 (255 registers per thread) or 12 (168 registers, some spills to L1-resident local memory,
+// three warps per scheduler to hide the fixed FP64 latencies) when the double buffers of 12 warps fit shared memory.
+template <int NX, bool LTV, typename FT, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT> io, const double* __restrict__ G,
                   const double* __restrict__ hg) {
     using S = Stream<NX, LTV, FT, 32>;
-    const int lane = threadIdx.x & 31;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    using SM = StreamSmem<NX, FT>;
+    extern __shared__ __align__(128) unsigned char stream_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     const bool has_cs = io.cshift != nullptr;
     const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV);
     double* const w64 = io.ws64 + warp * (long long)l.n64 * 32 + lane;
     FT* const wft = io.wsft + warp * (long long)l.nft * 32 + lane;
+    StreamPipeTma<NX, LTV, FT> pp;
+    pp.l = &l;
+    pp.w64g = w64 - lane;
+    pp.wftg = wft - lane;
+    pp.bufb = SM::buf_bytes(has_cs, LTV);
+    pp.buf = stream_smem + wib * SM::warp_bytes(has_cs, LTV);
+    pp.bar = reinterpret_cast<uint64_t*>(pp.buf + 2 * pp.bufb);
+    pp.lane = lane;
+    pp.pass = 0;
+    pp.n_issue = pp.n_wait = 0;
+    pp.has_cs = has_cs;
+    if (lane == 0) {
+        mbar_init(pp.bar, 1);
+        mbar_init(pp.bar + 1, 1);
+    }
+    __syncwarp();
     typename S::Lane ln;
     ln.q = -1;
+    ln.iters = 0;
+    ln.fresh = true;
+    ln.th = ln.dth = ln.dtha = ln.alpha = ln.sigmu = ln.iptt = ln.mu = 0.0;
     bool drained = false;  // warp-uniform: the queue has run dry
     for (;;) {
         const bool need = ln.q < 0;
@@ -839,18 +1104,37 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
             const long long mine = (long long)base + __popc(want & ((1u << lane) - 1u));
             if (need && mine < io.batch) S::init_qp(p, l, ln, io, mine, w64, has_cs);
             drained = (long long)base + __popc(want) >= io.batch;
+            stream_pass_fence();
         }
-        if (__all_sync(0xffffffffu, ln.q < 0)) break;
-        if (ln.q >= 0) {
-            int st = S::pass_bu(p, l, ln, G, hg, w64, wft, has_cs);
-            if (st < 0 && ln.iters >= p.max_iter) st = 1;
-            if (st >= 0) {
-                S::finish(p, l, ln, io, w64, st);
-                ln.q = -1;
-            } else {
-                S::pass_f1(p, l, ln, G, hg, w64, wft, has_cs);
-                S::pass_b2(p, l, ln, w64, wft);
-                S::pass_f2(p, l, ln, G, hg, w64, wft);
+        bool working = !__all_sync(0xffffffffu, ln.q < 0);
+        if (cta_tick(working) == 0) break;  // every warp of the CTA is out of work
+        if (working) {
+            int st = S::pass_bu(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            stream_pass_fence();
+            if (ln.q >= 0) {
+                if (st < 0 && ln.iters >= p.max_iter) st = 1;
+                if (st >= 0) {
+                    S::finish(p, l, ln, io, w64, st);
+                    ln.q = -1;
+                }
+            }
+            working = !__all_sync(0xffffffffu, ln.q < 0);  // nothing left to iterate on in this warp: refill or leave
+        }
+        __syncthreads();
+        if (working) {
+            S::pass_f1(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            stream_pass_fence();
+        }
+        __syncthreads();
+        if (working) {
+            S::pass_b2(p, l, ln, wft, pp);
+            stream_pass_fence();
+        }
+        __syncthreads();
+        if (working) {
+            S::pass_f2(p, l, ln, G, hg, w64, wft, pp);
+            stream_pass_fence();
+            if (ln.q >= 0) {
                 ln.iters += 1;
                 ln.fresh = false;
             }

@@ -74,3 +74,30 @@ def test_stream_long_horizon(emul_lib, models):
     got = stream_solve(emul_lib, mdl, "C", "LBMPC", 200, X0)
     ref = OracleProblem("C", "LBMPC", mdl, 200).solve_batch(X0)
     assert_parity(got, ref)
+
+
+def test_stream_mixed_storage_mode(emul_lib, models):
+    """"f32+f64" mode (LBMPC_KERNEL_STREAM_MIXED): affine directions, Riccati factors, feed-forward terms and the centring
+    coefficients are STORED in FP32; iterate, applied step, right-hand sides (residuals) and all arithmetic stay FP64.  The
+    Newton directions are then inexact (1e-7 relative) but the residuals exact, so the LBMPC problems converge to the same
+    tolerances: same verdicts, iteration counts within +-3 (a few marginal QPs take two or three extra refinement
+    iterations), objective 1e-8, inputs 1e-6 for >= 95 % (reported separately from the FP64 parity, as BASELINE.json
+    north_star asks).  With the 616-row tracking set the barrier weights of the active polytope rows reach 1e10 in the last
+    iterations and FP32 factors no longer contract: a few percent of those QPs stop at the iteration cap (status 1) — the
+    mode is therefore never the default and the test only bounds that fraction."""
+    for form, variant, N in (("C", "LBMPC", 50), ("F", "LBMPC", 30)):
+        mdl = models[variant]
+        X0 = sample_ics(64, seed=N + 1)
+        got = stream_solve(emul_lib, mdl, form, variant, N, X0, mode=1)
+        ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, nthreads=4)
+        assert_parity(got, ref, tol=1e-6, frac_tight=0.95, max_dit=3, caps=(1e-4, 1e-3))
+        ok = ref["status"] == 0
+        assert np.abs(got["obj"][ok] - ref["obj"][ok]).max() / np.abs(ref["obj"][ok]).max() < 1e-8
+    mdl = models["LMPC"]
+    X0 = sample_ics(64, seed=51)
+    got = stream_solve(emul_lib, mdl, "C", "LMPC", 50, X0, mode=1)
+    ref = OracleProblem("C", "LMPC", mdl, 50).solve_batch(X0, nthreads=4)
+    same = got["status"] == ref["status"]
+    assert same.mean() >= 0.9 and set(got["status"][~same]) <= {1}
+    both = same & (ref["status"] == 0)
+    assert np.abs(got["obj"][both] - ref["obj"][both]).max() / np.abs(ref["obj"][both]).max() < 1e-8
