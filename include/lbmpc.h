@@ -139,11 +139,23 @@ int lbmpc_solve_batch_shifted(lbmpc_handle *h, int64_t batch, const double *dx0,
                               double *u_or_c, double *theta, double *x_traj, double *obj, int32_t *iters,
                               int32_t *status, void *stream);
 
+/* The same with a state AND input shift: cost_shift_xu is (nx+nu) x (N+1) x batch, records [ex_k ; eu_k] (eu of stage N
+ * ignored); the objective is evaluated at [x_k + ex_k ; theta ; u_k + eu_k].  This is what the F-form LBMPC problem needs:
+ * costLBMPC.m:27 rolls the LEARNED model (transitionLearned.m:13-14, u = K x + c on the learned state) while
+ * constraintsLBMPC.m:23 rolls the NOMINAL one, so with the oracle frozen the two sequences differ by e_{k+1} = (A + B K) e_k
+ * + d_k in the states and by K e_k in the inputs, independently of the decision variables [c; theta]. */
+int lbmpc_solve_batch_shifted_xu(lbmpc_handle *h, int64_t batch, const double *dx0, const double *dx_ref,
+                                 const double *d_off, const double *cost_shift_xu, const double *warm,
+                                 double *u_or_c, double *theta, double *x_traj, double *obj, int32_t *iters,
+                                 int32_t *status, void *stream);
+
 /* replaces learnedModel.m:25 + oracleL2NW.m:2-36 (mask variant casadiL2NW.m:14-28) applied along
  * the horizon: rolls the learned model x+ = A x + B u + g([x1;x2;u]) for the given input sequence
  * and returns the per-stage corrections d_k = g(.) (feed them to lbmpc_solve_batch as d_off).
  *   dx0 nx x batch; du (nu*N) x batch; X 3 x q x batch; Y nx x q x batch; valid q x batch or NULL;
- *   d_off nx x N x batch OUT.  Pointers follow cfg.pointers_on_device. */
+ *   d_off nx x N x batch OUT.  Pointers follow cfg.pointers_on_device.
+ * F-form handles: `du` holds the decision variables c and the rollout applies u = K x + c on the learned state
+ * (transitionLearned.m:13-14); C-form handles: `du` is the input sequence itself (LBMPC_casadi.m:307-347). */
 int lbmpc_oracle_apply(lbmpc_handle *h, int64_t batch, int32_t q, double bandwidth, double lambda,
                        const double *dx0, const double *du, const double *X, const double *Y,
                        const double *valid, double *d_off, void *stream);
@@ -165,15 +177,35 @@ int lbmpc_closed_loop(lbmpc_handle *h, int64_t batch, int32_t steps, int32_t q, 
  * L2NW oracle inside the optimisation, a non-convex NLP) as a SEQUENCE of QPs.  Outer iteration j = 0..sqp_iters-1:
  *     d_k = g([x1;x2;u]_k ; X, Y) along the learned-model rollout of the previous inputs (u^-1 = warm or 0)   [lbmpc_oracle_apply]
  *     one QP with the frozen offsets d_k, started from the previous solution                                   [lbmpc_solve_batch]
- * twin = 0: ONE state sequence, the frozen d_k enter the dynamics (LBMPC_casadi.m / costLBMPC.m).  twin = 1: the twin
- * sequences of DMS_LBMPC_casadi.m:252-319 — the cost sees the learned states x_k + e_k (e_{k+1} = A e_k + d_k, e_0 = 0), the
- * constraint rows and the dynamics the nominal states x_k (lbmpc_solve_batch_shifted); x_traj returns the nominal sequence.
+ * twin = 0: ONE state sequence, the frozen d_k enter the dynamics and therefore the cost AND the rows (the C-form script
+ * LBMPC_casadi.m with its learned-dynamics line :292-293 switched on).  twin = 1: the cost sees the LEARNED sequence, the
+ * constraint rows and the dynamics the NOMINAL one — the twin sequences of DMS_LBMPC_casadi.m:252-319 (C-form: e_{k+1} =
+ * A e_k + d_k, e_0 = 0) and the F-form problem of costLBMPC.m:25-45 / constraintsLBMPC.m:18-45 (e_{k+1} = (A + B K) e_k + d_k,
+ * input gap K e_k; lbmpc_solve_batch_shifted_xu); x_traj returns the nominal sequence.  F-form handles accept twin = 1 only.
  * Outputs are those of the last QP; du_step (batch x sqp_iters, may be NULL) = |u^j - u^{j-1}|_inf per outer iteration.
- * C-form handles on the 4-state model; array conventions as in lbmpc_solve_batch / lbmpc_oracle_apply. */
+ * 4-state model; array conventions as in lbmpc_solve_batch / lbmpc_oracle_apply. */
 int lbmpc_solve_sqp(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t q, double bandwidth, double lambda,
                     const double *dx0, const double *dx_ref, const double *X, const double *Y, const double *valid,
                     const double *warm, double *u, double *theta, double *x_traj, double *obj, int32_t *iters,
                     int32_t *status, double *du_step, void *stream);
+
+/* lbmpc_solve_sqp with the ORDER of the oracle model chosen per call.
+ *   order = 0  the oracle VALUE is frozen along the previous solution (lbmpc_solve_sqp): cheap, but the fixed point of the
+ *              outer iteration misses the dg/d(x,u) terms of the stationarity condition (error O(|dg/dxi|));
+ *   order = 1  value AND Jacobian (the derivative CasADi's AD of casadiL2NW.m:14-28 gives IPOPT, and fmincon's finite
+ *              differences of costLBMPC.m): every outer iteration solves an LTV QP on the LEARNED state sequence,
+ *                  x+ = (A + [J_k(:,1:2) 0 0]) x + (B + J_k(:,3)) u + d_k,  d_k = g(xibar_k) - J_k xibar_k,
+ *              i.e. a genuine SQP step whose fixed point is a stationary point of the reference's NLP.  twin = 1: the rows
+ *              follow the NOMINAL sequence (constraintsLBMPC.m:23, DMS_LBMPC_casadi.m:283-319) — they act on x_k - e_k,
+ *              u_k - K e_k with the gap e_k between the learned and the nominal rollout of the previous solution (exact
+ *              row values at the fixed point, row Jacobians to O(|dg/dxi|)); x_traj then returns the LEARNED sequence.
+ *              Reproduces the reference's saved LBMPC_N50_sys_full.mat history (40 steps, learned term active from step
+ *              2) to 5e-6 on the inputs (tests/test_oracle_golden.py, tests/test_gpu_parity.py).
+ * order = 1 runs on the stream mapping (the only one with per-stage dynamics). */
+int lbmpc_solve_sqp_ex(lbmpc_handle *h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t order, int32_t q,
+                       double bandwidth, double lambda, const double *dx0, const double *dx_ref, const double *X,
+                       const double *Y, const double *valid, const double *warm, double *u, double *theta,
+                       double *x_traj, double *obj, int32_t *iters, int32_t *status, double *du_step, void *stream);
 
 /* Force a thread mapping (LBMPC_KERNEL_*) and the lock-step tick of the warp kernel (lockstep: -1 auto, 0 off, 1 on).
  * Every mapping runs the same algorithm: results agree to round-off (tests/test_gpu_parity.py forces each one).

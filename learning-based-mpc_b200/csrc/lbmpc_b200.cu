@@ -53,7 +53,7 @@ struct lbmpc_handle {
     bool cta_big = false;              // large polytope block: G stays in global memory, sums by block reduction
     bool dev_ptrs = false;
     int64_t max_batch = 0;
-    double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr;
+    double *dG = nullptr, *dhg = nullptr, *dA = nullptr, *dB = nullptr, *dK = nullptr;  // dK: Kinit (zero for the C-form)
     unsigned long long* dqueue = nullptr;   // ring of kQueueRing work counters: every launch takes the next one, so a launch
                                             // that is still running never sees its counter reset by the following call
     int64_t queue_next = 0;
@@ -74,12 +74,12 @@ struct lbmpc_handle {
     // outer-iteration (SQP) scratch, grown on demand
     int64_t sqp_batch = 0;
     int sqp_iters = 0;
-    double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr, *q_csh = nullptr;
+    double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr, *q_csh = nullptr, *q_jac = nullptr;
     // kernel choice (lbmpc_set_kernel; LBMPC_KERNEL / LBMPC_LOCKSTEP / LBMPC_STREAM_* are read ONCE, in lbmpc_create)
     int force_kernel = LBMPC_KERNEL_AUTO, force_lockstep = -1;
     // stream kernel (one thread per QP, iterate in HBM): workspace of the resident warps
     int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM (default layout)
-    int st_warps_cap = 0;              // 8: never use the 12-warp variant (LBMPC_STREAM_WARPS, experiments)
+    int st_warps_cap = 0;              // 6: use the 6-warp variant everywhere (LBMPC_STREAM_WARPS, experiments)
     int max_smem_optin = 0;
     int64_t st_min_batch = 0;          // auto choice: batches at least this large take the stream kernel
     double* st_ws64 = nullptr;
@@ -198,7 +198,7 @@ static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const dou
     if (e != cudaSuccess) return e;
     StreamIO<FT> s{};
     s.batch = io.batch; s.dx0 = io.dx0; s.dx_ref = io.dx_ref; s.d_off = io.d_off; s.warm = io.warm; s.cshift = io.cshift;
-    s.jac = jac; s.uc = io.uc; s.theta = io.theta; s.xtraj = io.xtraj; s.obj = io.obj; s.iters = io.iters; s.status = io.status;
+    s.cs_stride = io.cs_stride; s.row_shift = io.row_shift; s.jac = jac; s.uc = io.uc; s.theta = io.theta; s.xtraj = io.xtraj; s.obj = io.obj; s.iters = io.iters; s.status = io.status;
     s.queue = next_queue(h);
     s.ws64 = h->st_ws64;
     s.wsft = (FT*)h->st_wsft;
@@ -209,12 +209,13 @@ static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const dou
     h->last_kernel = sizeof(FT) == 4 ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM;
     return cudaGetLastError();
 }
-// warps per CTA (= per SM): 12 when their double buffers fit shared memory, else 8
+// warps per CTA (= per SM): 8 (255 registers per thread) when their double buffers fit shared memory, else 6 (per-stage
+// Jacobians and a shift record together make the buffers 15 KB).  12 warps at 168 registers measured 1.5x SLOWER (spills).
 template <bool LTV, typename FT>
 static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st) {
     const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV);
-    const bool w12 = 12 * per_warp <= (size_t)h->max_smem_optin && h->st_warps_cap != 8;
-    return w12 ? launch_stream_w<LTV, FT, 12>(h, io, jac, st, 12 * per_warp) : launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp);
+    const bool w8 = 8 * per_warp <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
+    return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp);
 }
 static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed) {
     if (mixed) return jac ? launch_stream_t<true, float>(h, io, jac, st) : launch_stream_t<false, float>(h, io, jac, st);
@@ -225,11 +226,12 @@ static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int
                           const double* dx0, const double* du, long long du_ld, const double* X, const double* Y,
                           const double* valid, double* d_off) {
     const unsigned grid = (unsigned)((batch + 3) / 4);
+    const double* Kfb = h->hp.form == LBMPC_FORM_F ? h->dK : nullptr;  // F-form sequences hold c: u = K x + c
     if (q <= 128)
-        oracle_kernel<4, 1, 4><<<grid, 128, 0, st>>>(h->dA, h->dB, h->hp.N, batch, q, inv_h2, lambda, dx0, du, du_ld, X,
+        oracle_kernel<4, 1, 4><<<grid, 128, 0, st>>>(h->dA, h->dB, Kfb, h->hp.N, batch, q, inv_h2, lambda, dx0, du, du_ld, X,
                                                     Y, valid, d_off);
     else
-        oracle_kernel<4, 1, kOracleMaxPerLane><<<grid, 128, 0, st>>>(h->dA, h->dB, h->hp.N, batch, q, inv_h2, lambda,
+        oracle_kernel<4, 1, kOracleMaxPerLane><<<grid, 128, 0, st>>>(h->dA, h->dB, Kfb, h->hp.N, batch, q, inv_h2, lambda,
                                                                     dx0, du, du_ld, X, Y, valid, d_off);
     h->launches += 1;
 }
@@ -355,6 +357,8 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     CU_TRY(dmalloc(&h->dhg, (size_t)hp.ngp));
     CU_TRY(dmalloc(&h->dA, (size_t)hp.nx * hp.nx));
     CU_TRY(dmalloc(&h->dB, (size_t)hp.nx * hp.nu));
+    CU_TRY(dmalloc(&h->dK, (size_t)hp.nx * hp.nu));
+    CU_TRY(cudaMemcpy(h->dK, hp.Kinit.data(), sizeof(double) * hp.nx * hp.nu, cudaMemcpyHostToDevice));
     CU_TRY(dmalloc(&h->dqueue, kQueueRing));
     CU_TRY(dmalloc(&h->dprof, 16));
     CU_TRY(cudaMemset(h->dprof, 0, 16 * sizeof(unsigned long long)));
@@ -370,8 +374,8 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         auto optin = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, std::max(smem8, max_smem))); };
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 8>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 8>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 8>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 8>));
-        CU_TRY(optin(ipm_stream_kernel<4, false, double, 12>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 12>));
-        CU_TRY(optin(ipm_stream_kernel<4, false, float, 12>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 12>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
         h->st_min_batch = (int64_t)h->num_sms * 64;  // >= 64 QPs (2 warps) per SM; below that the shared-memory kernels win
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
@@ -379,7 +383,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use
             const StreamLayout<4> l(hp.N, hp.ng, false, false);
             const int64_t ctas = std::min<int64_t>(h->num_sms, (h->max_batch + 255) / 256);
-            CU_TRY(stream_workspace(h, ctas * 12, l, false));
+            CU_TRY(stream_workspace(h, ctas * 8, l, false));
         }
     }
     // experiment / test overrides, read once
@@ -410,9 +414,26 @@ int lbmpc_solve_batch(lbmpc_handle* h, int64_t batch, const double* dx0, const d
     return lbmpc_solve_batch_shifted(h, batch, dx0, dx_ref, d_off, nullptr, warm, u_or_c, theta, x_traj, obj, iters, status, stream);
 }
 
+static int solve_batch_impl(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
+                            const double* cost_shift, int cs_stride, const double* warm, double* u_or_c, double* theta, double* x_traj,
+                            double* obj, int32_t* iters, int32_t* status, void* stream);
+
 int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
                               const double* cost_shift, const double* warm, double* u_or_c, double* theta, double* x_traj,
                               double* obj, int32_t* iters, int32_t* status, void* stream) {
+    return solve_batch_impl(h, batch, dx0, dx_ref, d_off, cost_shift, h ? h->hp.nx : 0, warm, u_or_c, theta, x_traj, obj, iters, status, stream);
+}
+int lbmpc_solve_batch_shifted_xu(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
+                                 const double* cost_shift_xu, const double* warm, double* u_or_c, double* theta, double* x_traj,
+                                 double* obj, int32_t* iters, int32_t* status, void* stream) {
+    return solve_batch_impl(h, batch, dx0, dx_ref, d_off, cost_shift_xu, h ? h->hp.nx + h->hp.nu : 0, warm, u_or_c, theta, x_traj, obj, iters, status, stream);
+}
+
+}  // extern "C"
+
+static int solve_batch_impl(lbmpc_handle* h, int64_t batch, const double* dx0, const double* dx_ref, const double* d_off,
+                            const double* cost_shift, int cs_stride, const double* warm, double* u_or_c, double* theta, double* x_traj,
+                            double* obj, int32_t* iters, int32_t* status, void* stream) {
     if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
     if (batch < 0) return fail(LBMPC_EINVAL, "negative batch");
     if (batch == 0) return LBMPC_OK;
@@ -425,6 +446,8 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
     io.batch = batch;
     io.queue = h->dqueue;
     io.prof = h->prof_on ? h->dprof : nullptr;
+    io.cs_stride = cost_shift ? cs_stride : 0;
+    const size_t nb_cs = sizeof(double) * (size_t)batch * (size_t)cs_stride * (hp.N + 1);
     if (h->dev_ptrs) {
         io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm; io.cshift = cost_shift;
         io.uc = u_or_c; io.theta = theta; io.xtraj = x_traj; io.obj = obj; io.iters = iters; io.status = status;
@@ -472,8 +495,8 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
         io.d_off = d_off ? in(d_off, nb_doff) : nullptr;
         io.warm = warm ? in(warm, nb_warm) : nullptr;
         if (cost_shift) {  // read in every iteration: keep it in device memory
-            if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * nx * (N + 1)));
-            CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_xt, cudaMemcpyHostToDevice, st));
+            if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * (nx + nu) * (N + 1)));
+            CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_cs, cudaMemcpyHostToDevice, st));
             io.cshift = h->s_csh;
         }
         char* b_uc = a_uc ? nullptr : out(nb_uc);
@@ -506,8 +529,8 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
     if (d_off) CU_TRY(cudaMemcpyAsync(h->s_doff, d_off, nb_doff, cudaMemcpyHostToDevice, st));
     if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, nb_warm, cudaMemcpyHostToDevice, st));
     if (cost_shift) {
-        if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * nx * (N + 1)));  // first use only
-        CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_xt, cudaMemcpyHostToDevice, st));
+        if (!h->s_csh) CU_TRY(dmalloc(&h->s_csh, (size_t)h->max_batch * (nx + nu) * (N + 1)));  // first use only
+        CU_TRY(cudaMemcpyAsync(h->s_csh, cost_shift, nb_cs, cudaMemcpyHostToDevice, st));
         io.cshift = h->s_csh;
     }
     io.dx0 = a_dx0 ? a_dx0 : h->s_dx0;
@@ -532,6 +555,8 @@ int lbmpc_solve_batch_shifted(lbmpc_handle* h, int64_t batch, const double* dx0,
     if (!small_direct) scatter_small(h, b, nt, theta, obj, iters, status);
     return LBMPC_OK;
 }
+
+extern "C" {
 
 int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwidth, double lambda, const double* dx0,
                        const double* du, const double* X, const double* Y, const double* valid, double* d_off,
@@ -576,12 +601,22 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
                     const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
                     const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
                     int32_t* status, double* du_step, void* stream) {
+    return lbmpc_solve_sqp_ex(h, batch, sqp_iters, twin, 0, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm, u, theta, x_traj, obj,
+                              iters, status, du_step, stream);
+}
+
+int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t order, int32_t q, double bandwidth,
+                       double lambda, const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
+                       const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
+                       int32_t* status, double* du_step, void* stream) {
     if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (order != 0 && order != 1) return fail(LBMPC_EINVAL, "order must be 0 (frozen oracle value) or 1 (value and Jacobian)");
     if (batch < 0 || sqp_iters < 1) return fail(LBMPC_EINVAL, "batch must be >= 0 and sqp_iters >= 1");
     if (batch == 0) return LBMPC_OK;
     if (!dx0 || !X || !Y || !u || !theta || !obj || !iters || !status) return fail(LBMPC_EINVAL, "required array is NULL");
-    if (h->shape != 0 || h->hp.form != LBMPC_FORM_C)
-        return fail(LBMPC_ESHAPE, "solve_sqp: C-form handle on the 4-state Moore-Greitzer model");
+    if (h->shape != 0) return fail(LBMPC_ESHAPE, "solve_sqp: 4-state Moore-Greitzer model (the L2NW oracle is defined on xi = [x1;x2;u])");
+    if (h->hp.form == LBMPC_FORM_F && !twin)
+        return fail(LBMPC_ESHAPE, "solve_sqp: the F-form rolls the learned model in the cost only (costLBMPC.m:27 vs constraintsLBMPC.m:23): twin = 1");
     if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
     if (!(bandwidth > 0)) return fail(LBMPC_EINVAL, "bandwidth must be positive");
     if (!h->dev_ptrs && batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
@@ -594,11 +629,12 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
         h->q_ulin = h->q_warm = h->q_doff = h->q_step = nullptr;
         CU_TRY(dmalloc(&h->q_ulin, b * N)); CU_TRY(dmalloc(&h->q_warm, b * (N + nt)));
         CU_TRY(dmalloc(&h->q_doff, b * nx * N)); CU_TRY(dmalloc(&h->q_step, b * (size_t)sqp_iters));
-        cudaFree(h->q_csh);
-        h->q_csh = nullptr;
+        cudaFree(h->q_csh); cudaFree(h->q_jac);
+        h->q_csh = h->q_jac = nullptr;
         h->sqp_batch = batch; h->sqp_iters = sqp_iters;
     }
-    if (twin && !h->q_csh) CU_TRY(dmalloc(&h->q_csh, (size_t)h->sqp_batch * nx * (N + 1)));
+    if (order == 1 && !h->q_jac) CU_TRY(dmalloc(&h->q_jac, (size_t)h->sqp_batch * nx * 3 * N));
+    if (twin && !h->q_csh) CU_TRY(dmalloc(&h->q_csh, (size_t)h->sqp_batch * (nx + 1) * (N + 1)));
     // device views of the inputs / outputs
     const double *d_dx0 = dx0, *d_ref = dx_ref, *d_X = X, *d_Y = Y, *d_V = valid, *d_warm = warm;
     double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
@@ -627,17 +663,42 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
     const unsigned ug = (unsigned)((batch + 3) / 4);
     CU_TRY(cudaEventRecord(h->ev0, st));
     for (int j = 0; j < sqp_iters; ++j) {
+        if (order == 1) {  // value + Jacobian of the oracle along the learned rollout, gap to the nominal rollout (twin)
+            const double* Kfb = hp.form == LBMPC_FORM_F ? h->dK : nullptr;
+            const unsigned og = (unsigned)((batch + 3) / 4);
+            if (q <= 128)
+                oracle_jac_kernel<4, 4><<<og, 128, 0, st>>>(h->dA, h->dB, Kfb, hp.N, batch, q, inv_h2, lambda, d_dx0, h->q_ulin, (long long)N,
+                                                           d_X, d_Y, d_V, h->q_doff, h->q_jac, twin ? h->q_csh : nullptr);
+            else
+                oracle_jac_kernel<4, kOracleMaxPerLane><<<og, 128, 0, st>>>(h->dA, h->dB, Kfb, hp.N, batch, q, inv_h2, lambda, d_dx0, h->q_ulin,
+                                                                           (long long)N, d_X, d_Y, d_V, h->q_doff, h->q_jac,
+                                                                           twin ? h->q_csh : nullptr);
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+            BatchIO io{};
+            io.batch = batch; io.prof = nullptr;
+            io.dx0 = d_dx0; io.dx_ref = d_ref; io.d_off = h->q_doff; io.warm = j == 0 ? d_warm : h->q_warm;
+            if (twin) { io.cshift = h->q_csh; io.cs_stride = (int)nx + 1; io.row_shift = 1; }
+            io.uc = d_u; io.theta = d_th; io.xtraj = d_xt; io.obj = d_obj; io.iters = d_it; io.status = d_st;
+            CU_TRY(launch_ipm_any(h, io, st, h->q_jac));
+            sqp_update_kernel<<<ug, 128, 0, st>>>(batch, hp.N, hp.nt, d_u, d_th, h->q_ulin, h->q_warm, du_step ? h->q_step : nullptr,
+                                                  sqp_iters, j);
+            h->launches += 1;
+            CU_TRY(cudaGetLastError());
+            continue;
+        }
         launch_oracle(h, st, batch, q, inv_h2, lambda, d_dx0, h->q_ulin, (long long)N, d_X, d_Y, d_V, h->q_doff);
         CU_TRY(cudaGetLastError());
         BatchIO io{};
         io.batch = batch; io.queue = h->dqueue; io.prof = nullptr;
         io.dx0 = d_dx0; io.dx_ref = d_ref; io.d_off = h->q_doff; io.warm = j == 0 ? d_warm : h->q_warm;
         if (twin) {  // cost on the learned sequence x + e, rows and dynamics on the nominal one
-            twin_shift_kernel<4><<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(batch, hp.N, h->dA, h->q_doff, h->q_csh);
+            twin_shift_kernel<4><<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(batch, hp.N, h->dA, h->dB, h->dK, h->q_doff, h->q_csh);
             h->launches += 1;
             CU_TRY(cudaGetLastError());
             io.d_off = nullptr;
             io.cshift = h->q_csh;
+            io.cs_stride = (int)nx + 1;
         }
         io.uc = d_u; io.theta = d_th; io.xtraj = d_xt; io.obj = d_obj; io.iters = d_it; io.status = d_st;
         CU_TRY(launch_ipm_any(h, io, st));
@@ -821,12 +882,12 @@ void lbmpc_destroy(lbmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     free_loop(h->loop);
-    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dqueue); cudaFree(h->dprof);
+    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dK); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_x); cudaFree(h->s_small); cudaFree(h->s_csh);
     if (h->hs_small) cudaFreeHost(h->hs_small);
     if (h->hs_bounce) cudaFreeHost(h->hs_bounce);
-    cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh);
+    cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh); cudaFree(h->q_jac);
     cudaFree(h->st_ws64); cudaFree(h->st_wsft);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -132,6 +132,16 @@ struct Layout {
     LB_HD int i_dv(int j, int k, bool aff) const { return r3(k) + (aff ? NVB : 0) + j; }  // [dx;du] / [dxa;dua]
 };
 
+// Cost shift of one QP: the objective is evaluated at [x_k + ex_k ; theta ; u_k + eu_k] while the dynamics and every row act
+// on (x_k, u_k).  p points at (N+1) records of `stride` doubles: ex (NX) and, when stride > NX, eu (NU) behind it.
+//   twin state sequences with the oracle frozen: C-form e_{k+1} = A e_k + d_k (DMS_LBMPC_casadi.m:252-319); F-form, where the
+//   input is u = K x + c (transitionLearned.m:13 vs transitionNominal.m:12): e_{k+1} = (A + B K) e_k + d_k and eu_k = K e_k
+//   (costLBMPC.m:27 rolls the learned model, constraintsLBMPC.m:23 the nominal one).
+struct CShift {
+    const double* p;
+    int stride;
+};
+
 struct RedAsm {  // reductions of the assembly pass
     double rp, sl, lam, hl;  // max |r_p|, sum s*lambda, max lambda, sum lambda*slack
     double gth;              // sum over the stages of g_theta (NT = 1): theta component of the dual residual
@@ -283,11 +293,19 @@ struct Core {
     // (G'lambda of the box rows, g-layout, first NV fields of record R3); accumulates reductions.
     // ============================================================================================
     static LB_HD void asm_core(const P& p, const L& l, double* s, int k, unsigned rows, const StageRows& r, RedAsm& red,
-                              const double* csh = nullptr) {
-        double v[NV], g[NV], e[NX];
+                              CShift csh = CShift{nullptr, 0}) {
+        double v[NV], g[NV], e[NV];
         const bool last = k >= p.N;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) e[j] = csh ? csh[k * NX + j] : 0.0;  // cost evaluated at x + e_k (twin state sequences)
+        for (int j = 0; j < NV; ++j) e[j] = 0.0;
+        if (csh.p) {  // cost evaluated at [x + ex_k; theta; u + eu_k] (twin state sequences)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) e[j] = csh.p[k * csh.stride + j];
+            if (csh.stride > NX && !last) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) e[NZ + j] = csh.p[k * csh.stride + NX + j];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < NX; ++j) v[j] = r.v[j];
 #pragma unroll
@@ -300,7 +318,7 @@ struct Core {
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int b = 0; b < NV; ++b) {
-                const double vb = b < NX ? v[b] + e[b < NX ? b : 0] : v[b];
+                const double vb = v[b] + e[b];
                 if (b & 1) a1 += W[a * NV + b] * vb;
                 else a0 += W[a * NV + b] * vb;
             }
@@ -345,7 +363,7 @@ struct Core {
         red.gth += g[NX];
     }
     // fresh QP: initial slacks and multipliers s = max(h - a v, 1), lambda = 1, then the assembly
-    static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red, const double* csh = nullptr) {
+    static LB_HD void init_assemble_stage(const P& p, const L& l, double* s, int k, RedAsm& red, CShift csh = CShift{nullptr, 0}) {
         const unsigned rows = stage_rows(p, k);
         StageRows r;
         double* r1 = s + l.r1(k);
@@ -369,7 +387,7 @@ struct Core {
     }
     // running QP: apply the step parked by final_stage (ds, dl in the scratch block; dx, du), then the assembly
     static LB_HD void update_assemble_stage(const P& p, const L& l, double* s, int k, double alpha, RedAsm& red,
-                                           const double* csh = nullptr) {
+                                           CShift csh = CShift{nullptr, 0}) {
         const unsigned rows = stage_rows(p, k);
         StageRows r;
         load_rows(l, s, k, r);
@@ -445,15 +463,16 @@ struct Core {
         if (j < NX || k < p.N) r1[j] += alpha * r3[j];
     }
     // cost gradient row a of stage k: W_type(k)[a,:] v_k (+ lin at kT)
-    static LB_HD double grad_row(const P& p, const RowTab& T, const L& l, const double* s, int k, int a, const double* csh = nullptr) {
+    static LB_HD double grad_row(const P& p, const RowTab& T, const L& l, const double* s, int k, int a, CShift csh = CShift{nullptr, 0}) {
         const bool last = k >= p.N;
         const double* r1 = s + l.r1(k);
         const double* W = T.W[stage_type(p, k)] + a * NV;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int b = 0; b < NV; ++b) {
-            const double vb = b < NX ? r1[b] + (csh ? csh[k * NX + (b < NX ? b : 0)] : 0.0)
-                                     : (b < NZ ? s[l.o_misc + L::M_TH + (b - NX)] : (last ? 0.0 : r1[NX + (b - NZ)]));
+            const double vb = b < NX ? r1[b] + (csh.p ? csh.p[k * csh.stride + (b < NX ? b : 0)] : 0.0)
+                                     : (b < NZ ? s[l.o_misc + L::M_TH + (b - NX)]
+                                               : (last ? 0.0 : r1[NX + (b - NZ)] + ((csh.p && csh.stride > NX) ? csh.p[k * csh.stride + NX + (b >= NZ ? b - NZ : 0)] : 0.0)));
             if (b & 1) a1 += W[b] * vb;
             else a0 += W[b] * vb;
         }
@@ -462,7 +481,7 @@ struct Core {
         return g;
     }
     // theta rows of stage k: gradient only
-    static LB_HD void asm_theta_item(const P& p, const RowTab& T, const L& l, double* s, int k, RedAsm& red, const double* csh = nullptr) {
+    static LB_HD void asm_theta_item(const P& p, const RowTab& T, const L& l, double* s, int k, RedAsm& red, CShift csh = CShift{nullptr, 0}) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             const double g = grad_row(p, T, l, s, k, NX + t, csh);
@@ -472,7 +491,7 @@ struct Core {
         }
     }
     // predictor assembly of item (k, j): cost gradient row, barrier diagonal, Newton rhs, Farkas input, reductions
-    static LB_HD void asm_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedAsm& red, const double* csh = nullptr) {
+    static LB_HD void asm_item(const P& p, const RowTab& T, const L& l, double* s, int k, int j, RedAsm& red, CShift csh = CShift{nullptr, 0}) {
         const bool last = k >= p.N;
         const double* r1 = s + l.r1(k);
         double* r2 = s + l.r2(k);
@@ -1524,15 +1543,16 @@ struct Core {
     }
 
     // stage: objective contribution 0.5 v'W v (+ lin'z at kT)
-    static LB_HD double objective_stage(const P& p, const L& l, const double* s, int k, const double* csh = nullptr) {
+    static LB_HD double objective_stage(const P& p, const L& l, const double* s, int k, CShift csh = CShift{nullptr, 0}) {
         double v[NV];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)] + (csh ? csh[k * NX + j] : 0.0);
+        for (int j = 0; j < NX; ++j) v[j] = s[l.i_x(j, k)] + (csh.p ? csh.p[k * csh.stride + j] : 0.0);
 #pragma unroll
         for (int j = 0; j < NT; ++j) v[NX + j] = s[l.o_misc + L::M_TH + j];
         const bool last = k >= p.N;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) v[NZ + j] = last ? 0.0 : s[l.i_u(j, k)];
+        for (int j = 0; j < NU; ++j)
+            v[NZ + j] = last ? 0.0 : s[l.i_u(j, k)] + ((csh.p && csh.stride > NX) ? csh.p[k * csh.stride + NX + j] : 0.0);
         const double* W = p.W[stage_type(p, k)];
         double J = 0.0;
 #pragma unroll

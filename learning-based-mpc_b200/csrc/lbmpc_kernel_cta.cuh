@@ -192,7 +192,7 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
 
         int iters = 0, status = 1;  // LBMPC_ST_MAXITER unless a verdict is reached
         double alpha = 0.0;
-        const double* const csh = io.cshift ? io.cshift + q * (long long)((N + 1) * NX) : nullptr;
+        const CShift csh{io.cshift ? io.cshift + q * (long long)((N + 1) * io.cs_stride) : nullptr, io.cs_stride};
         LB_PROF(0)
         for (;;) {
             // ================= phase E+A: apply the previous step (or initialise the rows), predictor assembly =================

@@ -38,7 +38,9 @@ struct BatchIO {
     int *iters, *status;
     unsigned long long* queue;  // global work counter (zeroed before launch)
     unsigned long long* prof;   // optional (may be null): per-phase SM cycles of CTA 0, see lbmpc_debug_phase_cycles
-    const double* cshift;       // optional NX x (N+1) per QP: the cost is evaluated at x_k + cshift_k (twin state sequences)
+    const double* cshift;       // optional cs_stride x (N+1) per QP: the cost is evaluated at [x_k + ex_k; u_k + eu_k] (CShift, lbmpc_core.cuh)
+    int cs_stride;              // NX: state shift only; NX + NU: state and input shift
+    int row_shift;              // stream mapping only: cshift moves the ROWS instead of the cost (first-order SQP)
     int lockstep;               // warp kernel: the warps of a CTA start every iteration together (see cta_tick)
 };
 
@@ -307,7 +309,7 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
 
         int iters = 0, status = 1;  // LBMPC_ST_MAXITER unless a verdict is reached
         double alpha = 0.0;
-        const double* const csh = io.cshift ? io.cshift + q * (long long)((N + 1) * NX) : nullptr;
+        const CShift csh{io.cshift ? io.cshift + q * (long long)((N + 1) * io.cs_stride) : nullptr, io.cs_stride};
         LB_PROF(0)
         for (;;) {
             if (io.lockstep) cta_tick(true);
@@ -542,8 +544,8 @@ constexpr int kOracleMaxPerLane = 16;  // q <= 512
 // PER = data points held in registers per lane (4: q <= 128, the reference's q = 10/50/100; 16: q <= 512)
 template <int NX, int NU, int PER>
 __global__ void __launch_bounds__(128, 6)
-oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N, long long batch, int q,
-              double inv_h2, double lambda, const double* __restrict__ dx0, const double* __restrict__ du,
+oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ Kfb, int N, long long batch,
+              int q, double inv_h2, double lambda, const double* __restrict__ dx0, const double* __restrict__ du,
               long long du_ld, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ valid,
               double* __restrict__ d_off) {
     constexpr int NI = 3;
@@ -562,7 +564,9 @@ oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N,
         for (int a = 0; a < NX; ++a) ys[r][a] = on ? Y[(qp * q + i) * NX + a] : 0.0;
         vs[r] = on ? (valid ? valid[qp * q + i] : 1.0) : -1.0;  // -1: slot unused
     }
-    double Am[NX * NX], Bm[NX * NU], x[NX];
+    double Am[NX * NX], Bm[NX * NU], Km[NU * NX], x[NX];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) Km[i] = Kfb ? Kfb[i] : 0.0;  // F-form: the sequence holds c, u = K x + c (transitionLearned.m:13)
 #pragma unroll
     for (int i = 0; i < NX * NX; ++i) Am[i] = A[i];
 #pragma unroll
@@ -572,7 +576,12 @@ oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N,
     for (int k = 0; k < N; ++k) {
         double u[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) u[i] = du[qp * du_ld + k * NU + i];
+        for (int i = 0; i < NU; ++i) {
+            double v = du[qp * du_ld + k * NU + i];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += Km[i * NX + j] * x[j];
+            u[i] = v;
+        }
         const double xi[NI] = {x[0], x[1], u[0]};
         double sk = 0.0, g[NX];
 #pragma unroll
@@ -613,6 +622,136 @@ oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, int N,
         }
 #pragma unroll
         for (int a = 0; a < NX; ++a) x[a] = xn[a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// first-order model of the learned dynamics along the learned rollout of the previous solution (warp per QP, lanes over the
+// q data points):  g(xi) AND dg/dxi of the L2NW oracle (what CasADi's AD of casadiL2NW.m:14-28 hands IPOPT,
+// DMS_LBMPC_casadi.m:252-319 / hybrid_LBMPC_casadi.m:250-267):
+//     k_i = exp(-|X_i - xi|^2 / h^2), D = lambda + sum v_i k_i, g = sum Y_i k_i / D
+//     dg/dxi = (sum Y_i dk_i - g sum v_i dk_i) / D,  dk_i = k_i 2 (X_i - xi) / h^2
+// Outputs per stage: J_k (NX x 3), d_k = g(xibar_k) - J_k xibar_k, and (rs != nullptr) the gap between the learned and the
+// nominal rollout of the same decision variables, records [e_k | K e_k] — the rows of the QP follow the nominal sequence.
+// ---------------------------------------------------------------------------------------------
+template <int NX, int PER>
+__global__ void __launch_bounds__(128, 4)
+oracle_jac_kernel(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ Kfb, int N, long long batch,
+                  int q, double inv_h2, double lambda, const double* __restrict__ dx0, const double* __restrict__ du,
+                  long long du_ld, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ valid,
+                  double* __restrict__ d_off, double* __restrict__ jac, double* __restrict__ rs) {
+    constexpr int NI = 3;
+    const int lane = threadIdx.x & 31;
+    const long long qp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qp >= batch) return;
+    double xs[PER][NI], ys[PER][NX], vs[PER];
+    const int per = (q + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int i = lane + 32 * r;
+        const bool on = r < per && i < q;
+#pragma unroll
+        for (int a = 0; a < NI; ++a) xs[r][a] = on ? X[(qp * q + i) * NI + a] : 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) ys[r][a] = on ? Y[(qp * q + i) * NX + a] : 0.0;
+        vs[r] = on ? (valid ? valid[qp * q + i] : 1.0) : -1.0;
+    }
+    double Am[NX * NX], Bm[NX], Km[NX], x[NX], xn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Km[i] = Kfb ? Kfb[i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) Am[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        Bm[i] = B[i];
+        x[i] = xn[i] = dx0[qp * NX + i];   // x: learned rollout, xn: nominal rollout
+    }
+    for (int k = 0; k <= N; ++k) {
+        if (rs && lane <= NX) {  // gap record of stage k
+            double eu = 0.0, ev = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                eu += Km[j] * (x[j] - xn[j]);
+                ev = lane == j ? x[j] - xn[j] : ev;
+            }
+            rs[(qp * (N + 1) + k) * (NX + 1) + lane] = lane == NX ? eu : ev;
+        }
+        if (k == N) break;
+        const double c = du[qp * du_ld + k];
+        double u = c, un = c;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            u += Km[j] * x[j];
+            un += Km[j] * xn[j];
+        }
+        const double xi[NI] = {x[0], x[1], u};
+        double sk = 0.0, g[NX], dD[NI], dn[NX][NI];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            g[a] = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NI; ++cc) dn[a][cc] = 0.0;
+        }
+#pragma unroll
+        for (int cc = 0; cc < NI; ++cc) dD[cc] = 0.0;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            if (r < per && vs[r] >= 0.0) {
+                double d2 = 0.0, dv[NI];
+#pragma unroll
+                for (int a = 0; a < NI; ++a) {
+                    dv[a] = xs[r][a] - xi[a];
+                    d2 += dv[a] * dv[a];
+                }
+                const double kv = exp(-d2 * inv_h2), vi = valid ? vs[r] : 1.0;
+                sk += vi * kv;
+#pragma unroll
+                for (int cc = 0; cc < NI; ++cc) {
+                    const double wk = kv * 2.0 * dv[cc] * inv_h2;
+                    dD[cc] += vi * wk;
+#pragma unroll
+                    for (int a = 0; a < NX; ++a) dn[a][cc] += ys[r][a] * wk;
+                }
+#pragma unroll
+                for (int a = 0; a < NX; ++a) g[a] += ys[r][a] * kv;
+            }
+        }
+        sk = warp_sum(sk);
+        const double wn = 1.0 / (lambda + sk);
+#pragma unroll
+        for (int cc = 0; cc < NI; ++cc) dD[cc] = warp_sum(dD[cc]);
+        double Jv = 0.0, dvv = 0.0;  // lane a*3+c keeps J[a][c]; lane a keeps d[a]
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            g[a] = warp_sum(g[a]) * wn;
+            double dk = g[a];
+#pragma unroll
+            for (int cc = 0; cc < NI; ++cc) {
+                const double J = (warp_sum(dn[a][cc]) - g[a] * dD[cc]) * wn;
+                dk -= J * xi[cc];
+                Jv = lane == a * NI + cc ? J : Jv;
+            }
+            dvv = lane == a ? dk : dvv;
+        }
+        if (lane < NX * NI) jac[((qp * N + k) * NX) * NI + lane] = Jv;
+        if (lane < NX) d_off[(qp * N + k) * NX + lane] = dvv;
+        double xl[NX], xm[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            double v = g[a] + Bm[a] * u, w = Bm[a] * un;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                v += Am[a * NX + j] * x[j];
+                w += Am[a * NX + j] * xn[j];
+            }
+            xl[a] = v;
+            xm[a] = w;
+        }
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            x[a] = xl[a];
+            xn[a] = xm[a];
+        }
     }
 }
 
@@ -772,19 +911,30 @@ sqp_update_kernel(long long batch, int N, int nt, const double* __restrict__ uc,
 // ---------------------------------------------------------------------------------------------
 template <int NX>
 __global__ void __launch_bounds__(128)
-twin_shift_kernel(long long batch, int N, const double* __restrict__ A, const double* __restrict__ d_off, double* __restrict__ csh) {
+twin_shift_kernel(long long batch, int N, const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ K,
+                  const double* __restrict__ d_off, double* __restrict__ csh) {
+    // e_{k+1} = (A + B K) e_k + d_k, eu_k = K e_k; records [ex (NX) | eu (1)] (K = 0 for the C-form: plain A, eu = 0)
     const long long qp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (qp >= batch) return;
-    double a[NX * NX], e[NX];
+    double a[NX * NX], kk[NX], e[NX];
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) a[i] = A[i];
+    for (int i = 0; i < NX; ++i) kk[i] = K[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) a[i * NX + j] = A[i * NX + j] + B[i] * kk[j];
 #pragma unroll
     for (int i = 0; i < NX; ++i) e[i] = 0.0;
     const double* d = d_off + qp * (long long)N * NX;
-    double* o = csh + qp * (long long)(N + 1) * NX;
+    double* o = csh + qp * (long long)(N + 1) * (NX + 1);
     for (int k = 0;; ++k) {
+        double eu = 0.0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) o[k * NX + i] = e[i];
+        for (int i = 0; i < NX; ++i) {
+            o[k * (NX + 1) + i] = e[i];
+            eu += kk[i] * e[i];
+        }
+        o[k * (NX + 1) + NX] = eu;
         if (k == N) break;
         double n[NX];
 #pragma unroll

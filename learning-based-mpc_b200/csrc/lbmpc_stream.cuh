@@ -66,7 +66,7 @@ struct StreamLayout {
         int o = 0;
         o_it = o; o += RS_IT * (N + 1);
         o_q = o;  o += RS_Q * (N + 1);
-        o_cs = o; o += cs ? NX * (N + 1) : 0;
+        o_cs = o; o += cs ? NVB * (N + 1) : 0;  // [ex | eu] per stage
         o_j = o;  o += ltv ? NJ * N : 0;
         o_sg = o; o += ng;
         o_lg = o; o += ng;
@@ -93,6 +93,8 @@ template <typename FT>
 struct StreamIO {  // batch-major caller arrays (include/lbmpc.h)
     long long batch;
     const double *dx0, *dx_ref, *d_off, *warm, *cshift, *jac;
+    int cs_stride;  // doubles per stage of cshift: NX (state shift) or NX + 1 (state and input shift)
+    int row_shift;  // 0: cshift moves the COST; 1: it moves the ROWS (they act on x_k - ex_k, u_k - eu_k; first-order SQP)
     double *uc, *theta, *xtraj, *obj;
     int *iters, *status;
     unsigned long long* queue;
@@ -111,7 +113,7 @@ struct StreamNeeds {
     static LB_HD int it(int pass) { return pass == PASS_B2 ? 0 : (pass == PASS_BU ? SL::RS_IT : SL::RS_IT0); }  // leading elements of the FP64 record
     static LB_HD int d_lo(int pass) { return (pass == PASS_BU || pass == PASS_F2) ? SL::D_DA : SL::D_RL; }
     static LB_HD int d_hi(int pass) { return pass == PASS_BU ? SL::D_RL : (pass == PASS_B2 ? SL::RS_D : SL::D_T2); }
-    static LB_HD bool cs(int pass) { return pass == PASS_BU || pass == PASS_F1; }
+    static LB_HD bool cs(int pass, bool rows) { return pass == PASS_BU || pass == PASS_F1 || (rows && pass == PASS_F2); }
 };
 
 // read-only view of the pipeline item a pass is working on (stride LS between elements):
@@ -152,7 +154,7 @@ struct StreamPipeDirect {
         v.it = w64 + (l->o_it + k * SL::RS_IT) * LS;
         v.d = wft + k * SL::RS_D * LS;
         v.q = w64 + (l->o_q + k * SL::RS_Q) * LS;
-        v.cs = w64 + (l->o_cs + k * NX) * LS;
+        v.cs = w64 + (l->o_cs + k * (NX + 1)) * LS;
         v.jac = w64 + (l->o_j + k * SL::NJ) * LS;
         v.sg = w64 + l->o_sg * LS;
         v.lg = w64 + l->o_lg * LS;
@@ -220,7 +222,7 @@ struct Stream {
 #pragma unroll
         for (int j = 0; j < NX; ++j) vv[j] = v[j] + (has_cs ? ld(cs, j) : 0.0);
         vv[NX] = ln.th;
-        vv[NZ] = last ? 0.0 : v[NX];
+        vv[NZ] = last ? 0.0 : v[NX] + (has_cs ? ld(cs, NX) : 0.0);
         const double* W = p.W[C::stage_type(p, k)];
         double J = 0.0;
 #pragma unroll
@@ -281,8 +283,10 @@ struct Stream {
             for (int i = 0; i < N * SL::NJ; ++i) st(w64, l.o_j + i, jq[i]);
         }
         if (has_cs) {
-            const double* cq = io.cshift + q * (long long)((N + 1) * NX);
-            for (int i = 0; i < (N + 1) * NX; ++i) st(w64, l.o_cs + i, cq[i]);
+            const double* cq = io.cshift + q * (long long)((N + 1) * io.cs_stride);
+            for (int k = 0; k <= N; ++k)
+#pragma unroll
+                for (int j = 0; j < NVB; ++j) st(w64, l.o_cs + k * NVB + j, j < io.cs_stride ? cq[k * io.cs_stride + j] : 0.0);
         }
         double x[NX];
 #pragma unroll
@@ -321,7 +325,7 @@ struct Stream {
     // ============================================================================================
     template <class Pipe>
     static LB_HD int pass_bu(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                             double* w64, FT* wft, bool has_cs, Pipe& pp) {
+                             double* w64, FT* wft, bool has_cs, bool rsh, Pipe& pp) {
         const int N = p.N;
         const int nch = (p.ng + CH - 1) / CH;
         const bool fresh = ln.fresh;
@@ -360,8 +364,10 @@ struct Stream {
                 vn[j] = vo[j] + alpha * dv[j];
                 if (ex) st(it, j, vn[j]);
             }
-            double g[NV];
-            cost_grad(p, ln, vw.cs, k, vn, has_cs, g, &J);
+            double g[NV], es[NVB];  // es: row shift of the stage (rows act on v - es)
+#pragma unroll
+            for (int j = 0; j < NVB; ++j) es[j] = (has_cs && rsh && (j < NX || !last)) ? ld(vw.cs, j) : 0.0;
+            cost_grad(p, ln, vw.cs, k, vn, has_cs && !rsh, g, &J);
             double qd[NVB], q[NVB], gl[NVB];
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
@@ -376,7 +382,7 @@ struct Stream {
                         S = ld(vw.it, SL::F_S + r);
                         Lm = ld(vw.it, SL::F_LB + r);
                     }
-                    const double slack_o = side == 0 ? p.hi[j] - vo[j] : vo[j] - p.lo[j];
+                    const double slack_o = side == 0 ? p.hi[j] - (vo[j] - es[j]) : (vo[j] - es[j]) - p.lo[j];
                     const double rp_o = S - slack_o, is = lb_rcp(S), w = Lm * is;
                     const double dsa = -rp_o - sgn * dva[j], dla = -Lm - w * dsa;
                     const double ds = -rp_o - sgn * dv[j];
@@ -390,7 +396,7 @@ struct Stream {
                         st(it, SL::F_S + r, Sn);
                         st(it, SL::F_LB + r, Ln);
                     }
-                    const double slack = side == 0 ? p.hi[j] - vn[j] : vn[j] - p.lo[j];
+                    const double slack = side == 0 ? p.hi[j] - (vn[j] - es[j]) : (vn[j] - es[j]) - p.lo[j];
                     const double rp = act ? Sn - slack : 0.0;
                     const double wn = Ln * lb_rcp(Sn);
                     qdj += wn;
@@ -412,7 +418,7 @@ struct Stream {
                 double zo[NZ], zn[NZ], dza[NZ], dz[NZ];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
-                    zo[a] = vo[a]; zn[a] = vn[a]; dza[a] = dva[a]; dz[a] = dv[a];
+                    zo[a] = vo[a] - es[a]; zn[a] = vn[a] - es[a]; dza[a] = dva[a]; dz[a] = dv[a];
                 }
                 zo[NX] = th_old; zn[NX] = th; dza[NX] = ln.dtha; dz[NX] = ln.dth;
                 for (int c = 0; c < nch; ++c) {
@@ -604,7 +610,7 @@ struct Stream {
     // ============================================================================================
     template <class Pipe>
     static LB_HD void pass_f1(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                              double* w64, FT* wft, bool has_cs, Pipe& pp) {
+                              double* w64, FT* wft, bool has_cs, bool rsh, Pipe& pp) {
         const int N = p.N;
         const int nch = (p.ng + CH - 1) / CH;
         double dxa[NX], ratio = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -640,8 +646,10 @@ struct Stream {
 #pragma unroll
             for (int j = 0; j < NVB; ++j)
                 if (j < NX || !last) stf(d, SL::D_DA + j, dva[j]);
-            double g[NV];
-            cost_grad(p, ln, vw.cs, k, v, has_cs, g, nullptr);
+            double g[NV], es[NVB];
+#pragma unroll
+            for (int j = 0; j < NVB; ++j) es[j] = (has_cs && rsh && (j < NX || !last)) ? ld(vw.cs, j) : 0.0;
+            cost_grad(p, ln, vw.cs, k, v, has_cs && !rsh, g, nullptr);
             double* qr = w64 + (l.o_q + k * SL::RS_Q) * LS;
             st(qr, NX, g[NX]);
 #pragma unroll
@@ -657,7 +665,7 @@ struct Stream {
                         S = ld(vw.it, SL::F_S + r);
                         Lm = ld(vw.it, SL::F_LB + r);
                     }
-                    const double slack = side == 0 ? p.hi[j] - v[j] : v[j] - p.lo[j];
+                    const double slack = side == 0 ? p.hi[j] - (v[j] - es[j]) : (v[j] - es[j]) - p.lo[j];
                     const double rp = act ? S - slack : 0.0, is = lb_rcp(S), w = Lm * is;
                     const double dsa = act ? -rp - sgn * dva[j] : 0.0, dla = -Lm - w * dsa;
                     const double rr = dsa * is;
@@ -678,7 +686,7 @@ struct Stream {
 #pragma unroll
                 for (int a = 0; a < NX; ++a) {
                     dza[a] = dxa[a];
-                    z[a] = v[a];
+                    z[a] = v[a] - es[a];
                 }
                 dza[NX] = ln.dtha;
                 z[NX] = ln.th;
@@ -783,7 +791,7 @@ struct Stream {
     // ============================================================================================
     template <class Pipe>
     static LB_HD void pass_f2(const P& p, const SL& l, Lane& ln, const double* __restrict__ G, const double* __restrict__ hg,
-                              double* w64, FT* wft, Pipe& pp) {
+                              double* w64, FT* wft, bool has_cs, bool rsh, Pipe& pp) {
         const int N = p.N;
         const int nch = (p.ng + CH - 1) / CH;
         const double sigmu = ln.sigmu;
@@ -820,6 +828,9 @@ struct Stream {
 #pragma unroll
             for (int j = 0; j < NVB; ++j)
                 if (j < NX || !last) st(it, SL::F_DV + j, dv[j]);
+            double es[NVB];
+#pragma unroll
+            for (int j = 0; j < NVB; ++j) es[j] = (has_cs && rsh && (j < NX || !last)) ? ld(vw.cs, j) : 0.0;
 #pragma unroll
             for (int j = 0; j < NVB; ++j) {
 #pragma unroll
@@ -832,7 +843,7 @@ struct Stream {
                         S = ld(vw.it, SL::F_S + r);
                         Lm = ld(vw.it, SL::F_LB + r);
                     }
-                    const double slack = side == 0 ? p.hi[j] - v[j] : v[j] - p.lo[j];
+                    const double slack = side == 0 ? p.hi[j] - (v[j] - es[j]) : (v[j] - es[j]) - p.lo[j];
                     const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
                     const double dsa = -rp - sgn * dva[j], dla = -Lm - w * dsa;
                     const double ds = -rp - sgn * dv[j];
@@ -847,7 +858,7 @@ struct Stream {
                 for (int a = 0; a < NX; ++a) {
                     dza[a] = dva[a];
                     dz[a] = dx[a];
-                    z[a] = v[a];
+                    z[a] = v[a] - es[a];
                 }
                 dza[NX] = ln.dtha;
                 dz[NX] = ln.dth;
@@ -924,19 +935,19 @@ struct Stream {
     static LB_HD void solve_one(const P& p, const SL& l, const StreamIO<FT>& io, long long q, const double* G, const double* hg,
                                 double* w64, FT* wft) {
         Lane ln;
-        const bool has_cs = io.cshift != nullptr;
+        const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
         StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
         init_qp(p, l, ln, io, q, w64, has_cs);
         for (;;) {
-            int st = pass_bu(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            int st = pass_bu(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             if (st < 0 && ln.iters >= p.max_iter) st = 1;
             if (st >= 0) {
                 finish(p, l, ln, io, w64, st);
                 return;
             }
-            pass_f1(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            pass_f1(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             pass_b2(p, l, ln, wft, pp);
-            pass_f2(p, l, ln, G, hg, w64, wft, pp);
+            pass_f2(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             ln.iters += 1;
             ln.fresh = false;
         }
@@ -960,7 +971,7 @@ struct StreamSmem {  // byte offsets inside one buffer
     static constexpr int off_cs = off_d + (SL::D_T2 - SL::D_DA) * kLineF;             // after the widest range next to an iterate record (F2)
     static constexpr int off_q = (SL::RS_D - SL::D_RL) * kLineF;                      // B2: after its FT range
     static_assert(off_q + SL::RS_Q * kLine <= off_cs, "layout");
-    static __host__ __device__ int off_j(bool cs) { return off_cs + (cs ? NX * kLine : 0); }
+    static __host__ __device__ int off_j(bool cs) { return off_cs + (cs ? (NX + 1) * kLine : 0); }
     static __host__ __device__ int buf_bytes(bool cs, bool ltv) {
         int b = off_j(cs) + (ltv ? SL::NJ * kLine : 0);
         const int b2 = off_q + SL::RS_Q * kLine, poly = 2 * SL::kPolyChunk * kLine;
@@ -983,7 +994,7 @@ struct StreamPipeTma {
     uint64_t* bar;        // two mbarriers
     int lane, pass, bufb, ring[2];
     unsigned n_issue, n_wait;
-    bool has_cs;
+    bool has_cs, rows;
     __device__ void start(int pass_) { pass = pass_; }
     __device__ void issue(int item) {
         if (item == kStreamNone) return;
@@ -997,15 +1008,15 @@ struct StreamPipeTma {
             if (item >= 0) {
                 const int k = item, dlo = ND::d_lo(pass), dn = ND::d_hi(pass) - dlo;
                 const int it = ND::it(pass);
-                const bool cs = has_cs && ND::cs(pass), jj = LTV && k < l->N;
+                const bool cs = has_cs && ND::cs(pass, rows), jj = LTV && k < l->N;
                 const bool qq = pass == PASS_B2;
-                const uint32_t bytes = it * SM::kLine + dn * SM::kLineF + (cs ? NX * SM::kLine : 0) + (jj ? SL::NJ * SM::kLine : 0) +
+                const uint32_t bytes = it * SM::kLine + dn * SM::kLineF + (cs ? (NX + 1) * SM::kLine : 0) + (jj ? SL::NJ * SM::kLine : 0) +
                                        (qq ? SL::RS_Q * SM::kLine : 0);
                 mbar_expect_tx(br, bytes);
                 if (qq) tma_bulk_g2s(dst + SM::off_q, w64g + (size_t)(l->o_q + k * SL::RS_Q) * 32, SL::RS_Q * SM::kLine, br);
                 if (it) tma_bulk_g2s(dst + SM::off_it, w64g + (size_t)(l->o_it + k * SL::RS_IT) * 32, it * SM::kLine, br);
                 tma_bulk_g2s(dst + (it ? SM::off_d : 0), wftg + (size_t)(k * SL::RS_D + dlo) * 32, dn * SM::kLineF, br);
-                if (cs) tma_bulk_g2s(dst + SM::off_cs, w64g + (size_t)(l->o_cs + k * NX) * 32, NX * SM::kLine, br);
+                if (cs) tma_bulk_g2s(dst + SM::off_cs, w64g + (size_t)(l->o_cs + k * (NX + 1)) * 32, (NX + 1) * SM::kLine, br);
                 if (jj) tma_bulk_g2s(dst + SM::off_j(has_cs), w64g + (size_t)(l->o_j + k * SL::NJ) * 32, SL::NJ * SM::kLine, br);
             } else {
                 const int c = -(item + 1), i0 = c * SL::kPolyChunk;
@@ -1056,8 +1067,8 @@ __device__ __forceinline__ void stream_pass_fence() { asm volatile("fence.proxy.
 // instruction fetches and two warps per scheduler issue no more than one).  Every warp executes every pass with the same
 // trip counts, so a CTA-wide barrier in front of each pass keeps the warps of an SM on the same lines at almost no cost
 // (cta_tick, lbmpc_kernels.cuh: it also counts the warps that still have work, so that the CTA leaves together).
-// WARPS per CTA (one CTA per SM): 8 (255 registers per thread) or 12 (168 registers, some spills to L1-resident local memory,
-// three warps per scheduler to hide the fixed FP64 latencies) when the double buffers of 12 warps fit shared memory.
+// WARPS per CTA (one CTA per SM): 8 at 255 registers per thread, or 6 when the double buffers of 8 warps do not fit shared
+// memory (LTV Jacobians + shift record).  12 warps at 168 registers measured 1.5x slower (spills in pass BU).
 template <int NX, bool LTV, typename FT, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT> io, const double* __restrict__ G,
@@ -1067,7 +1078,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     extern __shared__ __align__(128) unsigned char stream_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    const bool has_cs = io.cshift != nullptr;
+    const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
     const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV);
     double* const w64 = io.ws64 + warp * (long long)l.n64 * 32 + lane;
     FT* const wft = io.wsft + warp * (long long)l.nft * 32 + lane;
@@ -1082,6 +1093,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     pp.pass = 0;
     pp.n_issue = pp.n_wait = 0;
     pp.has_cs = has_cs;
+    pp.rows = rsh;
     if (lane == 0) {
         mbar_init(pp.bar, 1);
         mbar_init(pp.bar + 1, 1);
@@ -1109,7 +1121,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
         bool working = !__all_sync(0xffffffffu, ln.q < 0);
         if (cta_tick(working) == 0) break;  // every warp of the CTA is out of work
         if (working) {
-            int st = S::pass_bu(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            int st = S::pass_bu(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             stream_pass_fence();
             if (ln.q >= 0) {
                 if (st < 0 && ln.iters >= p.max_iter) st = 1;
@@ -1122,7 +1134,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
         }
         __syncthreads();
         if (working) {
-            S::pass_f1(p, l, ln, G, hg, w64, wft, has_cs, pp);
+            S::pass_f1(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             stream_pass_fence();
         }
         __syncthreads();
@@ -1132,7 +1144,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
         }
         __syncthreads();
         if (working) {
-            S::pass_f2(p, l, ln, G, hg, w64, wft, pp);
+            S::pass_f2(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             stream_pass_fence();
             if (ln.q >= 0) {
                 ln.iters += 1;

@@ -105,10 +105,14 @@ def load_library(path=None):
     lib.lbmpc_solve_batch.restype = C.c_int
     lib.lbmpc_solve_batch_shifted.argtypes = [vp, C.c_int64] + [vp] * 11 + [vp]
     lib.lbmpc_solve_batch_shifted.restype = C.c_int
+    lib.lbmpc_solve_batch_shifted_xu.argtypes = [vp, C.c_int64] + [vp] * 11 + [vp]
+    lib.lbmpc_solve_batch_shifted_xu.restype = C.c_int
     lib.lbmpc_oracle_apply.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [vp]
     lib.lbmpc_oracle_apply.restype = C.c_int
     lib.lbmpc_solve_sqp.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
     lib.lbmpc_solve_sqp.restype = C.c_int
+    lib.lbmpc_solve_sqp_ex.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double] + [vp] * 13 + [vp]
+    lib.lbmpc_solve_sqp_ex.restype = C.c_int
     lib.lbmpc_closed_loop.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double,
                                       vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp]
     lib.lbmpc_closed_loop.restype = C.c_int
@@ -229,7 +233,8 @@ class Solver:
 
     # -- host-pointer API -----------------------------------------------------------------------
     def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, want_x=True, stream=None, out=None, cost_shift=None):
-        """lbmpc_solve_batch; with cost_shift (batch,N+1,nx) lbmpc_solve_batch_shifted: objective at x_k + cost_shift_k."""
+        """lbmpc_solve_batch; with cost_shift (batch,N+1,nx) lbmpc_solve_batch_shifted: objective at x_k + cost_shift_k;
+        with cost_shift (batch,N+1,nx+nu) lbmpc_solve_batch_shifted_xu: objective at [x_k + ex_k; u_k + eu_k]."""
         if self.device_pointers:
             return self._solve_device(dx0, dx_ref, d_off, warm, want_x, stream, out, cost_shift)
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
@@ -237,13 +242,14 @@ class Solver:
         nb = dx0.shape[0]
         c = lambda a, shp: None if a is None else np.ascontiguousarray(a, np.float64).reshape(shp)
         dx_ref, d_off, warm = c(dx_ref, (nb, nx)), c(d_off, (nb, N, nx)), c(warm, (nb, N * nu + nt))
-        cost_shift = c(cost_shift, (nb, N + 1, nx))
+        xu = cost_shift is not None and np.shape(cost_shift)[-1] == nx + nu
+        cost_shift = c(cost_shift, (nb, N + 1, nx + nu if xu else nx))
+        fn = self.lib.lbmpc_solve_batch_shifted_xu if xu else self.lib.lbmpc_solve_batch_shifted
         o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)),
                  xtraj=np.empty((nb, N + 1, nx)) if want_x else None, obj=np.empty(nb),
                  iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32))
-        rc = self.lib.lbmpc_solve_batch_shifted(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
-                                                _ptr(o["uc"]), _ptr(o["theta"]), _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]),
-                                                _ptr(o["status"]), None)
+        rc = fn(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
+                _ptr(o["uc"]), _ptr(o["theta"]), _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]), None)
         self._check(rc, "lbmpc_solve_batch")
         return o
 
@@ -261,7 +267,13 @@ class Solver:
                        iters=torch.empty(nb, dtype=torch.int32, device=dev),
                        status=torch.empty(nb, dtype=torch.int32, device=dev))
         st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
-        rc = self.lib.lbmpc_solve_batch_shifted(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
+        for name, t in (("dx0", dx0), ("dx_ref", dx_ref), ("d_off", d_off), ("warm", warm), ("cost_shift", cost_shift)):
+            if t is not None and (t.dtype != torch.float64 or not t.is_contiguous() or t.device != dev or not t.is_cuda):
+                raise LbmpcError(f"{name}: device-pointer mode takes contiguous float64 CUDA tensors on one device "
+                                 f"(got {t.dtype}, contiguous={t.is_contiguous()}, {t.device})")
+        xu = cost_shift is not None and cost_shift.shape[-1] == nx + nu
+        fn = self.lib.lbmpc_solve_batch_shifted_xu if xu else self.lib.lbmpc_solve_batch_shifted
+        rc = fn(self.h, nb, _ptr(dx0), _ptr(dx_ref), _ptr(d_off), _ptr(cost_shift), _ptr(warm),
                                                 _ptr(out["uc"]), _ptr(out["theta"]), _ptr(out.get("xtraj")), _ptr(out["obj"]),
                                                 _ptr(out["iters"]), _ptr(out["status"]), C.c_void_p(st))
         self._check(rc, "lbmpc_solve_batch")
@@ -293,10 +305,11 @@ class Solver:
         return d
 
     def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, want_x=True,
-                  twin=False):
+                  twin=False, order=0):
         """Learned-oracle problem as a sequence of QPs (lbmpc_solve_sqp): X (batch,q,3), Y (batch,q,nx) data windows.
         Host arrays.  twin: cost on the learned state sequence, rows on the nominal one (DMS_LBMPC_casadi.m).  Returns the last
-        QP's solution plus du_step (batch, sqp_iters)."""
+        QP's solution plus du_step (batch, sqp_iters).  order=1: oracle value AND Jacobian per outer iteration (LTV QP on the
+        learned sequence, lbmpc_solve_sqp_ex)."""
         if self.device_pointers:
             raise LbmpcError("solve_sqp is exposed for host-pointer handles")
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
@@ -309,10 +322,10 @@ class Solver:
         o = dict(uc=np.empty((nb, N, nu)), theta=np.empty((nb, nt)), xtraj=np.empty((nb, N + 1, nx)) if want_x else None,
                  obj=np.empty(nb), iters=np.empty(nb, np.int32), status=np.empty(nb, np.int32),
                  du_step=np.empty((nb, sqp_iters)))
-        rc = self.lib.lbmpc_solve_sqp(self.h, nb, int(sqp_iters), int(bool(twin)), int(q), float(bandwidth), float(lam), _ptr(dx0), _ptr(dx_ref),
-                                      _ptr(X), _ptr(Y), _ptr(valid), _ptr(warm), _ptr(o["uc"]), _ptr(o["theta"]),
-                                      _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]),
-                                      _ptr(o["du_step"]), None)
+        rc = self.lib.lbmpc_solve_sqp_ex(self.h, nb, int(sqp_iters), int(bool(twin)), int(order), int(q), float(bandwidth), float(lam),
+                                         _ptr(dx0), _ptr(dx_ref), _ptr(X), _ptr(Y), _ptr(valid), _ptr(warm), _ptr(o["uc"]),
+                                         _ptr(o["theta"]), _ptr(o["xtraj"]), _ptr(o["obj"]), _ptr(o["iters"]), _ptr(o["status"]),
+                                         _ptr(o["du_step"]), None)
         self._check(rc, "lbmpc_solve_sqp")
         return o
 

@@ -9,9 +9,13 @@ function [sysHistory,art_refHistory,true_refHistory]...
 % batched interior-point solve on the GPU (batch = 1 here) through lbmpc_mex -> liblbmpc_b200.so.
 % `options` (fmincon options) is accepted and ignored.
 %
-% The learned-oracle term of costLBMPC.m:27 is non-convex in the reference; here it enters as the
-% frozen per-stage offset d_k = g(x_k,u_k;data) evaluated along the previous solution
-% (lbmpc_mex('oracle',...)), i.e. one SQP/RTI linearisation per control step (DESIGN.md, H2).
+% The reference's problem is stated as the reference states it: costLBMPC.m:27 rolls the LEARNED model
+% (transitionLearned.m:13-14: u = K x + c on the learned state, x+ = A x + B u + g(x,u;data)) while
+% constraintsLBMPC.m:23 rolls the NOMINAL model, so the oracle moves the cost only and the X, U, X(-)D
+% and terminal rows stay on the nominal prediction.  The non-convex oracle term is frozen along the
+% previous solution and re-evaluated `sqp_iters` times per control step (lbmpc_solve_sqp with twin = 1:
+% the gap between the two state sequences obeys e+ = (A + B K) e + g_k, the input gap is K e, and both
+% enter the QP as a cost shift).  With data = 0 (first step) this is the exact QP of the reference.
 model = struct('A',A,'B',B,'K',Kstabil,'Q',Q,'R',R,'P',P,'T',T,'LAMBDA',LAMBDA,'PSI',PSI, ...
                'F_x',F_x,'h_x',h_x,'F_u',F_u,'h_u',h_u,'F_w_N',F_w_N,'h_w_N',h_w_N, ...
                'F_x_d',F_x_d,'h_x_d',h_x_d);
@@ -19,6 +23,7 @@ cfg = struct('form','F','variant','LBMPC','N',N,'max_batch',1);
 h = lbmpc_mex('create', model, cfg);
 cleaner = onCleanup(@() lbmpc_mex('destroy', h));
 q = 100;                                   % moving window (ocpLBMPC.m:18)
+sqp_iters = 2;                             % re-linearisations of the oracle per control step
 for k = 1:iterations
     if k > 1
         X = [x(1:2)-x_wp(1:2); u-u_wp];                        % ocpLBMPC.m:14
@@ -29,18 +34,8 @@ for k = 1:iterations
     else
         dx = dx_init;
     end
-    d_off = [];
-    if size(data.X,2) > 1 || any(data.Y(:) ~= 0)
-        % inputs of the previous solution along the pre-stabilised rollout: du_k = K dx_k + c_k
-        c_prev = reshape(opt_var(1:end-m), m, N);
-        du = zeros(m*N,1); xk = dx;
-        for kk = 1:N
-            du((kk-1)*m+(1:m)) = Kstabil*xk + c_prev(:,kk);
-            xk = A*xk + B*du((kk-1)*m+(1:m));
-        end
-        d_off = lbmpc_mex('oracle', h, size(data.X,2), 0.5, 0.001, dx, du, data.X, data.Y, []);
-    end
-    out = lbmpc_mex('solve', h, dx, dx_ref, d_off, opt_var(:));    % replaces fmincon, ocpLBMPC.m:31
+    % replaces fmincon(COSTFUN,opt_var,...,CONSFUN,options), ocpLBMPC.m:27-31
+    out = lbmpc_mex('solve_sqp', h, sqp_iters, size(data.X,2), 0.5, 0.001, dx, dx_ref, data.X, data.Y, [], opt_var(:), 1);
     if out.status ~= 0
         warning('lbmpc:status', 'step %d: solver status %d', k, out.status);
     end

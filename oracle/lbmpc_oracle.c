@@ -354,7 +354,12 @@ typedef struct {
     double P0tt_inv[MAXNT * MAXNT];
     double *dx, *du, dth[MAXNT];
     double lin[MAXNZ], cconst;
-    const double *csh;                       /* (N+1)*nx or NULL: the cost is evaluated at x_k + csh_k (twin sequences) */
+    const double *csh;                       /* (N+1)*cs_stride or NULL: the cost is evaluated at [x_k + ex_k; u_k + eu_k] (twin sequences) */
+    int cs_stride;                           /* nx: state shift only; nx+nu: [ex_k | eu_k] */
+    int row_shift;                           /* 0: the shift moves the COST; 1: it moves the ROWS (rows act on x_k - ex_k, u_k - eu_k:
+                                                first-order SQP on the learned sequence, the rows follow the nominal one) */
+    const double *jac;                       /* N*nx*3 or NULL: per-stage Jacobian J_k of the learned term w.r.t. [x1;x2;u]:
+                                                A_k = A + [J(:,1:2) 0 0], B_k = B + J(:,3) (LTV dynamics) */
     double flops;
 } lbo_ws;
 
@@ -391,9 +396,17 @@ static inline double dvar_at(const lbo_problem *p, const lbo_ws *w, int k, int j
     return j < p->nx ? w->dx[k * p->nx + j] : w->du[k * p->nu + (j - p->nx)];
 }
 /* slack of a box row at the current iterate: upper hi - v, lower v - lo */
+static inline double row_shift_at(const lbo_problem *p, const lbo_ws *w, int k, int j);
 static inline double box_slack(const lbo_problem *p, const lbo_ws *w, int k, int j, int side) {
-    double v = var_at(p, w, k, j);
+    double v = var_at(p, w, k, j) - row_shift_at(p, w, k, j);
     return side == 0 ? p->hi[j] - v : v - p->lo[j];
+}
+static double gen_dot(const lbo_problem *p, int i, const double *xk, const double *th);
+/* slack of polytope row i at the current iterate (rows follow x_kg - ex_kg when the shift moves the rows) */
+static double gen_slack_ws(const lbo_problem *p, const lbo_ws *w, int i) {
+    double xs[MAXNX];
+    for (int j = 0; j < p->nx; ++j) xs[j] = w->x[(size_t)p->kg * p->nx + j] - row_shift_at(p, w, p->kg, j);
+    return p->hg[i] - gen_dot(p, i, xs, w->th);
 }
 static double gen_dot(const lbo_problem *p, int i, const double *xk, const double *th) {
     const double *g = p->G + (size_t)i * p->nz;
@@ -401,6 +414,30 @@ static double gen_dot(const lbo_problem *p, int i, const double *xk, const doubl
     for (int j = 0; j < p->nx; ++j) v += g[j] * xk[j];
     for (int j = 0; j < p->nt; ++j) v += g[p->nx + j] * th[j];
     return v;
+}
+
+/* dynamics of stage k: LTI (p->A, p->B) or LTV with the oracle Jacobian (nu = 1, nx >= 2) */
+static void stage_ab(const lbo_problem *p, const lbo_ws *w, int k, double *Ak, double *Bk, double *Abar, double *Bbar) {
+    const int nx = p->nx, nu = p->nu, nz = p->nz;
+    for (int a = 0; a < nx; ++a) {
+        for (int b = 0; b < nx; ++b) Ak[a * nx + b] = p->A[a * nx + b] + ((w->jac && b < 2) ? w->jac[((size_t)k * nx + a) * 3 + b] : 0.0);
+        for (int i = 0; i < nu; ++i) Bk[a * nu + i] = p->B[a * nu + i] + ((w->jac && i == 0) ? w->jac[((size_t)k * nx + a) * 3 + 2] : 0.0);
+    }
+    if (Abar) {
+        memset(Abar, 0, sizeof(double) * nz * nz);
+        memset(Bbar, 0, sizeof(double) * nz * nu);
+        for (int a = 0; a < nx; ++a) {
+            for (int b = 0; b < nx; ++b) Abar[a * nz + b] = Ak[a * nx + b];
+            for (int i = 0; i < nu; ++i) Bbar[a * nu + i] = Bk[a * nu + i];
+        }
+        for (int a = nx; a < nz; ++a) Abar[a * nz + a] = 1.0;
+    }
+}
+/* shift of bounded variable j at stage k when the shift moves the rows */
+static inline double row_shift_at(const lbo_problem *p, const lbo_ws *w, int k, int j) {
+    if (!w->csh || !w->row_shift) return 0.0;
+    if (j < p->nx) return w->csh[k * w->cs_stride + j];
+    return (w->cs_stride > p->nx && k < p->N) ? w->csh[k * w->cs_stride + j] : 0.0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -416,9 +453,11 @@ static void assemble(const lbo_problem *p, lbo_ws *w, int corr, double sigmu, do
         for (int k = 0; k <= N; ++k) {
             const double *W = p->W[p->wtype[k]];
             double v[MAXNV];
-            for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (w->csh ? w->csh[k * nx + j] : 0.0);
+            const int cshift = w->csh && !w->row_shift;
+            for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (cshift ? w->csh[k * w->cs_stride + j] : 0.0);
             for (int j = 0; j < p->nt; ++j) v[nx + j] = w->th[j];
-            for (int j = 0; j < nu; ++j) v[nz + j] = (k < N) ? w->u[k * nu + j] : 0.0;
+            for (int j = 0; j < nu; ++j)
+                v[nz + j] = (k < N) ? w->u[k * nu + j] + ((cshift && w->cs_stride > nx) ? w->csh[k * w->cs_stride + nx + j] : 0.0) : 0.0;
             int lim = (k < N) ? nv : nz;
             for (int a = 0; a < nv; ++a) {
                 double g = 0.0;
@@ -464,13 +503,12 @@ static void assemble(const lbo_problem *p, lbo_ws *w, int corr, double sigmu, do
             }
             w->dgp[k * nvb + j] = gp - gl;
         }
-    const double *xg = w->x + (size_t)p->kg * nx;
     for (int i = 0; i < p->ng; ++i) {
         const double *g = p->G + (size_t)i * nz;
         const double s = w->sg[i], l = w->lg[i];
         double t;
         if (!corr) {
-            const double slack = p->hg[i] - gen_dot(p, i, xg, w->th);
+            const double slack = gen_slack_ws(p, w, i);
             const double rp = s - slack;
             w->rpg[i] = rp;
             if (fabs(rp) > rpi) rpi = fabs(rp);
@@ -523,37 +561,39 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
     for (int k = N - 1; k >= 0; --k) {
         const double *W = p->W[p->wtype[k]];
         double *L = w->L + (size_t)k * nu * nz, *Ri = w->Ri + (size_t)k * nu * nu;
+        double Ak_[MAXNX * MAXNX], Bk_[MAXNX * MAXNU], Abar_k[MAXNZ * MAXNZ], Bbar_k[MAXNZ * MAXNU];
+        stage_ab(p, w, k, Ak_, Bk_, Abar_k, Bbar_k);
         if (factor) {
             double M[MAXNZ * MAXNZ], F[MAXNZ * MAXNZ], Rt[MAXNU * MAXNU], PB[MAXNZ * MAXNU];
             for (int a = 0; a < nz; ++a)
                 for (int b = 0; b < nz; ++b) {
                     double v = 0.0;
-                    for (int c = 0; c < nz; ++c) v += P[a * nz + c] * p->Abar[c * nz + b];
+                    for (int c = 0; c < nz; ++c) v += P[a * nz + c] * Abar_k[c * nz + b];
                     M[a * nz + b] = v;
                 }
             for (int a = 0; a < nz; ++a)
                 for (int b = 0; b < nz; ++b) {
                     double v = 0.0;
-                    for (int c = 0; c < nz; ++c) v += p->Abar[c * nz + a] * M[c * nz + b];
+                    for (int c = 0; c < nz; ++c) v += Abar_k[c * nz + a] * M[c * nz + b];
                     F[a * nz + b] = v;
                 }
             for (int i = 0; i < nu; ++i)
                 for (int b = 0; b < nz; ++b) {
                     double v = W[(nz + i) * nv + b];
-                    for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * M[c * nz + b];
+                    for (int c = 0; c < nz; ++c) v += Bbar_k[c * nu + i] * M[c * nz + b];
                     L[i * nz + b] = v;
                 }
             for (int a = 0; a < nz; ++a)
                 for (int i = 0; i < nu; ++i) {
                     double v = 0.0;
-                    for (int c = 0; c < nz; ++c) v += P[a * nz + c] * p->Bbar[c * nu + i];
+                    for (int c = 0; c < nz; ++c) v += P[a * nz + c] * Bbar_k[c * nu + i];
                     PB[a * nu + i] = v;
                 }
             for (int i = 0; i < nu; ++i)
                 for (int j = 0; j < nu; ++j) {
                     double v = W[(nz + i) * nv + nz + j];
                     if (i == j) v += w->Qd[k * nvb + nx + i];
-                    for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * PB[c * nu + j];
+                    for (int c = 0; c < nz; ++c) v += Bbar_k[c * nu + i] * PB[c * nu + j];
                     Rt[i * nu + j] = v;
                 }
             if (spd_inv(nu, Rt, Ri)) return 1;
@@ -579,7 +619,7 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
         double rt[MAXNU], kap[MAXNU], Atp[MAXNZ];
         for (int i = 0; i < nu; ++i) {
             double v = w->gres[k * nv + nz + i] + w->dgp[k * nvb + nx + i];
-            for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * pv[c];
+            for (int c = 0; c < nz; ++c) v += Bbar_k[c * nu + i] * pv[c];
             rt[i] = v;
         }
         for (int i = 0; i < nu; ++i) {
@@ -590,7 +630,7 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
         }
         for (int a = 0; a < nz; ++a) {
             double v = 0.0;
-            for (int c = 0; c < nz; ++c) v += p->Abar[c * nz + a] * pv[c];
+            for (int c = 0; c < nz; ++c) v += Abar_k[c * nz + a] * pv[c];
             Atp[a] = v;
         }
         for (int a = 0; a < nz; ++a) {
@@ -605,13 +645,13 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
             double npi[MAXNZ];
             for (int i = 0; i < nu; ++i) {
                 double v = w->gres[k * nv + nz + i];
-                for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * pi[c];
+                for (int c = 0; c < nz; ++c) v += Bbar_k[c * nu + i] * pi[c];
                 if (fabs(v) > rdi) rdi = fabs(v);
                 if (v != v) rdi = NAN;
             }
             for (int a = 0; a < nz; ++a) {
                 double v = w->gres[k * nv + a];
-                for (int c = 0; c < nz; ++c) v += p->Abar[c * nz + a] * pi[c];
+                for (int c = 0; c < nz; ++c) v += Abar_k[c * nz + a] * pi[c];
                 npi[a] = v;
             }
             memcpy(pi, npi, sizeof(double) * nz);
@@ -621,13 +661,13 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
             if (cert) {
                 for (int i = 0; i < nu; ++i) {
                     double v = w->gcon[k * nv + nz + i];
-                    for (int c = 0; c < nz; ++c) v += p->Bbar[c * nu + i] * pc[c];
+                    for (int c = 0; c < nz; ++c) v += Bbar_k[c * nu + i] * pc[c];
                     ci += fabs(v) * ((k >= p->ku0 && k <= p->ku1) ? p->fk_u[i] : p->fk_free);
                     ydot += v * w->u[k * nu + i];
                 }
                 for (int a = 0; a < nz; ++a) {
                     double v = w->gcon[k * nv + a];
-                    for (int c = 0; c < nz; ++c) v += p->Abar[c * nz + a] * pc[c];
+                    for (int c = 0; c < nz; ++c) v += Abar_k[c * nz + a] * pc[c];
                     npi[a] = v;
                 }
                 memcpy(pc, npi, sizeof(double) * nz);
@@ -677,10 +717,12 @@ static void forward(const lbo_problem *p, lbo_ws *w) {
             for (int j = 0; j < nu; ++j) v -= Ri[i * nu + j] * Lz[j];
             w->du[k * nu + i] = v;
         }
+        double Ak_[MAXNX * MAXNX], Bk_[MAXNX * MAXNU];
+        stage_ab(p, w, k, Ak_, Bk_, NULL, NULL);
         for (int a = 0; a < nx; ++a) {
             double v = 0.0;
-            for (int c = 0; c < nx; ++c) v += p->A[a * nx + c] * w->dx[k * nx + c];
-            for (int i = 0; i < nu; ++i) v += p->B[a * nu + i] * w->du[k * nu + i];
+            for (int c = 0; c < nx; ++c) v += Ak_[a * nx + c] * w->dx[k * nx + c];
+            for (int i = 0; i < nu; ++i) v += Bk_[a * nu + i] * w->du[k * nu + i];
             w->dx[(k + 1) * nx + a] = v;
         }
         w->flops += 2.0 * nu * nz + 2.0 * nu * nu + 2.0 * nx * (nx + nu);
@@ -744,10 +786,12 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
             for (int j = 0; j < nx; ++j) v += p->Kinit[i * nx + j] * w->x[k * nx + j];
             w->u[k * nu + i] = v;
         }
+        double Ak_[MAXNX * MAXNX], Bk_[MAXNX * MAXNU];
+        stage_ab(p, w, k, Ak_, Bk_, NULL, NULL);
         for (int a = 0; a < nx; ++a) {
             double v = d_off ? d_off[k * nx + a] : 0.0;
-            for (int j = 0; j < nx; ++j) v += p->A[a * nx + j] * w->x[k * nx + j];
-            for (int i = 0; i < nu; ++i) v += p->B[a * nu + i] * w->u[k * nu + i];
+            for (int j = 0; j < nx; ++j) v += Ak_[a * nx + j] * w->x[k * nx + j];
+            for (int i = 0; i < nu; ++i) v += Bk_[a * nu + i] * w->u[k * nu + i];
             w->x[(k + 1) * nx + a] = v;
         }
     }
@@ -769,7 +813,7 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
                 w->lb[r] = 1.0;
             }
     for (int i = 0; i < p->ng; ++i) {
-        const double slack = p->hg[i] - gen_dot(p, i, w->x + (size_t)p->kg * nx, w->th);
+        const double slack = gen_slack_ws(p, w, i);
         w->sg[i] = slack > 1.0 ? slack : 1.0;
         w->lg[i] = 1.0;
     }
@@ -821,9 +865,11 @@ static int solve_ws(const lbo_problem *p, lbo_ws *w, const double *dx0, const do
     for (int k = 0; k <= N; ++k) {
         const double *W = p->W[p->wtype[k]];
         double v[MAXNV];
-        for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (w->csh ? w->csh[k * nx + j] : 0.0);
+        const int cshift = w->csh && !w->row_shift;
+        for (int j = 0; j < nx; ++j) v[j] = w->x[k * nx + j] + (cshift ? w->csh[k * w->cs_stride + j] : 0.0);
         for (int j = 0; j < nt; ++j) v[nx + j] = w->th[j];
-        for (int j = 0; j < nu; ++j) v[nz + j] = (k < N) ? w->u[k * nu + j] : 0.0;
+        for (int j = 0; j < nu; ++j)
+            v[nz + j] = (k < N) ? w->u[k * nu + j] + ((cshift && w->cs_stride > nx) ? w->csh[k * w->cs_stride + nx + j] : 0.0) : 0.0;
         int lim = (k < N) ? nv : nz;
         for (int a = 0; a < lim; ++a)
             for (int b = 0; b < lim; ++b) J += 0.5 * v[a] * W[a * nv + b] * v[b];
@@ -857,6 +903,7 @@ int lbo_solve_shifted(const lbo_problem *p, const double *dx0, const double *dx_
                       double *obj, int *iters, int *status, double *stats) {
     lbo_ws *w = ws_alloc(p);
     w->csh = cost_shift;
+    w->cs_stride = p->nx;
     int rc = solve_ws(p, w, dx0, dx_ref, d_off, warm, uc, theta, xtraj, obj, iters, status, stats);
     ws_free(w);
     return rc;
@@ -864,7 +911,8 @@ int lbo_solve_shifted(const lbo_problem *p, const double *dx0, const double *dx_
 
 typedef struct {
     const lbo_problem *p; long batch; const double *dx0, *dx_ref, *d_off, *warm, *csh;
-    double *uc, *theta, *xtraj, *obj; int *iters, *status; long *next;
+    double *uc, *theta, *xtraj, *obj; int *iters, *status; long *next; int cs_stride;
+    int row_shift; const double *jac;
 } lbo_batch_job;
 
 static void *batch_worker(void *arg) {
@@ -877,7 +925,10 @@ static void *batch_worker(void *arg) {
         if (b0 >= j->batch) break;
         long b1 = b0 + 4 < j->batch ? b0 + 4 : j->batch;
         for (long b = b0; b < b1; ++b) {
-            w->csh = j->csh ? j->csh + b * (long)(N + 1) * nx : NULL;
+            w->csh = j->csh ? j->csh + b * (long)(N + 1) * j->cs_stride : NULL;
+            w->cs_stride = j->cs_stride;
+            w->row_shift = j->row_shift;
+            w->jac = j->jac ? j->jac + b * (long)N * nx * 3 : NULL;
             solve_ws(p, w, j->dx0 + b * nx, j->dx_ref ? j->dx_ref + b * nx : NULL,
                       j->d_off ? j->d_off + b * (long)nx * N : NULL,
                       j->warm ? j->warm + b * (long)(N * nu + nt) : NULL, j->uc + b * (long)N * nu,
@@ -899,8 +950,23 @@ int lbo_solve_batch(const lbo_problem *p, long batch, const double *dx0, const d
 int lbo_solve_batch_shifted(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
                             const double *d_off, const double *cost_shift, const double *warm, double *uc,
                             double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads) {
+    return lbo_solve_batch_shifted_xu(p, batch, dx0, dx_ref, d_off, cost_shift, p->nx, warm, uc, theta, xtraj, obj, iters, status, nthreads);
+}
+
+int lbo_solve_batch_shifted_xu(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                               const double *d_off, const double *cost_shift, int cs_stride, const double *warm, double *uc,
+                               double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads) {
+    return lbo_solve_batch_ex(p, batch, dx0, dx_ref, d_off, cost_shift, cs_stride, 0, NULL, warm, uc, theta, xtraj, obj, iters, status, nthreads);
+}
+
+int lbo_solve_batch_ex(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                       const double *d_off, const double *shift, int cs_stride, int row_shift, const double *jac,
+                       const double *warm, double *uc, double *theta, double *xtraj, double *obj, int *iters, int *status,
+                       int nthreads) {
     long next = 0;
-    lbo_batch_job job = {p, batch, dx0, dx_ref, d_off, warm, cost_shift, uc, theta, xtraj, obj, iters, status, &next};
+    lbo_batch_job job = {p, batch, dx0, dx_ref, d_off, warm, shift, uc, theta, xtraj, obj, iters, status, &next, cs_stride,
+                         row_shift, jac};
+    if (jac && (p->nu != 1 || p->nx < 2)) { snprintf(g_err, sizeof g_err, "LTV Jacobians: nu = 1 and nx >= 2 (xi = [x1;x2;u])"); return -1; }
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     pthread_t th[256];
@@ -950,6 +1016,57 @@ void lbo_plant_rk4(const double *x, double u, double delta, double *xn) { /* …
     for (int i = 0; i < 4; ++i) xn[i] = x[i] + delta / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
 }
 
+/* g(xi) and its Jacobian dg/dxi (nout x nin, row-major) of the L2NW oracle:
+ *   k_i = exp(-|X_i - xi|^2 / h^2), D = lambda + sum_i v_i k_i, g = sum_i Y_i k_i / D
+ *   dk_i/dxi = k_i 2 (X_i - xi) / h^2 ;  dg/dxi = (sum_i Y_i dk_i - g sum_i v_i dk_i) / D
+ * (what CasADi's algorithmic differentiation of casadiL2NW.m:14-28 evaluates inside IPOPT) */
+void lbo_oracle_l2nw_jac(const double *X, const double *Y, const double *valid, int q, int nin, int nout,
+                         const double *xi, double bandwidth, double lambda, double *g, double *J) {
+    const double ih2 = 1.0 / (bandwidth * bandwidth);
+    double D = lambda, num[8] = {0}, dnum[8][4] = {{0}}, dD[4] = {0};
+    for (int i = 0; i < q; ++i) {
+        double d2 = 0.0, dxv[4];
+        for (int c = 0; c < nin; ++c) { dxv[c] = X[c * q + i] - xi[c]; d2 += dxv[c] * dxv[c]; }
+        const double k = exp(-d2 * ih2), vi = valid ? valid[i] : 1.0;
+        D += vi * k;
+        for (int c = 0; c < nin; ++c) dD[c] += vi * k * 2.0 * dxv[c] * ih2;
+        for (int a = 0; a < nout; ++a) {
+            num[a] += Y[a * q + i] * k;
+            for (int c = 0; c < nin; ++c) dnum[a][c] += Y[a * q + i] * k * 2.0 * dxv[c] * ih2;
+        }
+    }
+    for (int a = 0; a < nout; ++a) {
+        g[a] = num[a] / D;
+        for (int c = 0; c < nin; ++c) J[a * nin + c] = (dnum[a][c] - g[a] * dD[c]) / D;
+    }
+}
+
+/* Oracle offsets AND Jacobians along the learned-model rollout of the sequence du from dx0 (see lbo_oracle_offsets):
+ * first-order model of the learned dynamics around the rollout (xbar_k, ubar_k):
+ *   x+ = (A + [J_k(:,1:2) 0 0]) x + (B + J_k(:,3)) u + d_k ,   d_k = g(xibar_k) - J_k xibar_k */
+void lbo_oracle_offsets_jac(const lbo_problem *p, const double *dx0, const double *du,
+                            const double *X, const double *Y, const double *valid, int q,
+                            double bandwidth, double lambda, double *d_off, double *jac, double *g_out) {
+    const int nx = p->nx, nu = p->nu, N = p->N;
+    double x[MAXNX], xn[MAXNX];
+    memcpy(x, dx0, sizeof(double) * nx);
+    for (int k = 0; k < N; ++k) {
+        double u0 = du[k * nu];
+        for (int j = 0; j < nx; ++j) u0 += p->Kinit[j] * x[j];
+        double xi[3] = {x[0], x[1], u0}, g[MAXNX], *J = jac + (size_t)k * nx * 3;
+        lbo_oracle_l2nw_jac(X, Y, valid, q, 3, nx, xi, bandwidth, lambda, g, J);
+        for (int a = 0; a < nx; ++a) {
+            if (g_out) g_out[k * nx + a] = g[a];
+            d_off[k * nx + a] = g[a] - (J[a * 3] * xi[0] + J[a * 3 + 1] * xi[1] + J[a * 3 + 2] * xi[2]);
+            double v = g[a];
+            for (int j = 0; j < nx; ++j) v += p->A[a * nx + j] * x[j];
+            v += p->B[a * nu] * u0;
+            xn[a] = v;
+        }
+        memcpy(x, xn, sizeof(double) * nx);
+    }
+}
+
 void lbo_oracle_offsets(const lbo_problem *p, const double *dx0, const double *du,
                         const double *X, const double *Y, const double *valid, int q,
                         double bandwidth, double lambda, double *d_off) {
@@ -957,12 +1074,15 @@ void lbo_oracle_offsets(const lbo_problem *p, const double *dx0, const double *d
     double x[MAXNX], xn[MAXNX];
     memcpy(x, dx0, sizeof(double) * nx);
     for (int k = 0; k < N; ++k) {
-        double xi[3] = {x[0], x[1], du[k * nu]};
+        /* F-form: the sequence holds c and u = K x + c on the learned state (transitionLearned.m:13); Kinit = 0 in the C-form */
+        double u0 = du[k * nu];
+        for (int j = 0; j < nx; ++j) u0 += p->Kinit[j] * x[j];
+        double xi[3] = {x[0], x[1], u0};
         lbo_oracle_l2nw(X, Y, valid, q, 3, nx, xi, bandwidth, lambda, d_off + (size_t)k * nx);
         for (int a = 0; a < nx; ++a) {
             double v = d_off[k * nx + a];
             for (int j = 0; j < nx; ++j) v += p->A[a * nx + j] * x[j];
-            for (int i = 0; i < nu; ++i) v += p->B[a * nu + i] * du[k * nu + i];
+            v += p->B[a * nu] * u0;
             xn[a] = v;
         }
         memcpy(x, xn, sizeof(double) * nx);

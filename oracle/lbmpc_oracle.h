@@ -106,6 +106,32 @@ int lbo_solve_batch_shifted(const lbo_problem *p, long batch, const double *dx0,
                             const double *d_off, const double *cost_shift, const double *warm, double *uc,
                             double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads);
 
+/* Same with a state AND input shift: cost_shift holds (N+1) records of cs_stride doubles, [ex_k (nx) | eu_k (nu)] when
+ * cs_stride = nx+nu; the objective is evaluated at [x_k + ex_k; theta; u_k + eu_k].  F-form LBMPC (costLBMPC.m:27 learned
+ * rollout with u = K x + c, constraintsLBMPC.m:23 nominal rollout): e_{k+1} = (A + B K) e_k + d_k, eu_k = K e_k. */
+int lbo_solve_batch_shifted_xu(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                               const double *d_off, const double *cost_shift, int cs_stride, const double *warm, double *uc,
+                               double *theta, double *xtraj, double *obj, int *iters, int *status, int nthreads);
+
+/* General form: `shift` ((N+1) records of cs_stride doubles, or NULL) moves the COST (row_shift = 0, as above) or the ROWS
+ * (row_shift = 1: every box / polytope row acts on x_k - ex_k, u_k - eu_k while cost and dynamics act on x_k, u_k);
+ * jac (N*nx*3 per QP, or NULL): per-stage Jacobians J_k of the learned term w.r.t. xi = [x1;x2;u] -> LTV dynamics
+ * A_k = A + [J_k(:,1:2) 0 0], B_k = B + J_k(:,3).  Together they state one first-order SQP step of the learned-oracle problem
+ * on the LEARNED state sequence (costLBMPC.m:27 / DMS_LBMPC_casadi.m:252-268), the rows following the NOMINAL sequence
+ * (constraintsLBMPC.m:23 / DMS_LBMPC_casadi.m:283-319) at the distance e_k frozen from the previous outer iteration. */
+int lbo_solve_batch_ex(const lbo_problem *p, long batch, const double *dx0, const double *dx_ref,
+                       const double *d_off, const double *shift, int cs_stride, int row_shift, const double *jac,
+                       const double *warm, double *uc, double *theta, double *xtraj, double *obj, int *iters, int *status,
+                       int nthreads);
+
+/* L2NW oracle value and Jacobian dg/dxi (nout x nin row-major); X nin*q, Y nout*q row-major as in lbo_oracle_l2nw */
+void lbo_oracle_l2nw_jac(const double *X, const double *Y, const double *valid, int q, int nin, int nout,
+                         const double *xi, double bandwidth, double lambda, double *g, double *J);
+/* offsets d_k = g(xibar_k) - J_k xibar_k, Jacobians J_k (N*nx*3) and optionally g(xibar_k) along the learned rollout */
+void lbo_oracle_offsets_jac(const lbo_problem *p, const double *dx0, const double *du,
+                            const double *X, const double *Y, const double *valid, int q,
+                            double bandwidth, double lambda, double *d_off, double *jac, double *g_out);
+
 /* Nadaraya-Watson oracle g(xi), xi=[dx1;dx2;du]  (oracleL2NW.m:26-36).  X 3*q, Y 4*q row-major
  * ([i][j] = component i of sample j), valid q or NULL (mask variant casadiL2NW.m:18-21). */
 void lbo_oracle_l2nw(const double *X, const double *Y, const double *valid, int q, int nin,
@@ -114,8 +140,9 @@ void lbo_oracle_l2nw(const double *X, const double *Y, const double *valid, int 
 /* Moore-Greitzer plant, one RK4 step of length delta (DMS_tracking_LMPC_casadi.m:297-304). */
 void lbo_plant_rk4(const double *x, double u, double delta, double *xnext);
 
-/* Frozen-affine oracle offsets along a nominal rollout with input sequence du (N) from dx0:
- * d_k = g([dx_k(1:2); du_k]) with dx_{k+1} = A dx_k + B du_k + d_k. */
+/* Frozen-affine oracle offsets along the learned-model rollout of the sequence du (N) from dx0:
+ * d_k = g([dx_k(1:2); u_k]) with dx_{k+1} = A dx_k + B u_k + d_k, u_k = du_k (C-form) or K dx_k + du_k (F-form: du holds c,
+ * transitionLearned.m:13-14). */
 void lbo_oracle_offsets(const lbo_problem *p, const double *dx0, const double *du,
                         const double *X, const double *Y, const double *valid, int q,
                         double bandwidth, double lambda, double *d_off);

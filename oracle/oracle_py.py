@@ -118,25 +118,36 @@ class OracleProblem:
                                cost_shift=None if cost_shift is None else np.asarray(cost_shift, float).reshape(1, self.N + 1, self.nx))
         return {k: v[0] for k, v in out.items()}
 
-    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, nthreads=1, stats=False, cost_shift=None):
-        """dx0 (batch,nx); d_off (batch,N,nx); warm (batch,N*nu+nt); cost_shift (batch,N+1,nx): the objective is evaluated at
-        x_k + cost_shift_k (lbo_solve_shifted).  Returns dict of arrays."""
+    def solve_batch(self, dx0, dx_ref=None, d_off=None, warm=None, nthreads=1, stats=False, cost_shift=None, row_shift=None,
+                    jac=None):
+        """dx0 (batch,nx); d_off (batch,N,nx); warm (batch,N*nu+nt); cost_shift (batch,N+1,nx or nx+nu): the objective is
+        evaluated at [x_k + ex_k; u_k + eu_k]; row_shift (same shape): the ROWS act on x_k - ex_k, u_k - eu_k instead; jac
+        (batch,N,nx,3): LTV dynamics A_k = A + [J 0 0], B_k = B + J(:,3) (lbo_solve_batch_ex).  Returns dict of arrays."""
+        assert cost_shift is None or row_shift is None
+        rows = row_shift is not None
+        if rows:
+            cost_shift = row_shift
+        jac = _d(jac)
         L = lib()
         dx0 = _d(dx0)
         nb = dx0.shape[0]
         nx, nu, nt, N = self.nx, self.nu, self.nt, self.N
         dx_ref, d_off, warm, cost_shift = _d(dx_ref), _d(d_off), _d(warm), _d(cost_shift)
+        cs_stride = nx if cost_shift is None else int(cost_shift.shape[-1])      # nx: state shift; nx+nu: [ex | eu]
         uc = np.empty((nb, N, nu)); th = np.empty((nb, nt)); xt = np.empty((nb, N + 1, nx)); obj = np.empty(nb)
         it = np.empty(nb, np.int32); st = np.empty(nb, np.int32)
         out = dict(uc=uc, theta=th, xtraj=xt, obj=obj, iters=it, status=st)
-        if stats and nb == 1:
+        if stats and nb == 1 and cs_stride == nx and not rows and jac is None:
             s = np.zeros(6)
             L.lbo_solve_shifted(self.h, _p(dx0), _p(dx_ref), _p(d_off), _p(cost_shift), _p(warm), _p(uc), _p(th), _p(xt), _p(obj),
                                 it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), _p(s))
             out["stats"] = s.reshape(1, 6)
         else:
-            L.lbo_solve_batch_shifted(self.h, C.c_long(nb), _p(dx0), _p(dx_ref), _p(d_off), _p(cost_shift), _p(warm), _p(uc),
-                                      _p(th), _p(xt), _p(obj), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), C.c_int(nthreads))
+            rc = L.lbo_solve_batch_ex(self.h, C.c_long(nb), _p(dx0), _p(dx_ref), _p(d_off), _p(cost_shift), C.c_int(cs_stride),
+                                      C.c_int(int(rows)), _p(jac), _p(warm), _p(uc), _p(th), _p(xt), _p(obj),
+                                      it.ctypes.data_as(_ip), st.ctypes.data_as(_ip), C.c_int(nthreads))
+            if rc:
+                raise ValueError(L.lbo_last_error().decode())
         return out
 
     def oracle_offsets(self, dx0, du, X, Y, valid=None, bandwidth=0.5, lam=0.001):
@@ -147,9 +158,63 @@ class OracleProblem:
                                  C.c_double(bandwidth), C.c_double(lam), _p(d))
         return d
 
-    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, twin=False, A=None):
+    def oracle_offsets_jac(self, dx0, du, X, Y, valid=None, bandwidth=0.5, lam=0.001):
+        """(d_off (N,nx) = g - J xi, jac (N,nx,3), g (N,nx)) along the learned rollout (lbo_oracle_offsets_jac)."""
+        X, Y, valid = _d(X), _d(Y), _d(valid)
+        d, J, g = np.empty((self.N, self.nx)), np.empty((self.N, self.nx, 3)), np.empty((self.N, self.nx))
+        dx0, du = _d(dx0), _d(du)
+        lib().lbo_oracle_offsets_jac(self.h, _p(dx0), _p(du), _p(X), _p(Y), _p(valid), C.c_int(X.shape[1]),
+                                     C.c_double(bandwidth), C.c_double(lam), _p(d), _p(J), _p(g))
+        return d, J, g
+
+    def solve_sqp1(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, twin=False,
+                   A=None, B=None, K=None):
+        """CPU mirror of lbmpc_solve_sqp with order = 1 (first-order SQP): every outer iteration linearises the learned model
+        x+ = A x + B u + g(xi) along the learned rollout of the previous solution (oracle value AND Jacobian) and solves one LTV
+        QP on the LEARNED state sequence.  twin: the rows follow the NOMINAL sequence (constraintsLBMPC.m:23,
+        DMS_LBMPC_casadi.m:283-319): they act on x_k - e_k, u_k - K e_k with the gap e_k = learned - nominal rollout of the
+        previous solution, frozen during the QP.  Outputs: uc (c or du), theta, xtraj = the LEARNED sequence."""
+        dx0 = np.ascontiguousarray(dx0, float).reshape(-1, self.nx)
+        nb, N, nx, nu = dx0.shape[0], self.N, self.nx, self.nu
+        Kf = np.zeros((nu, nx)) if K is None else np.asarray(K, float).reshape(nu, nx)
+        A_ = None if A is None else np.asarray(A, float)
+        B_ = None if B is None else np.asarray(B, float).reshape(nx, nu)
+        outs, steps = [], np.empty((nb, sqp_iters))
+        for b in range(nb):
+            ulin = np.zeros(N) if warm is None else np.array(warm[b][:N], float)
+            w = None if warm is None else np.array(warm[b], float)[None, :]
+            xr = None if dx_ref is None else np.asarray(dx_ref[b], float)[None, :]
+            Xb, Yb = np.ascontiguousarray(X[b].T), np.ascontiguousarray(Y[b].T)
+            vb = None if valid is None else valid[b]
+            for j in range(sqp_iters):
+                d, J, g = self.oracle_offsets_jac(dx0[b], ulin, Xb, Yb, vb, bandwidth, lam)
+                rs = None
+                if twin:   # gap between the learned and the nominal rollout of the same decision variables
+                    xl, xn_ = dx0[b].copy(), dx0[b].copy()
+                    rs = np.zeros((N + 1, nx + nu))
+                    for k in range(N):
+                        rs[k, :nx] = xl - xn_
+                        rs[k, nx:] = Kf @ (xl - xn_)
+                        ul, un = Kf @ xl + ulin[k], Kf @ xn_ + ulin[k]
+                        xl = A_ @ xl + B_ @ ul + g[k]
+                        xn_ = A_ @ xn_ + B_ @ un
+                    rs[N, :nx] = xl - xn_
+                    rs = rs[None]
+                o = self.solve_batch(dx0[b:b + 1], xr, d[None], w, row_shift=rs, jac=J[None])
+                u = o["uc"][0, :, 0]
+                steps[b, j] = np.abs(u - ulin).max()
+                ulin = u.copy()
+                w = np.concatenate([u, o["theta"][0]])[None, :]
+            outs.append(o)
+        res = {k: np.concatenate([o[k] for o in outs]) for k in outs[0] if outs[0][k] is not None}
+        res["du_step"] = steps
+        return res
+
+    def solve_sqp(self, dx0, X, Y, valid=None, sqp_iters=3, dx_ref=None, warm=None, bandwidth=0.5, lam=0.001, twin=False, A=None,
+                  B=None, K=None):
         """CPU mirror of lbmpc_solve_sqp (include/lbmpc.h): oracle offsets along the previous inputs, then one QP, repeated.
-        X (batch,q,3), Y (batch,q,nx), valid (batch,q) or None."""
+        X (batch,q,3), Y (batch,q,nx), valid (batch,q) or None.  twin: cost on the learned sequence, rows on the nominal one;
+        with K (F-form: u = K x + c) the gap obeys e+ = (A + B K) e + d and the input gap is K e."""
         dx0 = np.ascontiguousarray(dx0, float).reshape(-1, self.nx)
         nb, N = dx0.shape[0], self.N
         outs, steps = [], np.empty((nb, sqp_iters))
@@ -160,10 +225,14 @@ class OracleProblem:
             for j in range(sqp_iters):
                 d = self.oracle_offsets(dx0[b], ulin, np.ascontiguousarray(X[b].T), np.ascontiguousarray(Y[b].T),
                                         None if valid is None else valid[b], bandwidth, lam)
-                if twin:   # cost on x + e with e_{k+1} = A e_k + d_k, rows and dynamics on x
-                    e = np.zeros((N + 1, self.nx))
-                    for k in range(N):
-                        e[k + 1] = A @ e[k] + d[k]
+                if twin:   # cost on x + e with e_{k+1} = (A + B K) e_k + d_k (K = 0: C-form), rows and dynamics on x
+                    Kf = np.zeros((self.nu, self.nx)) if K is None else np.asarray(K, float).reshape(self.nu, self.nx)
+                    Acl = np.asarray(A, float) + (0.0 if K is None else np.asarray(B, float).reshape(self.nx, self.nu) @ Kf)
+                    e = np.zeros((N + 1, self.nx + self.nu))
+                    for k in range(N + 1):
+                        e[k, self.nx:] = Kf @ e[k, :self.nx]
+                        if k < N:
+                            e[k + 1, :self.nx] = Acl @ e[k, :self.nx] + d[k]
                     o = self.solve_batch(dx0[b:b + 1], xr, None, w, cost_shift=e[None])
                 else:
                     o = self.solve_batch(dx0[b:b + 1], xr, d[None], w)

@@ -11,7 +11,7 @@
 using namespace lbmpc;
 
 template <int NX, int NT, int NU>
-static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off, const double* csh,
+static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off, const CShift csh,
                      const double* warm, double* uc, double* theta, double* xtraj, double* obj, int* iters,
                      int* status) {
     using C = Core<NX, NT, NU>;
@@ -186,7 +186,7 @@ extern "C" const char* emul_last_error() { return g_err.c_str(); }
 
 // same argument conventions as lbmpc_create + lbmpc_solve_batch (column-major, one column per QP)
 extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg, long batch, const double* dx0,
-                                const double* dx_ref, const double* d_off, const double* cost_shift, const double* warm,
+                                const double* dx_ref, const double* d_off, const double* cost_shift, int cs_stride, const double* warm,
                                 double* uc, double* theta, double* xtraj, double* obj, int* iters, int* status) {
     HostProblem hp;
     int rc = build_problem(mdl, cfg, hp, g_err);
@@ -196,7 +196,7 @@ extern "C" int emul_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg,
         const double* x0 = dx0 + b * nx;
         const double* xr = dx_ref ? dx_ref + b * nx : nullptr;
         const double* dk = d_off ? d_off + b * (long)nx * N : nullptr;
-        const double* cs = cost_shift ? cost_shift + b * (long)nx * (N + 1) : nullptr;
+        const CShift cs{cost_shift ? cost_shift + b * (long)cs_stride * (N + 1) : nullptr, cs_stride};
         const double* wm = warm ? warm + b * (long)(nu * N + nt) : nullptr;
         double* xt = xtraj ? xtraj + b * (long)nx * (N + 1) : nullptr;
         if (nx == 4 && nt == 1 && nu == 1)
@@ -228,7 +228,7 @@ static void stream_batch(const HostProblem& hp, StreamIO<FT> io, int lane) {
 
 extern "C" int emul_stream_solve_batch(const lbmpc_model* mdl, const lbmpc_config* cfg, long batch, int mode, int lane_stride,
                                        const double* dx0, const double* dx_ref, const double* d_off, const double* cost_shift,
-                                       const double* jac, const double* warm, double* uc, double* theta, double* xtraj,
+                                       int cs_stride, int row_shift, const double* jac, const double* warm, double* uc, double* theta, double* xtraj,
                                        double* obj, int* iters, int* status) {
     HostProblem hp;
     int rc = build_problem(mdl, cfg, hp, g_err);
@@ -237,7 +237,7 @@ extern "C" int emul_stream_solve_batch(const lbmpc_model* mdl, const lbmpc_confi
     auto run = [&](auto ft, auto ltv) {
         using FT = decltype(ft);
         StreamIO<FT> io{};
-        io.batch = batch; io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm; io.cshift = cost_shift; io.jac = jac;
+        io.batch = batch; io.dx0 = dx0; io.dx_ref = dx_ref; io.d_off = d_off; io.warm = warm; io.cshift = cost_shift; io.cs_stride = cost_shift ? cs_stride : 0; io.row_shift = row_shift; io.jac = jac;
         io.uc = uc; io.theta = theta; io.xtraj = xtraj; io.obj = obj; io.iters = iters; io.status = status;
         if (lane_stride == 32) stream_batch<decltype(ltv)::value, FT, 32>(hp, io, 13);
         else stream_batch<decltype(ltv)::value, FT, 1>(hp, io, 0);

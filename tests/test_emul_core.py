@@ -22,7 +22,7 @@ def emul_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=No
     p = capi._ptr
     c = lambda a: None if a is None else np.ascontiguousarray(a, float)
     dx_ref, d_off, warm, cost_shift = c(dx_ref), c(d_off), c(warm), c(cost_shift)
-    rc = lib.emul_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), p(dx0), p(dx_ref), p(d_off), p(cost_shift), p(warm), p(o["uc"]),
+    rc = lib.emul_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), p(dx0), p(dx_ref), p(d_off), p(cost_shift), C.c_int(4 if cost_shift is None else cost_shift.shape[-1]), p(warm), p(o["uc"]),
                               p(o["theta"]), p(o["xtraj"]), p(o["obj"]), p(o["iters"]), p(o["status"]))
     assert rc == 0, lib.emul_last_error()
     return o
@@ -92,3 +92,27 @@ def test_second_shape_double_integrator(emul_lib, form, N):
     # vertex solutions with a 0.01-weighted input cost: many more weakly determined minimisers than on the compressor model;
     # the objective still has to agree to 1e-7 for every QP (this shape is covered at that level: SURVEY 8c calls it unpinned)
     assert_parity(g, r, tol=1e-7, frac_tight=0.8, max_dit=2, caps=(1e-3, 1e-2))
+
+
+def test_core_state_and_input_cost_shift(emul_lib, models):
+    """Cost evaluated at [x_k + ex_k; u_k + eu_k] (F-form LBMPC: costLBMPC.m:27 rolls the learned model with u = K x + c,
+    constraintsLBMPC.m:23 the nominal one -> e+ = (A + B K) e + d, eu = K e): device math vs the oracle."""
+    rng = np.random.default_rng(23)
+    for form, variant, N in (("F", "LBMPC", 30), ("C", "LBMPC", 20)):
+        mdl = models[variant]
+        nb = 24
+        X0 = sample_ics(nb, seed=N + 2)
+        K = mdl["K"].reshape(1, 4) if form == "F" else np.zeros((1, 4))
+        Acl = mdl["A"] + mdl["B"].reshape(4, 1) @ K
+        d = 5e-4 * rng.standard_normal((nb, N, 4))
+        e = np.zeros((nb, N + 1, 5))
+        for k in range(N + 1):
+            e[:, k, 4] = e[:, k, :4] @ K[0]
+            if k < N:
+                e[:, k + 1, :4] = e[:, k, :4] @ Acl.T + d[:, k]
+        got = emul_solve(emul_lib, mdl, form, variant, N, X0, cost_shift=e)
+        ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, cost_shift=e)
+        assert_parity(got, ref)
+        xonly = OracleProblem(form, variant, mdl, N).solve_batch(X0, cost_shift=e[:, :, :4].copy())
+        if form == "F":
+            assert np.abs(xonly["uc"] - ref["uc"]).max() > 1e-7          # the input shift does change the F-form problem

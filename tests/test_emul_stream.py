@@ -11,7 +11,11 @@ from lbmpc_b200 import capi
 from oracle_py import OracleProblem
 
 
-def stream_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None, cost_shift=None, jac=None, mode=0, stride=1):
+def stream_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=None, cost_shift=None, jac=None, mode=0, stride=1,
+                 row_shift=None):
+    rows = row_shift is not None
+    if rows:
+        cost_shift = row_shift
     m, keep = capi.pack_model(mdl)
     cfg = capi.make_config(form, variant, N)
     dx0 = np.ascontiguousarray(dx0, float)
@@ -22,7 +26,7 @@ def stream_solve(lib, mdl, form, variant, N, dx0, dx_ref=None, d_off=None, warm=
     c = lambda a: None if a is None else np.ascontiguousarray(a, float)
     dx_ref, d_off, warm, cost_shift, jac = c(dx_ref), c(d_off), c(warm), c(cost_shift), c(jac)
     rc = lib.emul_stream_solve_batch(C.byref(m), C.byref(cfg), C.c_long(nb), C.c_int(mode), C.c_int(stride), p(dx0), p(dx_ref),
-                                     p(d_off), p(cost_shift), p(jac), p(warm), p(o["uc"]), p(o["theta"]), p(o["xtraj"]),
+                                     p(d_off), p(cost_shift), C.c_int(4 if cost_shift is None else cost_shift.shape[-1]), C.c_int(int(rows)), p(jac), p(warm), p(o["uc"]), p(o["theta"]), p(o["xtraj"]),
                                      p(o["obj"]), p(o["iters"]), p(o["status"]))
     assert rc == 0, lib.emul_last_error()
     return o
@@ -101,3 +105,49 @@ def test_stream_mixed_storage_mode(emul_lib, models):
     assert same.mean() >= 0.9 and set(got["status"][~same]) <= {1}
     both = same & (ref["status"] == 0)
     assert np.abs(got["obj"][both] - ref["obj"][both]).max() / np.abs(ref["obj"][both]).max() < 1e-8
+
+
+def test_stream_state_and_input_cost_shift(emul_lib, models):
+    """Cost evaluated at [x_k + ex_k; u_k + eu_k] (F-form LBMPC: costLBMPC.m:27 rolls the learned model with u = K x + c,
+    constraintsLBMPC.m:23 the nominal one -> e+ = (A + B K) e + d, eu = K e): device math vs the oracle."""
+    rng = np.random.default_rng(23)
+    for form, variant, N in (("F", "LBMPC", 30), ("C", "LBMPC", 20)):
+        mdl = models[variant]
+        nb = 24
+        X0 = sample_ics(nb, seed=N + 2)
+        K = mdl["K"].reshape(1, 4) if form == "F" else np.zeros((1, 4))
+        Acl = mdl["A"] + mdl["B"].reshape(4, 1) @ K
+        d = 5e-4 * rng.standard_normal((nb, N, 4))
+        e = np.zeros((nb, N + 1, 5))
+        for k in range(N + 1):
+            e[:, k, 4] = e[:, k, :4] @ K[0]
+            if k < N:
+                e[:, k + 1, :4] = e[:, k, :4] @ Acl.T + d[:, k]
+        got = stream_solve(emul_lib, mdl, form, variant, N, X0, cost_shift=e)
+        ref = OracleProblem(form, variant, mdl, N).solve_batch(X0, cost_shift=e)
+        assert_parity(got, ref)
+        xonly = OracleProblem(form, variant, mdl, N).solve_batch(X0, cost_shift=e[:, :, :4].copy())
+        if form == "F":
+            assert np.abs(xonly["uc"] - ref["uc"]).max() > 1e-7          # the input shift does change the F-form problem
+
+
+def test_stream_ltv_dynamics_and_row_shift(emul_lib, models):
+    """One first-order SQP step of the learned-oracle problem as the engine states it: LTV dynamics A_k = A + [J_k 0 0],
+    B_k = B + J_k(:,3) from oracle Jacobians, offsets d_k, and the rows acting on x_k - e_k, u_k - K e_k (the nominal
+    sequence) while the cost acts on x_k (the learned one): stream passes vs the oracle, both forms."""
+    rng = np.random.default_rng(29)
+    for form, variant, N in (("F", "LBMPC", 30), ("C", "LBMPC", 50), ("C", "LMPC", 20)):
+        mdl = models[variant]
+        nb = 24
+        X0 = sample_ics(nb, seed=N + 3)
+        J = 2e-2 * rng.standard_normal((nb, N, 4, 3))
+        d = 5e-4 * rng.standard_normal((nb, N, 4))
+        e = np.concatenate([2e-3 * rng.standard_normal((nb, N + 1, 4)).cumsum(axis=1), 1e-3 * rng.standard_normal((nb, N + 1, 1))], axis=2)
+        e[:, 0] = 0.0
+        P = OracleProblem(form, variant, mdl, N)
+        assert_parity(stream_solve(emul_lib, mdl, form, variant, N, X0, d_off=d, jac=J), P.solve_batch(X0, d_off=d, jac=J))
+        got = stream_solve(emul_lib, mdl, form, variant, N, X0, d_off=d, jac=J, row_shift=e)
+        ref = P.solve_batch(X0, d_off=d, jac=J, row_shift=e)
+        assert_parity(got, ref)
+        x = ref["xtraj"][ref["status"] == 0]
+        assert np.abs(ref["uc"] - P.solve_batch(X0, d_off=d)["uc"]).max() > 1e-5          # the Jacobians do change the problem

@@ -518,3 +518,64 @@ def test_device_pointer_mode_oracle_and_closed_loop(fx, models):
     torch.cuda.synchronize()
     for k in ("x", "u", "theta", "iters", "status"):
         assert np.array_equal(d[k].cpu().numpy(), h[k]), k
+
+
+def test_fform_closed_loop_drivers_vs_reference_histories(fx, models):
+    """The Python mirrors of ocpLBMPC.m / ocpLMPC.m (lbmpc_b200.ocpLBMPC / ocpLMPC: the reference's argument lists, the
+    solver call replaced by the GPU engine) against the reference's saved F-form runs LBMPC_N50_sys_full.mat /
+    LMPC_N50_sys_full.mat (LBMPC_RunExample.m / LMPC_RunExample.m defaults): the first input at 2e-7 (step 1 is an exact QP),
+    the next 39 columns well inside 1e-3 — measured 5e-6 on the inputs, 5e-5 on the fast throttle-rate state (fmincon's 1e-6
+    noise, ode23 vs RK4); for LBMPC the learned term acts on the cost only (costLBMPC.m:27 vs constraintsLBMPC.m:23) and the
+    first-order SQP of lbmpc_solve_sqp_ex is what reaches that agreement.  SURVEY 8d config 1."""
+    import lbmpc_b200
+    x_wp, u_wp = X_EQ, U_EQ
+    steps = 39
+    for variant in ("LBMPC", "LMPC"):
+        mdl = models[variant]
+        ref = fx[f"{variant}_N50__sysH"]
+        art = fx[f"{variant}_N50__art_refH"]
+        common = dict(N=50, Ts=0.01, iterations=steps, options=None, opt_var=np.zeros(51))
+        mats = [mdl[k] for k in ("K", "Q", "R", "P", "T")] + [np.vstack([mdl["LAMBDA"], mdl["PSI"]]), mdl["LAMBDA"], mdl["PSI"], 1]
+        rows = [mdl[k] for k in ("F_x", "h_x", "F_u", "h_u", "F_w_N", "h_w_N")]
+        hist0 = [np.concatenate([DX0, [0.0]]).reshape(5, 1), np.zeros((1, 1)), np.zeros((4, 1))]
+        info = {}
+        if variant == "LBMPC":
+            sysH, artH, _ = lbmpc_b200.ocpLBMPC(x_wp + DX0, x_wp, DX0, np.zeros(4), u_wp, common["N"], common["Ts"], steps, None,
+                                                common["opt_var"], {"X": np.zeros((3, 1)), "Y": np.zeros((4, 1))}, mdl["A"], mdl["B"],
+                                                *mats, *rows, mdl["F_x_d"], mdl["h_x_d"], *hist0, info=info)
+        else:
+            sysH, artH, _ = lbmpc_b200.ocpLMPC(x_wp + DX0, DX0, x_wp, np.zeros(4), u_wp, common["N"], common["Ts"], steps, None,
+                                               common["opt_var"], *mats, *rows, *hist0, A=mdl["A"], B=mdl["B"], info=info)
+        assert sysH.shape == (5, steps + 1) and (info["status"] == 0).all()
+        assert abs(sysH[4, 1] - ref[4, 1]) < 2e-7 and abs(artH[0, 1] - art[0, 1]) < 2e-7     # first solve: known answer
+        err = np.abs(sysH[:, :steps + 1] - ref[:, :steps + 1])
+        assert err[[0, 1, 2, 4]].max() < 3e-5 and err[3].max() < 2e-4, err.max(1)
+        assert np.abs(artH[0, :steps + 1] - art[0, :steps + 1]).max() < 1e-3
+        if variant == "LBMPC":
+            assert info["data"]["X"].shape == (3, steps) and np.abs(info["data"]["Y"]).max() < 5e-3    # the window filled up
+
+
+@pytest.mark.parametrize("form,twin", [("C", False), ("C", True), ("F", True)])
+def test_first_order_sqp_matches_oracle_mirror(fx, models, form, twin):
+    """lbmpc_solve_sqp_ex with order = 1 (oracle value + Jacobian -> LTV QP on the learned sequence, rows on the nominal
+    sequence when twin) vs the CPU mirror of the same outer loop (OracleProblem.solve_sqp1); the outer iteration contracts
+    faster than the zero-order one and ends at a different (the NLP-stationary) point."""
+    mdl = models["LBMPC"]
+    data = fx["casadi_train_data__data"]
+    nb, N, q, its = 16, 50, 100, 3
+    rng = np.random.default_rng(6)
+    X0 = sample_ics(nb, seed=14) * 0.5
+    offs = rng.integers(0, data.shape[1] - q, nb)
+    Xw = np.stack([data[:3, o:o + q].T for o in offs])
+    Yw = np.stack([data[3:7, o:o + q].T for o in offs]) * 2.0
+    sol = solver(mdl, form, "LBMPC", N, max_batch=nb)
+    got = sol.solve_sqp(X0, Xw, Yw, sqp_iters=its, twin=twin, order=1)
+    assert sol.last_kernel == "stream"
+    ref = OracleProblem(form, "LBMPC", mdl, N).solve_sqp1(X0, Xw, Yw, sqp_iters=its, twin=twin, A=mdl["A"], B=mdl["B"],
+                                                          K=mdl["K"] if form == "F" else None)
+    assert_parity(got, ref, tol=1e-7, caps=(1e-5, 1e-4))
+    ok = ref["status"] == 0
+    assert np.abs(got["du_step"][ok] - ref["du_step"][ok]).max() < 1e-6
+    assert np.median(ref["du_step"][ok, 2]) < 0.1 * np.median(ref["du_step"][ok, 1])    # the outer iteration contracts
+    zero = sol.solve_sqp(X0, Xw, Yw, sqp_iters=6, twin=twin, order=0)
+    assert np.abs(zero["uc"][ok] - got["uc"][ok]).max() > 1e-6                           # not the same fixed point
