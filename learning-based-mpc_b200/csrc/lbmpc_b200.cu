@@ -141,8 +141,11 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     if (h->force_kernel == LBMPC_KERNEL_CTA) return cta_ok ? LBMPC_KERNEL_CTA : LBMPC_KERNEL_WARP;
     if (h->force_kernel == LBMPC_KERNEL_STREAM || h->force_kernel == LBMPC_KERNEL_STREAM_MIXED)
         return stream_ok ? h->force_kernel : LBMPC_KERNEL_WARP;
-    // many QPs per SM: one thread per QP with the iterate streamed from HBM (no shared-memory residency limit)
-    if (stream_ok && h->st_min_batch > 0 && batch >= h->st_min_batch) return LBMPC_KERNEL_STREAM;
+    // very many QPs per SM, small polytope block, moderate horizon: one thread per QP with the iterate streamed from HBM.
+    // Measured (C-form LBMPC, N = 50): 6.2 M QP/s at batch 262144 against 4.5 M for the warp mapping, level near 131072, behind
+    // below (one iteration of a lane lasts ~0.5 ms, so the launch needs several QPs per lane to amortise its last QPs);
+    // thread-local loops over a 616-row set and N = 200 at batch 65536 lose to the CTA mapping.
+    if (stream_ok && h->st_min_batch > 0 && batch >= h->st_min_batch && h->hp.ng <= 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
@@ -377,7 +380,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
-        h->st_min_batch = (int64_t)h->num_sms * 64;  // >= 64 QPs (2 warps) per SM; below that the shared-memory kernels win
+        h->st_min_batch = (int64_t)h->num_sms * 1024;  // >= 4 QPs per resident lane; below that the shared-memory kernels win
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
         if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use

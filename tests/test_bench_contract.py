@@ -35,6 +35,21 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
 
 
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_reference_arm_other_configs(config):
+    """--config 2/3/4 (BASELINE configs[2..4]): bounded CPU samples, same contract line, same `config` object as our arm."""
+    sys.path.insert(0, ROOT)
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", str(config), "--steps", "1",
+                          "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1])
+    for k in COMMON:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["scaling"] == bench.CONFIGS[config]["scaling"]
+    assert d["config"] == bench.config_object(dict(bench.CONFIGS[config], id=config), 2)     # identical object in both arms
+
+
 def test_committed_gpu_bench_line_schema():
     path = os.path.join(ROOT, "profiles", "r1_bench_ours.json")
     if not os.path.exists(path):
