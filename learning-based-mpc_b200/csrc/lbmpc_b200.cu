@@ -50,6 +50,7 @@ struct lbmpc_handle {
     int max_slots = 0, stage_g = 0, num_sms = 0;
     int cta_blocks_per_sm[2] = {0, 0};  // [0] > 0: the CTA-per-QP latency kernel (4 warps per QP) is available: resident CTAs per SM
     size_t cta_smem = 0;
+    int cta_warps_force = 0;           // 2 / 4: warps per QP of the CTA kernel (LBMPC_CTA_WARPS, experiments)
     bool cta_big = false;              // large polytope block: G stays in global memory, sums by block reduction
     bool dev_ptrs = false;
     int64_t max_batch = 0;
@@ -75,6 +76,10 @@ struct lbmpc_handle {
     int64_t sqp_batch = 0;
     int sqp_iters = 0;
     double *q_ulin = nullptr, *q_warm = nullptr, *q_doff = nullptr, *q_step = nullptr, *q_csh = nullptr, *q_jac = nullptr;
+    // staging of the host-pointer oracle / SQP calls (data windows, input sequences): grown on first use, then reused — no
+    // allocation in the steady state of a closed loop
+    double* og[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t og_cap[6] = {0, 0, 0, 0, 0, 0};
     // kernel choice (lbmpc_set_kernel; LBMPC_KERNEL / LBMPC_LOCKSTEP / LBMPC_STREAM_* are read ONCE, in lbmpc_create)
     int force_kernel = LBMPC_KERNEL_AUTO, force_lockstep = -1;
     // stream kernel (one thread per QP, iterate in HBM): workspace of the resident warps
@@ -153,6 +158,8 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     // still level at 440 QPs/SM: always picked.
     if (h->cta_big) return LBMPC_KERNEL_CTA;
     if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return LBMPC_KERNEL_CTA;
+    // (a two-warps-per-QP CTA variant exists — LBMPC_CTA_WARPS=2 — but 35 KB of shared memory per CTA keep it at 6 CTAs per SM,
+    //  and even four warps per QP gain only 9 % over the warp mapping at 4 QPs per SM: not picked automatically)
     // long horizons: shared memory holds only 1-2 QPs per SM either way, so the four warps of a CTA are free (N = 200: 1.18x)
     if (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots) return LBMPC_KERNEL_CTA;
     return LBMPC_KERNEL_WARP;
@@ -160,11 +167,14 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
 static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io_in, cudaStream_t st) {
     const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
     BatchIO io = io_in;
-    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * h->cta_blocks_per_sm[0], io.batch);
+    // four warps per QP; two warps per QP only when forced (experiments)
+    const bool two = !h->cta_big && h->cta_blocks_per_sm[1] > 0 && h->cta_warps_force == 2;
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * h->cta_blocks_per_sm[two ? 1 : 0], io.batch);
     io.queue = next_queue(h);
     cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (h->cta_big) ipm_kernel_cta<4, 1, 1, 4, true><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
+    else if (two) ipm_kernel_cta<4, 1, 1, 2, false><<<grid, 64, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
     else ipm_kernel_cta<4, 1, 1, 4, false><<<grid, 128, h->cta_smem, st>>>(p, io, h->dG, h->dhg);
     h->launches += 1;
     h->last_kernel = LBMPC_KERNEL_CTA;
@@ -291,6 +301,19 @@ template <typename T>
 static cudaError_t dmalloc(T** p, size_t n) {
     return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
 }
+// handle-owned staging buffer i with room for n doubles (grows, never shrinks)
+static cudaError_t staging(lbmpc_handle* h, int i, size_t n, double** out) {
+    if (h->og_cap[i] < n) {
+        cudaFree(h->og[i]);
+        h->og[i] = nullptr; h->og_cap[i] = 0;
+        const size_t cap = std::max<size_t>(n, (size_t)h->max_batch * 4);
+        cudaError_t e = cudaMalloc((void**)&h->og[i], cap * sizeof(double));
+        if (e != cudaSuccess) return e;
+        h->og_cap[i] = cap;
+    }
+    *out = h->og[i];
+    return cudaSuccess;
+}
 
 extern "C" {
 
@@ -306,37 +329,29 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
     if (device < 0 || device >= ndev) return fail(LBMPC_EINVAL, "bad device index");
     lbmpc_handle* h = new (std::nothrow) lbmpc_handle();
     if (!h) return fail(LBMPC_ENOMEM, "out of host memory");
+    struct Guard {  // every early return below releases what has been allocated so far (lbmpc_destroy tolerates partial handles)
+        lbmpc_handle* h;
+        ~Guard() { if (h) lbmpc_destroy(h); }
+    } guard{h};
     std::string err;
     int rc = build_problem(model, cfg, h->hp, err);
-    if (rc != LBMPC_OK) {
-        delete h;
-        return fail(rc, err);
-    }
+    if (rc != LBMPC_OK) return fail(rc, err);
     const HostProblem& hp = h->hp;
     if (hp.nx == 4 && hp.nt == 1 && hp.nu == 1) h->shape = 0;
     else if (hp.nx == 2 && hp.nt == 2 && hp.nu == 2) h->shape = 1;
-    else {
-        delete h;
-        return fail(LBMPC_ESHAPE, "compiled shapes: (nx,nt,nu) = (4,1,1) Moore-Greitzer, (2,2,2) double integrator");
-    }
+    else return fail(LBMPC_ESHAPE, "compiled shapes: (nx,nt,nu) = (4,1,1) Moore-Greitzer, (2,2,2) double integrator");
     h->device = device;
     h->dev_ptrs = cfg->pointers_on_device != 0;
     h->max_batch = std::max<int64_t>(cfg->max_batch, 1);
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        delete h;
-        return fail(LBMPC_ECUDA, "device is not sm_100 (Blackwell); the library carries sm_100a code only");
-    }
+    if (prop.major < 10) return fail(LBMPC_ECUDA, "device is not sm_100 (Blackwell); the library carries sm_100a code only");
     h->num_sms = prop.multiProcessorCount;
     int max_smem = 0;
     CU_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     rc = h->shape == 0 ? plan_slots<4, 1, 1>(h, (size_t)max_smem) : plan_slots<2, 2, 2>(h, (size_t)max_smem);
-    if (rc != LBMPC_OK) {
-        delete h;
-        return rc;
-    }
+    if (rc != LBMPC_OK) return rc;
     if (h->shape == 0)
         CU_TRY(cudaFuncSetAttribute(ipm_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     else
@@ -351,6 +366,9 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
             } else {
                 CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
                 CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[0], ipm_kernel_cta<4, 1, 1, 4, false>, 128, cplan.bytes));
+                CU_TRY(cudaFuncSetAttribute(ipm_kernel_cta<4, 1, 1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cplan.bytes));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->cta_blocks_per_sm[1], ipm_kernel_cta<4, 1, 1, 2, false>, 64, cplan.bytes));
+                if (const char* e = getenv("LBMPC_CTA_WARPS")) h->cta_warps_force = atoi(e);
             }
             h->cta_smem = cplan.bytes;
         }
@@ -407,6 +425,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(cudaHostAlloc((void**)&h->hs_small, std::max<size_t>(small, 16), cudaHostAllocDefault));
         CU_TRY(cudaHostAlloc((void**)&h->hs_bounce, kBounceBytes, cudaHostAllocMapped));
     }
+    guard.h = nullptr;  // success: the caller owns the handle
     *out = h;
     return LBMPC_OK;
 }
@@ -581,13 +600,9 @@ int lbmpc_oracle_apply(lbmpc_handle* h, int64_t batch, int32_t q, double bandwid
         return LBMPC_OK;
     }
     double *ddx0 = nullptr, *ddu = nullptr, *dX = nullptr, *dY = nullptr, *dV = nullptr, *dd = nullptr;
-    struct TmpGuard {  // staging of a host-pointer call: released on every exit path
-        double *&a, *&b, *&c, *&d, *&e, *&f;
-        ~TmpGuard() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); cudaFree(e); cudaFree(f); }
-    } tmp_guard{ddx0, ddu, dX, dY, dV, dd};
-    CU_TRY(dmalloc(&ddx0, b * 4)); CU_TRY(dmalloc(&ddu, b * N)); CU_TRY(dmalloc(&dX, b * 3 * q));
-    CU_TRY(dmalloc(&dY, b * 4 * q)); CU_TRY(dmalloc(&dd, b * 4 * N));
-    if (valid) CU_TRY(dmalloc(&dV, b * q));
+    CU_TRY(staging(h, 0, b * 4, &ddx0)); CU_TRY(staging(h, 1, b * N, &ddu)); CU_TRY(staging(h, 2, b * 3 * q, &dX));
+    CU_TRY(staging(h, 3, b * 4 * q, &dY)); CU_TRY(staging(h, 4, b * 4 * N, &dd));
+    if (valid) CU_TRY(staging(h, 5, b * q, &dV));
     CU_TRY(cudaMemcpyAsync(ddx0, dx0, 8 * b * 4, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(ddu, du, 8 * b * N, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(dX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
@@ -643,13 +658,9 @@ int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_
     double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
     int *d_it = iters, *d_st = status;
     double *tX = nullptr, *tY = nullptr, *tV = nullptr;
-    struct TmpGuard {  // the data-window staging of a host-pointer call is released on every exit path
-        double *&a, *&b, *&c;
-        ~TmpGuard() { cudaFree(a); cudaFree(b); cudaFree(c); }
-    } tmp_guard{tX, tY, tV};
     if (!h->dev_ptrs) {
-        CU_TRY(dmalloc(&tX, b * 3 * q)); CU_TRY(dmalloc(&tY, b * 4 * q));
-        if (valid) CU_TRY(dmalloc(&tV, b * q));
+        CU_TRY(staging(h, 2, b * 3 * q, &tX)); CU_TRY(staging(h, 3, b * 4 * q, &tY));
+        if (valid) CU_TRY(staging(h, 5, b * q, &tV));
         CU_TRY(cudaMemcpyAsync(tX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(tY, Y, 8 * b * 4 * q, cudaMemcpyHostToDevice, st));
         if (valid) CU_TRY(cudaMemcpyAsync(tV, valid, 8 * b * q, cudaMemcpyHostToDevice, st));
@@ -858,8 +869,12 @@ int lbmpc_measure_fp64_peak(int device, double* tflops) {
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     double* d = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct Guard {
+        double*& d; cudaEvent_t &e0, &e1;
+        ~Guard() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); cudaFree(d); }
+    } guard{d, e0, e1};
     CU_TRY(dmalloc(&d, 1));
-    cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
     const int grid = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
@@ -874,9 +889,6 @@ int lbmpc_measure_fp64_peak(int device, double* tflops) {
         const double flops = 2.0 * 64.0 * (double)iters * (double)grid * (double)threads;
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
     *tflops = best;
     return LBMPC_OK;
 }
@@ -892,6 +904,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     if (h->hs_bounce) cudaFreeHost(h->hs_bounce);
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh); cudaFree(h->q_jac);
     cudaFree(h->st_ws64); cudaFree(h->st_wsft);
+    for (int i = 0; i < 6; ++i) cudaFree(h->og[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -53,7 +53,7 @@ struct Params {
     double tol_res, tol_mu, inf_trigger, inv_m;
     // Farkas test: status 2 when h_red'lambda < 0 and inf_scale * sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda, ybar_j an
     // upper bound of |y_j| on the feasible set: fk_u (input bound) inside the stage range of the input rows, fk_free else
-    double fk_u[NU], fk_free, inf_scale;
+    double fk_u[NU], fk_th[NT], fk_free, inf_scale;   // fk_th: |theta_t| on the feasible set, derived from the polytope block (lbmpc_problem.hpp)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -902,7 +902,7 @@ struct Core {
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            nrm = farkas ? nrm + lb_abs(pi[NX + t]) * p.fk_free : lb_nanmax(nrm, lb_abs(pi[NX + t]));
+            nrm = farkas ? nrm + lb_abs(pi[NX + t]) * p.fk_th[t] : lb_nanmax(nrm, lb_abs(pi[NX + t]));
             ydot += pi[NX + t] * m[L::M_TH + t];
         }
         if (farkas) {
@@ -1003,7 +1003,7 @@ struct Core {
         if (b == 0) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                nrm += lb_abs(pi[NX + t]) * p.fk_free;
+                nrm += lb_abs(pi[NX + t]) * p.fk_th[t];
                 ydot += pi[NX + t] * m[L::M_TH + t];
             }
         }

@@ -39,7 +39,7 @@ struct HostProblem {
     std::vector<double> A, B, Kinit, Kout, W, lo, hi, Lref, Tm;  // row-major
     std::vector<double> G, hg;                                   // G component-major [NZ][ngp]
     double tol_res = 1e-9, tol_mu = 1e-10, inf_trigger = 1e2, inf_scale = 1.01;
-    std::vector<double> fk_u;
+    std::vector<double> fk_u, fk_th;
 };
 
 namespace detail {
@@ -211,7 +211,32 @@ inline int build_problem(const lbmpc_model* m, const lbmpc_config* c, HostProble
     // where they exist, 10 per unbounded variable), margin 1 % for round-off:  1.01 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
     // (raising the box multipliers of u_j by |(G_red'lambda)_j| cancels that component exactly and costs ybar_j each: the
     // test says the corrected lambda is an exact Farkas certificate)
-    double Rb = 10.0 * nt;
+    // theta: every polytope row with ONE non-zero theta coefficient g_t bounds that component once x_kg is boxed,
+    //     g_t theta_t <= hg_i + sum_j |G_ij| max(|lo_j|, |hi_j|);
+    // tightest upper / lower bound over the rows -> ybar_theta (10 if a side stays unbounded).  Exact for the reference's sets
+    // (0.98 for Moore-Greitzer); a model with a wider steady-state range is judged by its own range.
+    double Rb = 0.0;
+    hp.fk_th.assign(nt, 10.0);
+    for (int t = 0; t < nt; ++t) {
+        double ub = inf, lb = -inf;
+        const bool boxed = hp.kg >= hp.kx0 && hp.kg <= hp.kx1;
+        for (int i = 0; i < hp.ng && boxed; ++i) {
+            int others = 0;
+            for (int a = 0; a < nt; ++a) others += (a != t && hp.G[(size_t)(nx + a) * hp.ngp + i] != 0.0);
+            const double gt = hp.G[(size_t)(nx + t) * hp.ngp + i];
+            if (others || gt == 0.0) continue;
+            double rhs = hp.hg[i];
+            for (int j = 0; j < nx; ++j) {
+                const double gj = hp.G[(size_t)j * hp.ngp + i];
+                if (gj != 0.0) rhs += std::fabs(gj) * std::fmax(std::fabs(hp.lo[j]), std::fabs(hp.hi[j]));
+            }
+            if (!std::isfinite(rhs)) continue;
+            if (gt > 0.0) { if (rhs / gt < ub) ub = rhs / gt; }
+            else          { if (rhs / gt > lb) lb = rhs / gt; }
+        }
+        if (std::isfinite(ub) && std::isfinite(lb)) hp.fk_th[t] = std::fmax(std::fabs(ub), std::fabs(lb));
+        Rb += hp.fk_th[t];
+    }
     hp.fk_u.assign(nu, 10.0);
     for (int j = nx; j < nx + nu; ++j) {
         const double bnd = std::fmax(std::fabs(hp.lo[j]), std::fabs(hp.hi[j]));
@@ -264,6 +289,7 @@ inline Params<NX, NT, NU> to_params(const HostProblem& hp) {
     for (int i = 0; i < NX * NX; ++i) p.Tm[i] = hp.Tm[i];
     p.tol_res = hp.tol_res; p.tol_mu = hp.tol_mu; p.inf_trigger = hp.inf_trigger; p.inf_scale = hp.inf_scale; p.fk_free = 10.0;
     for (int i = 0; i < NU; ++i) p.fk_u[i] = hp.fk_u[i];
+    for (int i = 0; i < NT; ++i) p.fk_th[i] = hp.fk_th[i];
     p.inv_m = 1.0 / (double)hp.m_rows;
     return p;
 }

@@ -584,7 +584,7 @@ struct Stream {
         ln.iptt = 1.0 / ptt;
         ln.dtha = -ln.iptt * pv[NX];
         rd = lb_nanmax(rd, lb_abs(pi[NX]));
-        ci += lb_abs(pc[NX]) * p.fk_free;
+        ci += lb_abs(pc[NX]) * p.fk_th[0];
         yd += pc[NX] * th;
 #pragma unroll
         for (int a = 0; a < NZ; ++a) ln.gGl[a] = gGl[a];

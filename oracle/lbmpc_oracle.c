@@ -61,6 +61,7 @@ struct lbo_problem {
     int m_rows;
     double tol_res, tol_mu, inf_trigger, inf_scale, inf_bound_sum;
     double fk_u[MAXNU], fk_free; /* Farkas test: upper bounds of |u_i| (inside the input-row stage range) / of a free variable */
+    double fk_th[MAXNT];         /* ... of |theta_t| on the feasible set, derived from the polytope block and the state box */
     int max_iter;
 };
 
@@ -192,7 +193,31 @@ static void count_rows(lbo_problem *p) {
      *     h_red'lambda < 0  and  1.01 sum_j |(G_red'lambda)_j| ybar_j <= -h_red'lambda
      * (raising the box multipliers of u_j by |(G_red'lambda)_j| cancels that component exactly at the price ybar_j each,
      *  so the test says: the corrected lambda is an exact Farkas certificate)                                 */
-    double R = 10.0 * p->nt;
+    /* theta: every polytope row with ONE non-zero theta coefficient g_t bounds that component once x_kg is boxed:
+     *     g_t theta_t <= hg_i + sum_j |G_ij| max(|lo_j|, |hi_j|)
+     * the tightest upper and lower bound over the rows give ybar_theta (10 if a side stays unbounded).  For the reference's
+     * sets this is the exact range of theta on the feasible set (0.98 for the Moore-Greitzer model), so models with a larger
+     * steady-state range are judged by their own range, not by a constant. */
+    double R = 0.0;
+    for (int t = 0; t < p->nt; ++t) {
+        double ub = INFINITY, lb = -INFINITY;
+        const int boxed = p->kg >= p->kx0 && p->kg <= p->kx1;
+        for (int i = 0; i < p->ng && boxed; ++i) {
+            const double *g = p->G + (size_t)i * p->nz;
+            int others = 0;
+            for (int a = 0; a < p->nt; ++a) others += (a != t && g[p->nx + a] != 0.0);
+            const double gt = g[p->nx + t];
+            if (others || gt == 0.0) continue;
+            double rhs = p->hg[i];
+            for (int j = 0; j < p->nx; ++j)
+                if (g[j] != 0.0) rhs += fabs(g[j]) * fmax(fabs(p->lo[j]), fabs(p->hi[j]));
+            if (!isfinite(rhs)) continue;
+            if (gt > 0.0) { if (rhs / gt < ub) ub = rhs / gt; }
+            else          { if (rhs / gt > lb) lb = rhs / gt; }
+        }
+        p->fk_th[t] = (isfinite(ub) && isfinite(lb)) ? fmax(fabs(ub), fabs(lb)) : 10.0;
+        R += p->fk_th[t];
+    }
     p->fk_free = 10.0;
     for (int j = p->nx; j < p->nvb; ++j) {
         const double b = fmax(fabs(p->lo[j]), fabs(p->hi[j]));
@@ -685,7 +710,7 @@ static int backward(const lbo_problem *p, lbo_ws *w, int factor, double *rd_inf,
             if (fabs(pi[nx + a]) > rdi) rdi = fabs(pi[nx + a]);
             if (pi[nx + a] != pi[nx + a]) rdi = NAN;
             if (cert) {
-                ci += fabs(pc[nx + a]) * p->fk_free;
+                ci += fabs(pc[nx + a]) * p->fk_th[a];
                 ydot += pc[nx + a] * w->th[a];
             }
         }

@@ -53,7 +53,7 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
 
 
-def assert_parity(got, ref, tol=1e-8, frac_tight=0.995, max_dit=1, caps=(1e-6, 1e-4)):
+def assert_parity(got, ref, tol=1e-8, frac_tight=0.999, max_dit=1, caps=(1e-7, 1e-6)):
     """The parity rule of SURVEY.md §8c / BASELINE.json north_star, FP64:
       * identical feasibility verdicts (status) for every QP,
       * iteration counts within +-1,
@@ -64,9 +64,10 @@ def assert_parity(got, ref, tol=1e-8, frac_tight=0.995, max_dit=1, caps=(1e-6, 1
     the ulp of the states in the last interior-point iterations): there the objective still agrees to 1e-12
     but the primal iterate carries round-off noise ~ eps*lambda/mu that ANY FP64 interior-point implementation
     shows (the oracle and the independent dense formulation differ by the same amount,
-    tests/test_oracle_golden.py).  So: >= 99.5 % of the optimal QPs must meet 1e-8, none may exceed 1e-6
-    (1e-4 when the two sides stopped one iteration apart, where a degenerate vertex is only reached to
-    O(sqrt(mu)))."""
+    tests/test_oracle_golden.py).  So: >= 99.9 % of the optimal QPs must meet 1e-8, none may exceed 1e-7
+    (1e-6 when the two sides stopped one iteration apart, where a degenerate vertex is only reached to
+    O(sqrt(mu))) — the levels a 184 k-QP sweep measured (profiles/r1_stress_parity.json: 99.97 % within 1e-8, worst
+    4e-8), so that a 10x regression fails.  Batches below 1000 QPs: at most ONE QP may sit between 1e-8 and the cap."""
     assert (got["status"] == ref["status"]).all(), np.nonzero(got["status"] != ref["status"])
     dit = np.abs(got["iters"].astype(int) - ref["iters"].astype(int))
     assert dit.max(initial=0) <= max_dit
@@ -86,7 +87,8 @@ def assert_parity(got, ref, tol=1e-8, frac_tight=0.995, max_dit=1, caps=(1e-6, 1
     e = np.max(np.stack(errs), axis=0)
     cap = np.where(dit[ok] == 0, caps[0], caps[1])
     assert (e < cap).all(), (e.max(), int(np.argmax(e)))
-    assert (e < tol).mean() >= frac_tight, ((e < tol).mean(), e.max())
+    n_loose = int((e >= tol).sum())
+    assert n_loose <= max(1, int((1.0 - frac_tight) * e.size)), ((e < tol).mean(), e.max())
 
 
 def double_integrator_cases(n, seed=0):

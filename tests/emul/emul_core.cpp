@@ -10,6 +10,14 @@
 
 using namespace lbmpc;
 
+// Lane order of the emulated warp phases.  On the GPU the lanes of a phase run concurrently and only __syncwarp() / shuffles
+// separate the phases, so a phase must not depend on the order in which its lanes execute.  The harness can run every lane
+// loop backwards (emul_set_lane_order(1)): bit-identical results forwards and backwards are the CPU-side stand-in for
+// compute-sanitizer's racecheck (closed on this GPU pool) — a read-after-write between lanes inside one phase would show.
+static int g_reverse_lanes = 0;
+extern "C" void emul_set_lane_order(int reverse) { g_reverse_lanes = reverse; }
+#define LANES(var, n) for (int var##_i = 0, var = g_reverse_lanes ? (n) - 1 : 0; var##_i < (n); ++var##_i, var += g_reverse_lanes ? -1 : 1)
+
 template <int NX, int NT, int NU>
 static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_ref, const double* d_off, const CShift csh,
                      const double* warm, double* uc, double* theta, double* xtraj, double* obj, int* iters,
@@ -49,25 +57,25 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
     // blocked substitution sweeps: lane-phases as loops (kernel: lanes of the QP's warp, __syncwarp between phases)
     auto solve_sweeps = [&](bool aff, bool with_T) {
         const int ntask = l.nb * (with_T ? NX + 1 : 1);
-        for (int t = 0; t < ntask; ++t) C::bwd_p1(p, l, s, zero_rec.data(), t, with_T);
+        LANES(t, ntask) C::bwd_p1(p, l, s, zero_rec.data(), t, with_T);
         C::bwd_p2(l, s, aff);
         std::vector<double> pin((size_t)l.nb * NZ);
-        for (int b = 0; b < l.nb; ++b) C::bwd_p3_in(p, l, s, b, pin.data() + (size_t)b * NZ);
-        for (int b = 0; b < l.nb; ++b) C::bwd_p3_fwd_p1(p, l, s, b, pin.data() + (size_t)b * NZ, aff);
+        LANES(b, l.nb) C::bwd_p3_in(p, l, s, b, pin.data() + (size_t)b * NZ);
+        LANES(b, l.nb) C::bwd_p3_fwd_p1(p, l, s, b, pin.data() + (size_t)b * NZ, aff);
         C::fwd_p2(l, s);
-        for (int b = l.nb - 1; b >= 0; --b) C::fwd_p3(p, l, s, b, aff);
+        LANES(b, l.nb) C::fwd_p3(p, l, s, b, aff);
     };
     int it = 0, st = 1;
     for (it = 0;; ++it) {
         // ---- phase A: predictor assembly (kernel: warp per QP, lanes over stages / rows) ----
         RedAsm ra{0, 0, 0, 0, 0};
-        for (int k = 0; k <= N; ++k) {
+        LANES(k, N + 1) {
             if (it == 0) C::init_assemble_stage(p, l, s, k, ra, csh);
             else C::update_assemble_stage(p, l, s, k, alpha, ra, csh);
         }
         double acc[NH + 2 * NZ];
         std::memset(acc, 0, sizeof acc);
-        for (int i = 0; i < p.ng; ++i) C::assemble_gen_row(p, l, s, G, hg, i, acc, ra);
+        LANES(i, p.ng) C::assemble_gen_row(p, l, s, G, hg, i, acc, ra);
         for (int a = 0; a < NH; ++a) m[L::M_HG + a] = acc[a];
         for (int a = 0; a < NZ; ++a) { m[L::M_GGL + a] = acc[NH + a]; m[L::M_DG + a] = acc[NH + NZ + a]; }
         m[L::M_RP] = ra.rp; m[L::M_MU] = ra.sl * p.inv_m; m[L::M_LAM] = ra.lam; m[L::M_HLAM] = ra.hl;
@@ -79,27 +87,27 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
             using CP = Coop<NX>;
             static thread_local typename CP::Lane ln[32];
             static thread_local double xch[CP::kXch];
-            for (int h = 0; h < 32; ++h) { CP::lane_init(p, h, xch, ln[h]); CP::xch_init(h, xch); CP::begin(p, l, s, zero_rec.data(), ln[h]); }
+            LANES(h, 32) { CP::lane_init(p, h, xch, ln[h]); CP::xch_init(h, xch); CP::begin(p, l, s, zero_rec.data(), ln[h]); }
             int type = C::stage_type(p, N);
             for (int k = N - 1; k >= 0; --k) {
                 const int t = C::stage_type(p, k);
-                if (t != type) { type = t; for (int h = 0; h < 32; ++h) CP::load_type(p, t, ln[h]); }
+                if (t != type) { type = t; LANES(h, 32) CP::load_type(p, t, ln[h]); }
                 double* rec = s + l.r2(k);
                 if (k & 1) {
-                    for (int h = 0; h < 32; ++h) CP::template st1<1>(ln[h], rec, k == p.kg);
-                    for (int h = 0; h < 32; ++h) CP::template st2<1>(ln[h]);
+                    LANES(h, 32) CP::template st1<1>(ln[h], rec, k == p.kg);
+                    LANES(h, 32) CP::template st2<1>(ln[h]);
                 } else {
-                    for (int h = 0; h < 32; ++h) CP::template st1<0>(ln[h], rec, k == p.kg);
-                    for (int h = 0; h < 32; ++h) CP::template st2<0>(ln[h]);
+                    LANES(h, 32) CP::template st1<0>(ln[h], rec, k == p.kg);
+                    LANES(h, 32) CP::template st2<0>(ln[h]);
                 }
                 double d1[32];
                 for (int h = 0; h < 32; ++h) d1[h] = ln[h].d1;
-                for (int h = 0; h < 32; ++h)          // kernel: three warp shuffles
+                LANES(h, 32)          // kernel: three warp shuffles
                     CP::st3(ln[h], d1[ln[h].srcA], d1[ln[h].srcB], d1[CP::kFu]);
             }
             bool ok = true;
             double fin[32], rdm = 0.0;
-            for (int h = 0; h < 32; ++h) fin[h] = CP::finish(ln[h]);
+            LANES(h, 32) fin[h] = CP::finish(ln[h]);
             for (int k = 0; k < N; ++k) CP::check_stage(l, s, k, ok, rdm);
             const double ptt = fin[NH - 1], iptt = 1.0 / ptt;
             m[L::M_PIV] = (ok && ptt > 0.0) ? 1.0 : 0.0;
@@ -112,7 +120,7 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         }
         if (cert) {
             if constexpr (NT == 1 && NU == 1 && NX <= 4) {   // blocked Farkas recursion (kernel: lanes = blocks)
-                for (int b = 0; b < l.nb; ++b) C::farkas_p1(p, l, s, b);
+                LANES(b, l.nb) C::farkas_p1(p, l, s, b);
                 C::farkas_p2(p, l, s);
                 double nrm = 0.0, yd = 0.0;
                 for (int b = 0; b < l.nb; ++b) {
@@ -133,34 +141,34 @@ static int solve_one(const HostProblem& hp, const double* dx0, const double* dx_
         if (it >= p.max_iter) break;                     // the last allowed iterate has been tested: status 1
         if constexpr (NT == 1 && NU == 1 && NX <= 4) {   // affine backward substitution rode on the factor sweep
             for (int t = 0; t < l.nb * NX; ++t) C::bwd_p1_T(p, l, s, zero_rec.data(), t);
-            for (int b = 0; b < l.nb; ++b) C::fwd_p1(p, l, s, b, true);
+            LANES(b, l.nb) C::fwd_p1(p, l, s, b, true);
             C::fwd_p2(l, s);
-            for (int b = l.nb - 1; b >= 0; --b) C::fwd_p3(p, l, s, b, true);
+            LANES(b, l.nb) C::fwd_p3(p, l, s, b, true);
         } else {
             solve_sweeps(true, true);
         }
         // ---- phase C: affine step length, sigma, corrector rhs ----
         RedStep rs{0, 0, 0, 0};
-        for (int k = 0; k <= N; ++k) C::affine_stage(p, l, s, k, rs);
+        LANES(k, N + 1) C::affine_stage(p, l, s, k, rs);
         double dg[2 * NZ];
         std::memset(dg, 0, sizeof dg);
-        for (int i = 0; i < p.ng; ++i) C::affine_gen_row(p, l, s, G, hg, i, dg, rs);
+        LANES(i, p.ng) C::affine_gen_row(p, l, s, G, hg, i, dg, rs);
         const double aaff = rs.ratio > 1.0 ? 1.0 / rs.ratio : 1.0;
         const double mu_aff = (rs.s0 + aaff * rs.s1 + aaff * aaff * rs.s2) * p.inv_m;
         const double sr = mu_aff / m[L::M_MU];
         const double sigmu = lb_max(sr * sr * m[L::M_MU], 0.1 * p.tol_mu);
         m[L::M_SIGMU] = sigmu;
-        for (int k = 0; k <= N; ++k) C::corr_stage(p, l, s, k, sigmu);
+        LANES(k, N + 1) C::corr_stage(p, l, s, k, sigmu);
         for (int a = 0; a < NZ; ++a) m[L::M_DG + a] = dg[a] + sigmu * dg[NZ + a];
         // ---- phase D: corrector substitution sweeps ----
         solve_sweeps(false, false);
         // ---- phase E: step length, update ----
         double ratio = 0.0;
-        for (int k = 0; k <= N; ++k) ratio = lb_max(ratio, C::final_stage(p, l, s, k, sigmu));
-        for (int i = 0; i < p.ng; ++i) ratio = lb_max(ratio, C::final_gen_row(p, l, s, G, hg, i, sigmu));
+        LANES(k, N + 1) ratio = lb_max(ratio, C::final_stage(p, l, s, k, sigmu));
+        LANES(i, p.ng) ratio = lb_max(ratio, C::final_gen_row(p, l, s, G, hg, i, sigmu));
         alpha = ratio > 0.0 ? 0.99 / ratio : 1.0;
         if (alpha > 1.0) alpha = 1.0;
-        for (int i = 0; i < p.ng; ++i) C::update_gen_row(p, l, s, G, hg, i, sigmu, alpha);
+        LANES(i, p.ng) C::update_gen_row(p, l, s, G, hg, i, sigmu, alpha);
         for (int t = 0; t < NT; ++t) m[L::M_TH + t] += alpha * m[L::M_DTH + t];
         // the box rows / x / u step is applied at the top of the next pass (update_assemble_stage)
     }

@@ -116,3 +116,24 @@ def test_core_state_and_input_cost_shift(emul_lib, models):
         xonly = OracleProblem(form, variant, mdl, N).solve_batch(X0, cost_shift=e[:, :, :4].copy())
         if form == "F":
             assert np.abs(xonly["uc"] - ref["uc"]).max() > 1e-7          # the input shift does change the F-form problem
+
+
+def test_lane_order_independence_of_every_phase(emul_lib, models):
+    """CPU stand-in for compute-sanitizer racecheck (closed on the GPU pool, profiles/r2_sanitizer_closed.txt): the warp
+    kernel separates its phases with __syncwarp() / shuffles and inside a phase the lanes run concurrently, so no phase may
+    depend on the order of its lanes.  The emulation runs every lane loop (Coop factorisation st1/st2/st3, blocked sweeps
+    P1/P3, Farkas blocks, row phases) forwards and backwards: a write by one lane that another lane of the SAME phase reads
+    would change the result grossly; what remains is the rounding of the reduction order (1e-13)."""
+    for form, variant, N in (("C", "LBMPC", 50), ("F", "LMPC", 20), ("C", "LMPC", 30)):
+        mdl = models[variant]
+        X0 = sample_ics(48, seed=N + 7)
+        emul_lib.emul_set_lane_order(0)
+        a = emul_solve(emul_lib, mdl, form, variant, N, X0)
+        emul_lib.emul_set_lane_order(1)
+        try:
+            b = emul_solve(emul_lib, mdl, form, variant, N, X0)
+        finally:
+            emul_lib.emul_set_lane_order(0)
+        assert np.array_equal(a["status"], b["status"]) and np.abs(a["iters"] - b["iters"]).max() <= 1
+        same = (a["status"] == 0) & (a["iters"] == b["iters"])
+        assert np.abs(a["uc"][same] - b["uc"][same]).max() < 1e-9 and np.abs(a["obj"][same] - b["obj"][same]).max() < 1e-10
