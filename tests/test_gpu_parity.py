@@ -579,3 +579,21 @@ def test_first_order_sqp_matches_oracle_mirror(fx, models, form, twin):
     assert np.median(ref["du_step"][ok, 2]) < 0.1 * np.median(ref["du_step"][ok, 1])    # the outer iteration contracts
     zero = sol.solve_sqp(X0, Xw, Yw, sqp_iters=6, twin=twin, order=0)
     assert np.abs(zero["uc"][ok] - got["uc"][ok]).max() > 1e-6                           # not the same fixed point
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])
+def test_wide_steady_state_range_model(models, kernel):
+    """A model whose feasible theta exceed the old constant bound of the Farkas test (theta' = 100 theta): the engine derives
+    the bound from the polytope block and the state box, like the oracle (tests/test_oracle_golden.py checks the verdicts
+    against an LP); every mapping agrees with it on verdicts, iterations and solutions."""
+    base = models["LBMPC"]
+    mdl = dict(base)
+    mdl["LAMBDA"], mdl["PSI"] = base["LAMBDA"] / 100.0, base["PSI"] / 100.0
+    Fw = base["F_w_N"].copy()
+    Fw[:, 4] /= 100.0
+    mdl["F_w_N"] = Fw
+    X0 = sample_ics(200, seed=6)
+    got = solver(mdl, "C", "LBMPC", 30, max_batch=200, kernel=kernel).solve_batch(X0)
+    ref = OracleProblem("C", "LBMPC", mdl, 30).solve_batch(X0, nthreads=8)
+    assert_parity(got, ref)
+    assert (ref["status"] == 2).any() and np.abs(ref["theta"][ref["status"] == 0]).max() > 10.0

@@ -242,3 +242,28 @@ def test_l2nw_jacobian_matches_finite_differences(fx):
                 h = np.zeros(3); h[c] = 1e-6
                 fd = (oracle_l2nw(X, Y, xi + h, valid) - oracle_l2nw(X, Y, xi - h, valid)) / 2e-6
                 assert np.abs(fd - J[:, c]).max() < 1e-9 * max(1.0, np.abs(J).max()) + 1e-10
+
+
+def test_verdicts_on_a_model_with_a_wide_steady_state_range(models):
+    """Farkas bound on theta: the certificate uses an upper bound of |theta| on the feasible set.  It is
+    derived from the model's own polytope block and state box (lbmpc_problem.hpp / lbo count_rows), not a constant: here the
+    steady-state parametrisation is rescaled (LAMBDA/100, PSI/100, theta column of F_w_N / 100), so feasible theta reach ~98 and optimal ones 20 —
+    beyond the old constant 10 — and verdicts must still agree with an LP feasibility check for every initial state."""
+    from scipy.optimize import linprog
+    base = models["LBMPC"]
+    mdl = dict(base)
+    mdl["LAMBDA"], mdl["PSI"] = base["LAMBDA"] / 100.0, base["PSI"] / 100.0
+    Fw = base["F_w_N"].copy()
+    Fw[:, 4] /= 100.0
+    mdl["F_w_N"] = Fw
+    N = 30
+    X0 = sample_ics(120, seed=6)
+    r = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, nthreads=4)
+    r0 = OracleProblem("C", "LBMPC", base, N).solve_batch(X0, nthreads=4)
+    assert np.array_equal(r["status"], r0["status"]) and set(np.unique(r["status"])) == {0, 2}
+    ok = r["status"] == 0
+    assert np.abs(r["theta"][ok] / 100.0 - r0["theta"][ok]).max() < 1e-7 and np.abs(r["theta"][ok]).max() > 10.0   # same problem, theta' = 100 theta
+    for i in range(0, X0.shape[0], 3):
+        _, _, _, G, h, _ = condensed_qp("C", "LBMPC", mdl, N, X0[i])
+        lp = linprog(np.zeros(G.shape[1]), A_ub=G, b_ub=h, bounds=[(None, None)] * G.shape[1], method="highs")
+        assert (lp.status == 0) == (r["status"][i] == 0), i
