@@ -164,6 +164,11 @@ int lbmpc_oracle_apply(lbmpc_handle *h, int64_t batch, int32_t q, double bandwid
  * independent scenarios: solve, apply the first move to the Moore-Greitzer plant (RK4,
  * DMS_tracking_LMPC_casadi.m:297-304), add a bounded uniform disturbance (RunExample_robust.m:250-252),
  * update the q-sample data window (get_data.m:3-9), shift the warm start (…casadi.m:187-189).
+ * Warm-start shift, stated exactly: the next initial guess is [u_1 .. u_{N-1}, u_{N-1}; theta] (the last input is
+ * repeated).  The reference appends K_loc * x_OL(end-n-m+1:end-m) instead (DMS_tracking_LMPC_casadi.m:187), a slice of the
+ * ABSOLUTE state vector that straddles x_{N-1}(4) and x_N(1:3); that is only IPOPT's starting point and is deliberately not
+ * reproduced: the initial guess changes iteration counts (by at most one in our sweeps), never the minimiser, and oracle
+ * and kernels use the same rule so iteration parity stays exact.
  *   x_init nx x batch (absolute); x_eq nx; wbar nx or NULL;
  *   x_hist nx x (steps+1) x batch OUT; u_hist steps x batch OUT; theta_hist steps x batch OUT;
  *   iters_hist/status_hist steps x batch OUT (any OUT may be NULL).  C-form handles only. */

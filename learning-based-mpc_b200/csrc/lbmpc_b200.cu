@@ -86,6 +86,11 @@ struct lbmpc_handle {
     int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM (default layout)
     int st_warps_cap = 0;              // 6: use the 6-warp variant everywhere (LBMPC_STREAM_WARPS, experiments)
     int max_smem_optin = 0;
+    int64_t st_loop_min_batch = 0;     // fused closed loop picked automatically from this many scenarios (0: only when forced)
+    int st_loop_chunk = 10;            // control steps a lane runs before it hands the scenario back to the queue
+    double* lp_store = nullptr;        // fused closed loop: scenario state between chunks
+    long long* lp_rq = nullptr;        // [0]: tail counter, [1..]: re-queued scenarios
+    size_t lp_store_cap = 0, lp_rq_cap = 0;
     int64_t st_min_batch = 0;          // auto choice: batches at least this large take the stream kernel
     double* st_ws64 = nullptr;
     void* st_wsft = nullptr;
@@ -395,6 +400,9 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         auto optin = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, std::max(smem8, max_smem))); };
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 8>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 8>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 8>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 8>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, double, 8, true>));
+        if (const char* e = getenv("LBMPC_LOOP_CHUNK")) h->st_loop_chunk = std::max(1, atoi(e));
+        if (const char* e = getenv("LBMPC_LOOP_MIN_BATCH")) h->st_loop_min_batch = atoll(e);
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
@@ -759,7 +767,9 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
     const HostProblem& hp = h->hp;
     const size_t b = (size_t)batch, N = hp.N, S = (size_t)steps;
     LoopScratch& L = h->loop;
-    if (L.batch != batch || L.q != q || L.steps != steps) {
+    // scratch is sized by (batch, q); the host-pointer history staging also by the number of steps: reallocated only when one of
+    // them GROWS, so that a short warm-up run followed by the real one does not allocate inside the timed call
+    if (L.batch < batch || L.q != q || (!h->dev_ptrs && L.steps < steps)) {
         free_loop(L);
         CU_TRY(dmalloc(&L.x, b * 4)); CU_TRY(dmalloc(&L.dx0, b * 4)); CU_TRY(dmalloc(&L.X, b * 3 * q));
         CU_TRY(dmalloc(&L.Y, b * 4 * q)); CU_TRY(dmalloc(&L.V, b * q)); CU_TRY(dmalloc(&L.warm, b * (N + 1)));
@@ -775,6 +785,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
     CU_TRY(cudaMemsetAsync(L.X, 0, 8 * b * 3 * q, st));
     CU_TRY(cudaMemsetAsync(L.Y, 0, 8 * b * 4 * q, st));
     CU_TRY(cudaMemsetAsync(L.V, 0, 8 * b * q, st));
+    CU_TRY(cudaMemsetAsync(L.warm, 0, 8 * b * (N + 1), st));
     const double* xi_dev = x_init;
     if (!h->dev_ptrs) {
         CU_TRY(cudaMemcpyAsync(L.x_init, x_init, 8 * b * 4, cudaMemcpyHostToDevice, st));
@@ -794,12 +805,58 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
         Sx.theta_hist = theta_hist ? L.t_hist : nullptr; Sx.iters_hist = iters_hist ? L.i_hist : nullptr;
         Sx.status_hist = status_hist ? L.s_hist : nullptr;
     }
+    // Fused closed loop (stream mapping): one persistent kernel runs every control step of every scenario.  Picked when
+    // the stream mapping is forced, or automatically for scenario counts where it measures faster than one oracle / solve /
+    // plant launch triple per step.
+    const bool fused = h->shape == 0 && h->st_ctas_per_sm > 0 && hp.ng <= 64 && q <= 512 &&
+                       (h->force_kernel == LBMPC_KERNEL_STREAM ||
+                        (h->force_kernel == LBMPC_KERNEL_AUTO && h->st_loop_min_batch > 0 && batch >= h->st_loop_min_batch));
+    if (fused) {
+        constexpr int kW = 8;
+        using SK = Stream<4, false, double, 32>;
+        const Params<4, 1, 1> p = to_params<4, 1, 1>(hp);
+        const StreamLayout<4> l(p.N, p.ng, false, false, q);
+        const int chunk = std::max(1, std::min<int>(steps, h->st_loop_chunk));
+        const int nchunks = (steps + chunk - 1) / chunk;
+        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(h->num_sms, (batch + 32 * kW - 1) / (32 * kW)));
+        CU_TRY(stream_workspace(h, ctas * kW, l, false));
+        const size_t slen = (size_t)SK::store_len(l), store_n = (size_t)batch * slen, rq_n = (size_t)batch * (size_t)std::max(nchunks - 1, 1);
+        if (h->lp_store_cap < store_n) {
+            cudaFree(h->lp_store); h->lp_store = nullptr; h->lp_store_cap = 0;
+            CU_TRY(dmalloc(&h->lp_store, store_n));
+            h->lp_store_cap = store_n;
+        }
+        if (h->lp_rq_cap < rq_n + 1) {
+            cudaFree(h->lp_rq); h->lp_rq = nullptr; h->lp_rq_cap = 0;
+            CU_TRY(dmalloc(&h->lp_rq, rq_n + 1));
+            h->lp_rq_cap = rq_n + 1;
+        }
+        CU_TRY(cudaMemsetAsync(h->lp_rq, 0, sizeof(long long) * (rq_n + 1), st));
+        StreamLoopParams lp{};
+        lp.steps = steps; lp.chunk = chunk; lp.warm_shift = warm_shift; lp.use_oracle = use_oracle; lp.use_w = wbar != nullptr;
+        lp.nscen = batch; lp.u_eq = u_eq; lp.inv_h2 = 1.0 / (0.5 * 0.5); lp.lambda = 0.001; lp.seed = seed; lp.scen0 = scenario0;
+        for (int j = 0; j < 4; ++j) { lp.x_eq[j] = x_eq[j]; lp.wbar[j] = wbar ? wbar[j] : 0.0; }
+        lp.x_init = xi_dev; lp.x_hist = Sx.x_hist; lp.u_hist = Sx.u_hist; lp.theta_hist = Sx.theta_hist;
+        lp.iters_hist = Sx.iters_hist; lp.status_hist = Sx.status_hist;
+        lp.store = h->lp_store; lp.rq = h->lp_rq + 1; lp.rq_tail = reinterpret_cast<unsigned long long*>(h->lp_rq);
+        StreamIO<double> sio{};
+        sio.batch = batch; sio.queue = next_queue(h); sio.ws64 = h->st_ws64; sio.wsft = (double*)h->st_wsft; sio.qwin = q;
+        CU_TRY(cudaMemsetAsync(sio.queue, 0, sizeof(unsigned long long), st));
+        const size_t smem = kW * StreamSmem<4, double>::warp_bytes(false, false);
+        CU_TRY(cudaEventRecord(h->ev0, st));
+        ipm_stream_kernel<4, false, double, kW, true><<<(unsigned)ctas, 32 * kW, smem, st>>>(p, sio, h->dG, h->dhg, lp);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+        h->launches += 1;
+        h->last_kernel = LBMPC_KERNEL_STREAM;
+    }
     const unsigned tg = (unsigned)((batch + 127) / 128);
-    loop_init_kernel<<<tg, 128, 0, st>>>(Sx, xi_dev, batch, steps, xe);
-    h->launches += 1;
+    if (!fused) loop_init_kernel<<<tg, 128, 0, st>>>(Sx, xi_dev, batch, steps, xe);
+    if (!fused) h->launches += 1;
     CU_TRY(cudaGetLastError());
     const double inv_h2 = 1.0 / (0.5 * 0.5);  // oracleL2NW.m:9 bandwidth = 0.5
-    for (int it = 0; it < steps; ++it) {
+    for (int it = 0; it < steps && !fused; ++it) {
         const bool have = it > 0;
         if (use_oracle && have) {
             launch_oracle(h, st, batch, q, inv_h2, 0.001, L.dx0, L.warm, (long long)(N + 1), L.X, L.Y, L.V, L.doff);
@@ -905,6 +962,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh); cudaFree(h->q_jac);
     cudaFree(h->st_ws64); cudaFree(h->st_wsft);
     for (int i = 0; i < 6; ++i) cudaFree(h->og[i]);
+    cudaFree(h->lp_store); cudaFree(h->lp_rq);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -801,7 +801,13 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
         x[j] = S.x[b * 4 + j];
         dx[j] = x[j] - xe[j];
     }
-    const double du0 = S.uc[b * N], u0 = du0 + u_eq;
+    // no optimal solution (infeasible / iteration cap): keep executing the last optimal plan = the shifted previous plan that
+    // was this step's warm start (zero before any plan exists); the same rule as oracle/lbmpc_oracle.c lbo_closed_loop
+    const bool ok = S.status[b] == 0;
+    double* wm = S.warm + b * (N + 1);
+    const double* plan = ok ? S.uc + b * N : wm;
+    const double th_plan = ok ? S.theta[b] : wm[N];
+    const double du0 = plan[0], u0 = du0 + u_eq;
     double k1[4], k2[4], k3[4], k4[4], t[4], xn[4];
     const double delta = 0.01;
     mg_rhs(x, u0, k1);
@@ -852,11 +858,11 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
     for (int a = 0; a < 4; ++a) Yb[nd * 4 + a] = ys[a];
     Vb[nd] = 1.0;
     S.nd[b] = nd + 1;
-    // warm-start shift
-    double* wm = S.warm + b * (N + 1);
-    for (int k = 0; k + 1 < N; ++k) wm[k] = S.uc[b * N + k + 1];
-    wm[N - 1] = S.uc[b * N + N - 1];
-    wm[N] = S.theta[b];
+    // warm-start shift (in place when the plan is the previous warm start)
+    const double last = plan[N - 1];
+    for (int k = 0; k + 1 < N; ++k) wm[k] = plan[k + 1];
+    wm[N - 1] = last;
+    wm[N] = th_plan;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         S.x[b * 4 + j] = xn[j];
@@ -864,7 +870,7 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
         if (S.x_hist) S.x_hist[(b * (steps + 1) + step + 1) * 4 + j] = xn[j];
     }
     if (S.u_hist) S.u_hist[b * steps + step] = u0;
-    if (S.theta_hist) S.theta_hist[b * steps + step] = S.theta[b];
+    if (S.theta_hist) S.theta_hist[b * steps + step] = th_plan;
     if (S.iters_hist) S.iters_hist[b * steps + step] = S.iters[b];
     if (S.status_hist) S.status_hist[b * steps + step] = S.status[b];
 }

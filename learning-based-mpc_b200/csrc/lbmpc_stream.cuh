@@ -60,9 +60,15 @@ struct StreamLayout {
     static constexpr int kPolyChunk = 16;  // polytope rows fetched per pipeline item
     static constexpr int NJ = NX * 3;  // LTV: Jacobian of the learned term w.r.t. xi = [x1; x2; u] per stage
     int N, ng, o_it, o_q, o_cs, o_j, o_sg, o_lg, n64, nft;  // offsets / sizes in elements (per QP)
-    LB_HD StreamLayout(int N_, int ng_, bool cs, bool ltv) {
+    int o_loop, qwin;  // fused closed loop: plant state x[NX], current plan [u (N); theta], data ring X[3 qwin], Y[NX qwin]
+    LB_HD int lp_x() const { return o_loop; }
+    LB_HD int lp_plan() const { return o_loop + NX; }
+    LB_HD int lp_X() const { return o_loop + NX + N + 1; }
+    LB_HD int lp_Y() const { return o_loop + NX + N + 1 + 3 * qwin; }
+    LB_HD StreamLayout(int N_, int ng_, bool cs, bool ltv, int qwin_ = 0) {
         N = N_;
         ng = ng_;
+        qwin = qwin_;
         int o = 0;
         o_it = o; o += RS_IT * (N + 1);
         o_q = o;  o += RS_Q * (N + 1);
@@ -70,6 +76,7 @@ struct StreamLayout {
         o_j = o;  o += ltv ? NJ * N : 0;
         o_sg = o; o += ng;
         o_lg = o; o += ng;
+        o_loop = o; o += qwin > 0 ? NX + N + 1 + (3 + NX) * qwin : 0;
         n64 = o;
         nft = RS_D * (N + 1);
     }
@@ -95,6 +102,7 @@ struct StreamIO {  // batch-major caller arrays (include/lbmpc.h)
     const double *dx0, *dx_ref, *d_off, *warm, *cshift, *jac;
     int cs_stride;  // doubles per stage of cshift: NX (state shift) or NX + 1 (state and input shift)
     int row_shift;  // 0: cshift moves the COST; 1: it moves the ROWS (they act on x_k - ex_k, u_k - eu_k; first-order SQP)
+    int qwin;       // fused closed loop: data window length (0 otherwise)
     double *uc, *theta, *xtraj, *obj;
     int *iters, *status;
     unsigned long long* queue;
@@ -160,6 +168,20 @@ struct StreamPipeDirect {
         v.lg = w64 + l->o_lg * LS;
         return v;
     }
+};
+
+// fused closed loop: parameters and caller arrays (include/lbmpc.h lbmpc_closed_loop)
+struct StreamLoopParams {
+    int steps, chunk, warm_shift, use_oracle, use_w;
+    long long nscen;
+    double x_eq[4], u_eq, wbar[4], inv_h2, lambda;
+    unsigned long long seed, scen0;
+    const double* x_init;                      // NX x nscen, absolute plant states
+    double *x_hist, *u_hist, *theta_hist;      // histories (any may be null)
+    int *iters_hist, *status_hist;
+    double* store;                             // nscen x store_len: scenario state between chunks
+    long long* rq;                             // re-queued scenarios, entry = scenario + 1 (0: not produced yet)
+    unsigned long long* rq_tail;
 };
 
 template <int NX, bool LTV, typename FT, int LS>
@@ -331,7 +353,7 @@ struct Stream {
         const bool fresh = ln.fresh;
         const double alpha = fresh ? 0.0 : ln.alpha, sigmu = ln.sigmu;
         const double th_old = ln.th;
-        ln.th = th_old + alpha * ln.dth;
+        ln.th = fresh ? th_old : th_old + alpha * ln.dth;
         const double th = ln.th;
         double Pm[NH], pv[NZ], pi[NZ], pc[NZ];
         double HG[NH], gGl[NZ], dG[NZ];
@@ -904,6 +926,192 @@ struct Stream {
     }
 
     // ============================================================================================
+    // Fused closed loop (ocpLBMPC.m:10-47, LBMPC_casadi.m:160-223): a lane owns a scenario for a CHUNK of
+    // control steps and, between two solves, does everything the reference's loop body does besides the solve — first move
+    // to the RK4 plant (DMS_tracking_LMPC_casadi.m:297-304), bounded uniform disturbance, data window (a ring: no O(q) shift),
+    // warm-start shift, learned-model rollout with the L2NW oracle for the next QP's offsets — thread-locally, without
+    // leaving the kernel.  Scenario state between chunks lives in a per-scenario store (any lane may continue a scenario).
+    // ============================================================================================
+    static LB_HD void mg_rhs_s(const double* x, double u, double* f) {  // trueModel.m:21-41
+        f[0] = -x[1] + 1.0 + 3.0 * (x[0] / 2.0) - (x[0] * x[0] * x[0] / 2.0);
+        f[1] = x[0] + 1.0 - x[2] * sqrt(x[1]);
+        f[2] = x[3];
+        f[3] = -1000.0 * x[2] - 2.0 * sqrt(500.0) * x[3] + 1000.0 * u;
+    }
+    static LB_HD double uniform_s(unsigned long long seed, unsigned long long scen, unsigned long long step, unsigned long long comp) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (scen * 0x100000001B3ULL + step * 8ULL + comp + 1ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+    struct LoopLane {      // scenario bookkeeping of a lane (registers)
+        long long sc;      // scenario, -1: none
+        long long ticket;  // queue ticket held while waiting for a re-queued scenario, -1: none
+        int t, nd, head;   // control step, samples in the window, next ring slot
+        bool cont;         // the scenario continues: set up the next QP at the refill point
+    };
+    // store <-> workspace; store record: nd head t | x[NX] plan[N+1] X[3 q] Y[NX q] (the loop region of the workspace, verbatim)
+    static LB_HD int store_len(const SL& l) { return 3 + NX + l.N + 1 + (3 + NX) * l.qwin; }
+    static LB_HD void loop_spill(const SL& l, const LoopLane& ll, const double* w64, double* st) {
+        st[0] = (double)ll.nd; st[1] = (double)ll.head; st[2] = (double)ll.t;
+        const int n = store_len(l) - 3;
+        for (int i = 0; i < n; ++i) st[3 + i] = ld(w64, l.o_loop + i);
+    }
+    static LB_HD void loop_restore(const SL& l, LoopLane& ll, double* w64, const double* st) {
+        ll.nd = (int)st[0]; ll.head = (int)st[1]; ll.t = (int)st[2];
+        const int n = store_len(l) - 3;
+        for (int i = 0; i < n; ++i) st_(w64, l.o_loop + i, st[3 + i]);
+    }
+    static LB_HD void st_(double* p, int e, double v) { p[e * LS] = v; }
+    // a fresh scenario
+    template <class LP>
+    static LB_HD void loop_begin(const SL& l, const LP& lp, Lane& ln, LoopLane& ll, double* w64, long long sc) {
+        ll.sc = sc; ll.t = 0; ll.nd = 0; ll.head = 0;
+        (void)ln;
+        for (int j = 0; j < NX; ++j) {
+            const double v = lp.x_init[sc * NX + j];
+            st_(w64, l.lp_x() + j, v);
+            if (lp.x_hist) lp.x_hist[(sc * (lp.steps + 1)) * NX + j] = v;
+        }
+        for (int k = 0; k <= l.N; ++k) st_(w64, l.lp_plan() + k, 0.0);
+    }
+    // set up the QP of control step ll.t: oracle offsets along the learned rollout of the plan, initial rollout -> iterate record
+    // lane state of the QP of control step ll.t (the iterate record is filled by loop_start_step / its warp-cooperative form)
+    template <class LP>
+    static LB_HD void loop_lane_reset(const P& p, const SL& l, const LP& lp, Lane& ln, const LoopLane& ll, const double* w64) {
+        ln.q = ll.sc;
+        ln.iters = 0;
+        ln.fresh = true;
+        ln.alpha = ln.sigmu = ln.dth = ln.dtha = 0.0;
+        ln.cconst = 0.0;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) ln.lin[a] = ln.gGl[a] = ln.dG1[a] = ln.dG2[a] = 0.0;
+        const bool warm = lp.warm_shift && ll.t > 0;
+        ln.th = warm ? ld(w64, l.lp_plan() + p.N) : 0.0;
+    }
+    template <class LP>
+    static LB_HD void loop_start_step(const P& p, const SL& l, const LP& lp, Lane& ln, const LoopLane& ll, double* w64) {
+        const int N = p.N;
+        loop_lane_reset(p, l, lp, ln, ll, w64);
+        const bool warm = lp.warm_shift && ll.t > 0;
+        double x[NX], xo[NX];  // x: rollout of the QP's starting point; xo: learned rollout of the plan (oracle arguments)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = xo[j] = ld(w64, l.lp_x() + j) - lp.x_eq[j];
+        const bool orc = lp.use_oracle && ll.nd > 0;
+        for (int k = 0; k <= N; ++k) {
+            double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) st_(it, SL::F_X + j, x[j]);
+            if (k == N) break;
+            const double pk = ld(w64, l.lp_plan() + k);
+            double g[NX];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) g[a] = 0.0;
+            if (orc) {  // g([x1;x2;u]) = sum_i Y_i k_i / (lambda + sum_i k_i), oracleL2NW.m:26-36
+                double sk = 0.0;
+                for (int i = 0; i < ll.nd; ++i) {
+                    const double d0 = ld(w64, l.lp_X() + 3 * i) - xo[0], d1 = ld(w64, l.lp_X() + 3 * i + 1) - xo[1],
+                                 d2 = ld(w64, l.lp_X() + 3 * i + 2) - pk;
+                    const double kv = exp(-(d0 * d0 + d1 * d1 + d2 * d2) * lp.inv_h2);
+                    sk += kv;
+#pragma unroll
+                    for (int a = 0; a < NX; ++a) g[a] += ld(w64, l.lp_Y() + NX * i + a) * kv;
+                }
+                const double wn = 1.0 / (lp.lambda + sk);
+#pragma unroll
+                for (int a = 0; a < NX; ++a) g[a] *= wn;
+            }
+            const double u = warm ? pk : 0.0;
+            st_(it, SL::F_U, u);
+            double xn[NX], xon[NX];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) {
+                double v = g[a] + p.B[a] * u, w = g[a] + p.B[a] * pk;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    v += p.A[a * NX + j] * x[j];
+                    w += p.A[a * NX + j] * xo[j];
+                }
+                xn[a] = v;
+                xon[a] = w;
+            }
+#pragma unroll
+            for (int a = 0; a < NX; ++a) {
+                x[a] = xn[a];
+                xo[a] = xon[a];
+            }
+        }
+    }
+    // the QP of step ll.t has its verdict: apply the first move, advance plant / window / plan / histories
+    template <class LP>
+    static LB_HD void loop_advance(const P& p, const SL& l, const LP& lp, Lane& ln, LoopLane& ll, double* w64, int status) {
+        const int N = p.N;
+        const bool ok = status == 0;
+        // no optimal solution: keep executing the last optimal plan (same rule as plant_kernel / lbo_closed_loop)
+        const double du0 = ok ? ld(w64 + (l.o_it) * LS, SL::F_U) : ld(w64, l.lp_plan());
+        double x[NX], dx[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            x[j] = ld(w64, l.lp_x() + j);
+            dx[j] = x[j] - lp.x_eq[j];
+        }
+        const double u0 = du0 + lp.u_eq, delta = 0.01;
+        double k1[NX], k2[NX], k3[NX], k4[NX], tt[NX], xn[NX];
+        mg_rhs_s(x, u0, k1);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tt[i] = x[i] + delta / 2 * k1[i];
+        mg_rhs_s(tt, u0, k2);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tt[i] = x[i] + delta / 2 * k2[i];
+        mg_rhs_s(tt, u0, k3);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tt[i] = x[i] + delta * k3[i];
+        mg_rhs_s(tt, u0, k4);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = x[i] + delta / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+        if (lp.use_w) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                xn[j] += lp.wbar[j] * (2.0 * uniform_s(lp.seed, lp.scen0 + (unsigned long long)ll.sc, (unsigned long long)ll.t, (unsigned long long)j) - 1.0);
+        }
+        // data acquisition (ocpLBMPC.m:14-15): X = [dx1;dx2;du], Y = dx+ - (A dx + B du); ring slot `head`
+        {
+            const int slot = ll.head;
+            st_(w64, l.lp_X() + 3 * slot, dx[0]);
+            st_(w64, l.lp_X() + 3 * slot + 1, dx[1]);
+            st_(w64, l.lp_X() + 3 * slot + 2, du0);
+#pragma unroll
+            for (int a = 0; a < NX; ++a) {
+                double v = xn[a] - lp.x_eq[a] - p.B[a] * du0;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) v -= p.A[a * NX + j] * dx[j];
+                st_(w64, l.lp_Y() + NX * slot + a, v);
+            }
+            ll.head = slot + 1 == l.qwin ? 0 : slot + 1;
+            ll.nd = ll.nd < l.qwin ? ll.nd + 1 : ll.nd;
+        }
+        // plan <- shift of (solution | previous plan), last input repeated
+        if (ok) {
+            for (int k = 0; k + 1 < N; ++k) st_(w64, l.lp_plan() + k, ld(w64 + (l.o_it + (k + 1) * SL::RS_IT) * LS, SL::F_U));
+            st_(w64, l.lp_plan() + N - 1, ld(w64 + (l.o_it + (N - 1) * SL::RS_IT) * LS, SL::F_U));
+            st_(w64, l.lp_plan() + N, ln.th);
+        } else {
+            for (int k = 0; k + 1 < N; ++k) st_(w64, l.lp_plan() + k, ld(w64, l.lp_plan() + k + 1));
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            st_(w64, l.lp_x() + j, xn[j]);
+            if (lp.x_hist) lp.x_hist[(ll.sc * (lp.steps + 1) + ll.t + 1) * NX + j] = xn[j];
+        }
+        if (lp.u_hist) lp.u_hist[ll.sc * lp.steps + ll.t] = u0;
+        if (lp.theta_hist) lp.theta_hist[ll.sc * lp.steps + ll.t] = ld(w64, l.lp_plan() + N);
+        if (lp.iters_hist) lp.iters_hist[ll.sc * lp.steps + ll.t] = ln.iters;
+        if (lp.status_hist) lp.status_hist[ll.sc * lp.steps + ll.t] = status;
+        ll.t += 1;
+    }
+
+    // ============================================================================================
     // results of a finished QP: c = u - Kout x (transitionNominal.m:12 undone), theta, objective
     // ============================================================================================
     static LB_HD void finish(const P& p, const SL& l, const Lane& ln, const StreamIO<FT>& io, const double* w64, int status) {
@@ -929,6 +1137,37 @@ struct Stream {
         io.obj[q] = ln.obj;
         io.iters[q] = ln.iters;
         io.status[q] = status;
+    }
+
+    // one whole scenario by one lane, chunk by chunk through the store (tests/emul; the kernel adds the ticket queue)
+    static LB_HD void loop_one(const P& p, const SL& l, const StreamLoopParams& lp, long long sc, const double* G, const double* hg,
+                               double* w64, FT* wft, double* store_rec) {
+        Lane ln;
+        LoopLane ll;
+        StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
+        loop_begin(l, lp, ln, ll, w64, sc);
+        while (ll.t < lp.steps) {
+            loop_start_step(p, l, lp, ln, ll, w64);
+            for (;;) {
+                int st = pass_bu(p, l, ln, G, hg, w64, wft, false, false, pp);
+                if (st < 0 && ln.iters >= p.max_iter) st = 1;
+                if (st >= 0) {
+                    loop_advance(p, l, lp, ln, ll, w64, st);
+                    break;
+                }
+                pass_f1(p, l, ln, G, hg, w64, wft, false, false, pp);
+                pass_b2(p, l, ln, wft, pp);
+                pass_f2(p, l, ln, G, hg, w64, wft, false, false, pp);
+                ln.iters += 1;
+                ln.fresh = false;
+            }
+            if (ll.t < lp.steps && ll.t % lp.chunk == 0) {  // chunk boundary: the state travels through the store
+                loop_spill(l, ll, w64, store_rec);
+                for (int i = 0; i < store_len(l) - 3; ++i) st_(w64, l.o_loop + i, -7.0);
+                ll.nd = ll.head = ll.t = -1;
+                loop_restore(l, ll, w64, store_rec);
+            }
+        }
     }
 
     // one whole solve by one lane (tests/emul; the kernel interleaves the same calls with the queue logic)
@@ -1054,6 +1293,76 @@ struct StreamPipeTma {
     }
 };
 
+// Warp-cooperative set-up of the next QP of ONE lane of the warp (fused closed loop).  The learned-model rollout evaluates
+// the L2NW oracle N times over the q-sample window; done by the owning lane alone it is N q exponentials executed with 31
+// idle lanes, and with ~4 of 32 lanes finishing a QP per iteration that would cost as much as the iteration itself.  Here
+// the 32 lanes take the data points (like oracle_kernel) and reduce with shuffles; every lane carries the rollout, lane
+// `b`'s workspace column receives the iterate.  Same arithmetic as Stream::loop_start_step up to the order of the sums.
+template <int NX, typename S, typename LP>
+__device__ __forceinline__ void stream_loop_start_step_coop(const Params<NX, 1, 1>& p, const StreamLayout<NX>& l, const LP& lp, int b,
+                                                            int lane, bool warm, int nd, double* w64_lane0) {
+    using SL = StreamLayout<NX>;
+    const int N = p.N;
+    double* const wb = w64_lane0 + b;  // lane b's column
+    auto ldb = [&](int e) { return wb[e * 32]; };
+    double x[NX], xo[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = xo[j] = ldb(l.lp_x() + j) - lp.x_eq[j];
+    const bool orc = lp.use_oracle && nd > 0;
+    constexpr int PER = 16;  // q <= 512
+    const int per = (nd + 31) / 32;
+    for (int k = 0; k <= N; ++k) {
+        double* it = wb + (l.o_it + k * SL::RS_IT) * 32;
+        if (lane < NX) {
+            double v = x[0];
+#pragma unroll
+            for (int j = 1; j < NX; ++j) v = lane == j ? x[j] : v;
+            it[(SL::F_X + lane) * 32] = v;
+        }
+        if (k == N) break;
+        const double pk = ldb(l.lp_plan() + k);
+        double g[NX], sk = 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) g[a] = 0.0;
+        if (orc) {
+            for (int r = 0; r < per && r < PER; ++r) {
+                const int i = lane + 32 * r;
+                if (i < nd) {
+                    const double d0 = ldb(l.lp_X() + 3 * i) - xo[0], d1 = ldb(l.lp_X() + 3 * i + 1) - xo[1],
+                                 d2 = ldb(l.lp_X() + 3 * i + 2) - pk;
+                    const double kv = exp(-(d0 * d0 + d1 * d1 + d2 * d2) * lp.inv_h2);
+                    sk += kv;
+#pragma unroll
+                    for (int a = 0; a < NX; ++a) g[a] += ldb(l.lp_Y() + NX * i + a) * kv;
+                }
+            }
+            sk = warp_sum(sk);
+            const double wn = 1.0 / (lp.lambda + sk);
+#pragma unroll
+            for (int a = 0; a < NX; ++a) g[a] = warp_sum(g[a]) * wn;
+        }
+        const double u = warm ? pk : 0.0;
+        if (lane == 0) it[SL::F_U * 32] = u;
+        double xn[NX], xon[NX];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            double v = g[a] + p.B[a] * u, w = g[a] + p.B[a] * pk;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                v += p.A[a * NX + j] * x[j];
+                w += p.A[a * NX + j] * xo[j];
+            }
+            xn[a] = v;
+            xon[a] = w;
+        }
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+            x[a] = xn[a];
+            xo[a] = xon[a];
+        }
+    }
+}
+
 // generic-proxy stores to the workspace (this pass) -> async-proxy reads (bulk copies of the next pass)
 __device__ __forceinline__ void stream_pass_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -1069,17 +1378,19 @@ __device__ __forceinline__ void stream_pass_fence() { asm volatile("fence.proxy.
 // (cta_tick, lbmpc_kernels.cuh: it also counts the warps that still have work, so that the CTA leaves together).
 // WARPS per CTA (one CTA per SM): 8 at 255 registers per thread, or 6 when the double buffers of 8 warps do not fit shared
 // memory (LTV Jacobians + shift record).  12 warps at 168 registers measured 1.5x slower (spills in pass BU).
-template <int NX, bool LTV, typename FT, int WARPS>
+// LOOP: fused closed loop — the work items are (scenario, chunk of control steps) tickets; a lane sets up, solves and advances
+// the control steps of its chunk back to back and hands the scenario over through the store + the re-queue ring.
+template <int NX, bool LTV, typename FT, int WARPS, bool LOOP = false>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT> io, const double* __restrict__ G,
-                  const double* __restrict__ hg) {
+                  const double* __restrict__ hg, const StreamLoopParams lp = StreamLoopParams{}) {
     using S = Stream<NX, LTV, FT, 32>;
     using SM = StreamSmem<NX, FT>;
     extern __shared__ __align__(128) unsigned char stream_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
-    const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV);
+    const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV, LOOP ? io.qwin : 0);
     double* const w64 = io.ws64 + warp * (long long)l.n64 * 32 + lane;
     FT* const wft = io.wsft + warp * (long long)l.nft * 32 + lane;
     StreamPipeTma<NX, LTV, FT> pp;
@@ -1105,28 +1416,101 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     ln.fresh = true;
     ln.th = ln.dth = ln.dtha = ln.alpha = ln.sigmu = ln.iptt = ln.mu = 0.0;
     bool drained = false;  // warp-uniform: the queue has run dry
+    typename S::LoopLane ll;
+    ll.sc = ll.ticket = -1;
+    ll.t = ll.nd = ll.head = 0;
+    ll.cont = false;
+    bool lane_done = false;  // LOOP: this lane's ticket was beyond the last chunk
+    const int nchunks = LOOP ? (lp.steps + lp.chunk - 1) / lp.chunk : 0;
+    const long long n_tickets = LOOP ? lp.nscen * nchunks : 0;
+    const int slen = LOOP ? S::store_len(l) : 0;
     for (;;) {
-        const bool need = ln.q < 0;
-        const unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, need);
-        if (want) {
-            unsigned long long base = 0;
-            const int leader = __ffs(want) - 1;
-            if (lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(want));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            const long long mine = (long long)base + __popc(want & ((1u << lane) - 1u));
-            if (need && mine < io.batch) S::init_qp(p, l, ln, io, mine, w64, has_cs);
-            drained = (long long)base + __popc(want) >= io.batch;
+        bool working;
+        if constexpr (LOOP) {
+            const bool need = ln.q < 0 && !ll.cont && ll.ticket < 0 && !lane_done;
+            const unsigned want = __ballot_sync(0xffffffffu, need);
+            if (want) {
+                unsigned long long base = 0;
+                const int leader = __ffs(want) - 1;
+                if (lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) {
+                    ll.ticket = (long long)base + __popc(want & ((1u << lane) - 1u));
+                    if (ll.ticket >= n_tickets) {
+                        lane_done = true;
+                        ll.ticket = -1;
+                    }
+                }
+            }
+            if (ln.q < 0 && !ll.cont && ll.ticket >= 0) {
+                if (ll.ticket < lp.nscen) {  // first chunk of a scenario
+                    S::loop_begin(l, lp, ln, ll, w64, ll.ticket);
+                    ll.cont = true;
+                    ll.ticket = -1;
+                } else {                     // a re-queued scenario: wait (without blocking the warp) until it has been produced
+                    const long long e = *reinterpret_cast<volatile long long*>(lp.rq + (ll.ticket - lp.nscen));
+                    if (e != 0) {
+                        __threadfence();
+                        ll.sc = e - 1;
+                        S::loop_restore(l, ll, w64, lp.store + ll.sc * (long long)slen);
+                        ll.cont = true;
+                        ll.ticket = -1;
+                    }
+                }
+            }
+            {   // set up the next QP of every lane that continues its scenario: one lane at a time, the whole warp on its rollout
+                unsigned todo = __ballot_sync(0xffffffffu, ln.q < 0 && ll.cont);
+                while (todo) {
+                    const int b = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int t_b = __shfl_sync(0xffffffffu, ll.t, b), nd_b = __shfl_sync(0xffffffffu, ll.nd, b);
+                    stream_loop_start_step_coop<NX, S>(p, l, lp, b, lane, lp.warm_shift && t_b > 0, nd_b, w64 - lane);
+                }
+                __syncwarp();
+                if (ln.q < 0 && ll.cont) {
+                    S::loop_lane_reset(p, l, lp, ln, ll, w64);
+                    ll.cont = false;
+                }
+            }
             stream_pass_fence();
+            working = !__all_sync(0xffffffffu, ln.q < 0);
+            const bool alive = !__all_sync(0xffffffffu, lane_done && ln.q < 0);
+            if (cta_tick(alive) == 0) break;
+        } else {
+            const bool need = ln.q < 0;
+            const unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, need);
+            if (want) {
+                unsigned long long base = 0;
+                const int leader = __ffs(want) - 1;
+                if (lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const long long mine = (long long)base + __popc(want & ((1u << lane) - 1u));
+                if (need && mine < io.batch) S::init_qp(p, l, ln, io, mine, w64, has_cs);
+                drained = (long long)base + __popc(want) >= io.batch;
+                stream_pass_fence();
+            }
+            working = !__all_sync(0xffffffffu, ln.q < 0);
+            if (cta_tick(working) == 0) break;  // every warp of the CTA is out of work
         }
-        bool working = !__all_sync(0xffffffffu, ln.q < 0);
-        if (cta_tick(working) == 0) break;  // every warp of the CTA is out of work
         if (working) {
             int st = S::pass_bu(p, l, ln, G, hg, w64, wft, has_cs, rsh, pp);
             stream_pass_fence();
             if (ln.q >= 0) {
                 if (st < 0 && ln.iters >= p.max_iter) st = 1;
                 if (st >= 0) {
-                    S::finish(p, l, ln, io, w64, st);
+                    if constexpr (LOOP) {
+                        S::loop_advance(p, l, lp, ln, ll, w64, st);
+                        if (ll.t < lp.steps && ll.t % lp.chunk == 0) {  // chunk done: hand the scenario over
+                            S::loop_spill(l, ll, w64, lp.store + ll.sc * (long long)slen);
+                            __threadfence();
+                            const unsigned long long idx = atomicAdd(lp.rq_tail, 1ULL);
+                            *reinterpret_cast<volatile long long*>(lp.rq + idx) = ll.sc + 1;
+                        } else if (ll.t < lp.steps) {
+                            ll.cont = true;
+                        }
+                    } else {
+                        S::finish(p, l, ln, io, w64, st);
+                    }
                     ln.q = -1;
                 }
             }

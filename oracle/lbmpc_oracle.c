@@ -1147,6 +1147,12 @@ int lbo_closed_loop(const lbo_problem *p, const double *x_eq, double u_eq, const
         }
         double J; int iters, st;
         lbo_solve(p, dx0, NULL, dptr, (warm_shift && have_warm) ? warm : NULL, uc, th, xtraj, &J, &iters, &st, NULL);
+        /* A QP without an optimal solution (infeasible: the disturbance pushed the state out of the robust set; or the
+         * iteration cap) has no first move to apply: the loop then keeps executing the LAST OPTIMAL plan, i.e. applies the
+         * first element of the shifted previous plan (zero before any plan exists) and keeps shifting it.  The reference
+         * discards the solver status and would apply IPOPT's last iterate. */
+        const int ok = (st == LBO_ST_OPTIMAL);
+        if (!ok) { memcpy(uc, warm, sizeof(double) * (size_t)N * nu); th[0] = warm[N * nu]; }
         const double u0 = uc[0] + u_eq; /* C-form: uc = du */
         double xn[4];
         lbo_plant_rk4(x, u0, 0.01, xn);

@@ -255,3 +255,27 @@ extern "C" int emul_stream_solve_batch(const lbmpc_model* mdl, const lbmpc_confi
     else     { if (f32) run(float(), std::false_type()); else run(double(), std::false_type()); }
     return 0;
 }
+
+
+// fused closed loop of the stream mapping, one scenario at a time (lane stride 1), chunked through the scenario store
+extern "C" int emul_stream_closed_loop(const lbmpc_model* mdl, const lbmpc_config* cfg, long nscen, int steps, int q, int chunk,
+                                       int use_oracle, int warm_shift, const double* x_eq, double u_eq, const double* x_init,
+                                       const double* wbar, unsigned long long seed, unsigned long long scen0, double* x_hist,
+                                       double* u_hist, double* theta_hist, int* iters_hist, int* status_hist) {
+    HostProblem hp;
+    int rc = build_problem(mdl, cfg, hp, g_err);
+    if (rc) return rc;
+    if (!(hp.nx == 4 && hp.nt == 1 && hp.nu == 1) || hp.form != LBMPC_FORM_C) { g_err = "emul loop: C-form (4,1,1)"; return LBMPC_ESHAPE; }
+    using S = Stream<4, false, double, 1>;
+    const Params<4, 1, 1> p = to_params<4, 1, 1>(hp);
+    const StreamLayout<4> l(p.N, p.ng, false, false, q);
+    StreamLoopParams lp{};
+    lp.steps = steps; lp.chunk = chunk; lp.warm_shift = warm_shift; lp.use_oracle = use_oracle; lp.use_w = wbar != nullptr;
+    lp.nscen = nscen; lp.u_eq = u_eq; lp.inv_h2 = 1.0 / 0.25; lp.lambda = 0.001; lp.seed = seed; lp.scen0 = scen0;
+    for (int j = 0; j < 4; ++j) { lp.x_eq[j] = x_eq[j]; lp.wbar[j] = wbar ? wbar[j] : 0.0; }
+    lp.x_init = x_init; lp.x_hist = x_hist; lp.u_hist = u_hist; lp.theta_hist = theta_hist; lp.iters_hist = iters_hist;
+    lp.status_hist = status_hist;
+    std::vector<double> w64((size_t)l.n64, std::nan("")), wft((size_t)l.nft, std::nan("")), rec((size_t)S::store_len(l));
+    for (long sc = 0; sc < nscen; ++sc) S::loop_one(p, l, lp, sc, hp.G.data(), hp.hg.data(), w64.data(), wft.data(), rec.data());
+    return 0;
+}

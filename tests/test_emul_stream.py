@@ -151,3 +151,37 @@ def test_stream_ltv_dynamics_and_row_shift(emul_lib, models):
         assert_parity(got, ref)
         x = ref["xtraj"][ref["status"] == 0]
         assert np.abs(ref["uc"] - P.solve_batch(X0, d_off=d)["uc"]).max() > 1e-5          # the Jacobians do change the problem
+
+
+def test_stream_fused_closed_loop_vs_oracle_loop(emul_lib, models):
+    """The fused closed loop of the stream mapping (plant RK4 + disturbance + ring data window + warm shift + L2NW oracle
+    rollout + solve, per lane, chunked through the scenario store) against the oracle's loop (lbo_closed_loop: shifted
+    window, separate solve calls): same verdict history, iterations +-1, states to 1e-7 — including scenarios whose QP turns
+    infeasible under the disturbance (the loop then keeps executing the last optimal plan) and a window shorter than the run."""
+    import lbmpc_b200
+    mdl = models["LBMPC"]
+    m, keep = capi.pack_model(mdl)
+    N, steps, q, ns = 30, 14, 6, 10
+    cfg = capi.make_config("C", "LBMPC", N)
+    x_eq, u_eq = lbmpc_b200.X_WP, float(lbmpc_b200.U_WP)
+    x_init = np.ascontiguousarray(x_eq[None, :] + sample_ics(ns, seed=3))
+    x_init[1] = x_eq + np.array([-0.395, -0.44, 0.0, 0.0])            # near the edge of the robust set: infeasible steps occur
+    wbar = np.array([0.02, 5e-4, 0.0, 0.0]) * 3.0
+    xh, uh, th = np.empty((ns, steps + 1, 4)), np.empty((ns, steps)), np.empty((ns, steps))
+    ih, sh = np.empty((ns, steps), np.int32), np.empty((ns, steps), np.int32)
+    p = capi._ptr
+    P = OracleProblem("C", "LBMPC", mdl, N)
+    for chunk in (steps, 4):
+        rc = emul_lib.emul_stream_closed_loop(C.byref(m), C.byref(cfg), C.c_long(ns), C.c_int(steps), C.c_int(q), C.c_int(chunk),
+                                              C.c_int(1), C.c_int(1), p(np.ascontiguousarray(x_eq)), C.c_double(u_eq), p(x_init),
+                                              p(wbar), C.c_ulonglong(7), C.c_ulonglong(100), p(xh), p(uh), p(th), p(ih), p(sh))
+        assert rc == 0, emul_lib.emul_last_error()
+        seen_bad = 0
+        for b in range(ns):
+            ref = P.closed_loop(x_eq, u_eq, x_init[b], steps, q=q, use_oracle=True, wbar=wbar, seed=7, scenario=100 + b)
+            assert np.array_equal(ref["status"], sh[b]), (b, ref["status"], sh[b])
+            assert np.abs(ref["iters"] - ih[b]).max() <= 1
+            assert np.abs(ref["x"] - xh[b]).max() < 1e-7 and np.abs(ref["u"] - uh[b]).max() < 1e-7
+            assert np.abs(ref["theta"] - th[b]).max() < 1e-7
+            seen_bad += int((ref["status"] != 0).sum())
+        assert seen_bad > 0                                            # the hold-the-plan rule was exercised

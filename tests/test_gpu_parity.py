@@ -328,16 +328,20 @@ def test_oracle_apply_matches_l2nw(fx, models):
             assert np.abs(got[b] - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()) + 1e-16
 
 
-def test_closed_loop_matches_oracle(models):
+@pytest.mark.parametrize("kernel", ["auto", "stream"])
+def test_closed_loop_matches_oracle(models, kernel):
     """ocpLBMPC.m:10-47 / LBMPC_casadi.m:160-223 as a batch: solve, RK4 plant, disturbance, data window,
-    oracle offsets, warm-start shift.  Same counter-based disturbance on both sides."""
+    oracle offsets, warm-start shift.  Same counter-based disturbance on both sides.  kernel="stream": the FUSED closed
+    loop (one persistent kernel for all control steps, scenarios handed between lanes every 10 steps through the store);
+    "auto": one oracle / solve / plant launch triple per step.  Scenarios with a non-optimal step keep executing the last
+    optimal plan on both sides and are compared like the others."""
     mdl = models["LBMPC"]
     nb, steps = 12, 25
     rng = np.random.default_rng(5)
     x_init = X_EQ + sample_ics(nb, seed=6) * np.array([0.5, 0.5, 0.2, 0.2])
     x_init[0] = X_INIT
     wbar = np.array([0.02, 5e-4, 0.0, 0.0])
-    sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb)
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=nb, kernel=kernel)
     P = OracleProblem("C", "LBMPC", mdl, 50)
     for use_oracle, w in ((False, None), (True, wbar)):
         got = sol.closed_loop(x_init, steps, X_EQ, U_EQ, q=10, use_oracle=use_oracle, wbar=w, seed=42, scenario0=100)
@@ -346,9 +350,8 @@ def test_closed_loop_matches_oracle(models):
                                 scenario=100 + b)
             assert np.array_equal(got["status"][b], ref["status"])
             assert np.abs(got["iters"][b] - ref["iters"]).max() <= 1
-            if (ref["status"] == 0).all():
-                assert np.abs(got["x"][b] - ref["x"]).max() < 1e-6
-                assert np.abs(got["u"][b] - ref["u"]).max() < 1e-6
+            assert np.abs(got["x"][b] - ref["x"]).max() < 1e-6
+            assert np.abs(got["u"][b] - ref["u"]).max() < 1e-6 and np.abs(got["theta"][b] - ref["theta"]).max() < 1e-6
 
 
 @pytest.mark.parametrize("kernel", ["warp", "cta", "stream"])

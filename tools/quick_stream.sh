@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "kernels or config2 or four_problem" 2>&1 | tail -3
-for b in 592 1024 1036; do python tools/prof_solve.py warp LBMPC 50 $b 6; python tools/prof_solve.py cta LBMPC 50 $b 6; LBMPC_CTA_WARPS=2 python tools/prof_solve.py cta LBMPC 50 $b 6; LBMPC_CTA_WARPS=4 python tools/prof_solve.py cta LBMPC 50 $b 6; python tools/prof_solve.py auto LBMPC 50 $b 6; done
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "closed_loop or config5" 2>&1 | tail -8
+python tools/loop_bench.py 125000 20 auto,stream
+LBMPC_LOOP_CHUNK=5 python tools/loop_bench.py 125000 20 stream
