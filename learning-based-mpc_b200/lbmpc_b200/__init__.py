@@ -10,9 +10,9 @@ from .capi import (FORM, VARIANT, ST_OPTIMAL, ST_MAXITER, ST_INFEASIBLE, ST_NUME
 from .model import (mgcmDLTI, matOCP, getCONS, getCONSPOLY, pdiff, tightened_state_set, moore_greitzer_model, double_integrator_model,
                     X_WP, U_WP)
 from .drivers import ocpLBMPC, ocpLMPC, trueModel, transitionTrue, update_data
-from . import sets
+from . import sets, matio
 
 __all__ = ["FORM", "VARIANT", "ST_OPTIMAL", "ST_MAXITER", "ST_INFEASIBLE", "ST_NUMERICAL", "LbmpcError", "Solver",
            "load_library", "pack_model", "make_config", "measure_fp64_peak", "mgcmDLTI", "matOCP", "getCONS", "getCONSPOLY",
            "pdiff", "tightened_state_set", "moore_greitzer_model", "double_integrator_model", "X_WP", "U_WP", "sets",
-           "ocpLBMPC", "ocpLMPC", "trueModel", "transitionTrue", "update_data"]
+           "ocpLBMPC", "ocpLMPC", "trueModel", "transitionTrue", "update_data", "matio"]

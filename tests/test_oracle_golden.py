@@ -267,3 +267,34 @@ def test_verdicts_on_a_model_with_a_wide_steady_state_range(models):
         _, _, _, G, h, _ = condensed_qp("C", "LBMPC", mdl, N, X0[i])
         lp = linprog(np.zeros(G.shape[1]), A_ub=G, b_ub=h, bounds=[(None, None)] * G.shape[1], method="highs")
         assert (lp.status == 0) == (r["status"][i] == 0), i
+
+
+def test_cform_twin_lbmpc_closed_loop_tracks_saved_trajectory_loosely(fx, models):
+    """DMS_LBMPC_casadi.m (twin state sequences, learned oracle in the cost, q = 100, window seeded with one valid zero sample:
+    `data(8,1)=1`, :160-161) against its saved run DMS_N50_tLBMPC_q100.mat `xlo`: the first step is the exact QP (1e-7); the
+    next steps solve a non-convex NLP in the reference (IPOPT, its own local solution and tolerance) and are tracked LOOSELY
+    by the first-order SQP — 1e-3 on the slow states x1, x2, 5e-3 on x3 over 30 steps; the fast throttle-rate state x4
+    (|x4| <= 20, amplifies an input difference by 10 per step) only to 0.2.  SURVEY 8f-1."""
+    from oracle_py import plant_rk4
+    mdl = models["LBMPC"]
+    A, B = mdl["A"], mdl["B"].reshape(4, 1)
+    x_eq, u_eq, x = np.array([0.5, 1.6875, 1.1547, 0.0]), 1.1547, np.array([0.15, 1.2875, 1.1547, 0.0])
+    P = OracleProblem("C", "LBMPC", mdl, 50)
+    q, steps = 100, 30
+    X, Y, V = np.zeros((q, 3)), np.zeros((q, 4)), np.zeros(q)
+    V[0] = 1.0
+    H, warm = [x.copy()], None
+    for it in range(1, steps + 1):
+        dx = x - x_eq
+        o = P.solve_sqp1(dx[None], X[None], Y[None], valid=V[None], sqp_iters=2, warm=warm, twin=True, A=A, B=B)
+        assert o["status"][0] == 0
+        u0 = o["uc"][0, 0, 0]
+        xn = plant_rk4(x, u0 + u_eq)
+        X[it], Y[it], V[it] = [dx[0], dx[1], u0], xn - (x_eq + A @ dx + B[:, 0] * u0), 1.0     # get_data.m:4-5 (it < q)
+        u = o["uc"][0, :, 0]
+        warm = np.concatenate([u[1:], u[-1:], o["theta"][0]])[None]
+        x = xn
+        H.append(x.copy())
+    e = np.abs(np.array(H).T - fx["casadi_DMS_N50_tLBMPC_q100__xlo"][:, :steps + 1])
+    assert e[:, 1].max() < 1e-7                                            # first step: known answer
+    assert e[0].max() < 1e-3 and e[1].max() < 1e-3 and e[2].max() < 5e-3 and e[3].max() < 0.2, e.max(1)
