@@ -317,9 +317,9 @@ def main():
             if rc != 0:
                 raise RuntimeError(hsol.lib.lbmpc_last_error().decode())
             if world > 1:     # per-rank results -> rank 0 over NCCL (first input, objective, iterations, status)
-                lbmpc_b200.dist.gather_results({"u0": h_uc[:, 0, 0].to(dev, non_blocking=True), "obj": h_obj.to(dev, non_blocking=True),
-                                                "iters": h_it.to(dev, non_blocking=True), "status": h_st.to(dev, non_blocking=True)},
-                                               total, dst=0)
+                lbmpc_b200.dist.gather_packed({"u0": h_uc[:, 0, 0].to(dev, non_blocking=True), "obj": h_obj.to(dev, non_blocking=True),
+                                               "iters": h_it.to(dev, non_blocking=True), "status": h_st.to(dev, non_blocking=True)},
+                                              total, dst=0)
         h2d = nb * 4 * 8
         d2h = nb * (N * 8 + 8 + 8 + 4 + 4)
         e2e_check = lambda: (np.array_equal(h_st.numpy(), status) and np.array_equal(h_it.numpy(), iters))
@@ -343,7 +343,7 @@ def main():
                 res = {"x_final": o["x"][:, -1, :].contiguous(), "iters_sum": o["iters"].sum(1, dtype=torch.int32),
                        "status_max": o["status"].max(1).values}
             if world > 1:
-                res = lbmpc_b200.dist.gather_results(res, total, dst=0)
+                res = lbmpc_b200.dist.gather_packed(res, total, dst=0)
             for k, v in res.items():
                 res_host[k] = v.cpu()                          # D2H (rank 0: the gathered arrays)
         h2d = sum(v.numel() * v.element_size() for v in h_in.values())

@@ -37,6 +37,26 @@ def gather_results(local, batch, group=None, dst=None):
     return out
 
 
+def gather_packed(local, batch, group=None, dst=None):
+    """gather_results with ONE collective: the per-QP result columns (first input, objective, iterations, status ... any
+    1-D / (n,k) arrays; int32 columns are exact in float64) are packed into one float64 matrix per rank, gathered once and
+    unpacked with their dtypes.  At a few KB per rank the cost of a gather is its launch latency, so one call instead of
+    four is what matters (NVLink bandwidth is irrelevant here)."""
+    import torch
+    names = list(local)
+    cols = [local[n].reshape(local[n].shape[0], -1).to(torch.float64) for n in names]
+    widths = [c.shape[1] for c in cols]
+    g = gather_results({"packed": torch.cat(cols, dim=1).contiguous()}, batch, group=group, dst=dst)
+    if "packed" not in g:
+        return {}
+    out, o = {}, 0
+    for n, w in zip(names, widths):
+        part = g["packed"][:, o:o + w].to(local[n].dtype)
+        out[n] = part.reshape((part.shape[0],) + tuple(local[n].shape[1:]))
+        o += w
+    return out
+
+
 def reduce_stats(status, iters, obj, group=None):
     """{n_optimal, n_maxiter, n_infeasible, n_numerical, sum_iters, max_iters, sum_obj_optimal} over all ranks."""
     import torch

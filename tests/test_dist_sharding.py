@@ -53,6 +53,13 @@ def _worker(rank, world, port, batch, q):
     r = OracleProblem("C", "LBMPC", mdl, 20).solve_batch(X0[lo:hi])     # stand-in for the GPU shard solve
     local = {k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in ("uc", "theta", "obj", "iters", "status")}
     full = gather_results(local, batch)
+    from lbmpc_b200.dist import gather_packed
+    packed = gather_packed(local, batch, dst=0)          # the one-collective form bench.py uses
+    if rank == 0:
+        for k in full:
+            assert packed[k].dtype == full[k].dtype and torch.equal(packed[k], full[k]), k
+    else:
+        assert packed == {}
     stats = reduce_stats(local["status"], local["iters"], local["obj"])
     if rank == 0:
         q.put(({k: v.numpy() for k, v in full.items()}, stats))
