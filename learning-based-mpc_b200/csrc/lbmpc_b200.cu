@@ -86,6 +86,11 @@ struct lbmpc_handle {
     int st_ctas_per_sm = 0;            // resident 128-thread CTAs per SM (default layout)
     int st_warps_cap = 0;              // 6: use the 6-warp variant everywhere (LBMPC_STREAM_WARPS, experiments)
     int max_smem_optin = 0;
+    bool st_evict_forced = false;      // LBMPC_STREAM_EVICT set: budget also when the mapping is forced (experiments)
+    int st_evict_iters = 12;           // iteration budget of the stream mapping when the engine picks it for long horizons (0: none)
+    long long* st_left = nullptr;      // [0]: count, [1..]: QPs handed over
+    size_t st_left_cap = 0;
+    int64_t st_min_batch_long = 0;     // long horizons (N > 100): stream + hand-over picked from this batch on
     int64_t st_loop_min_batch = 0;     // fused closed loop picked automatically from this many scenarios (0: only when forced)
     int st_loop_chunk = 10;            // control steps a lane runs before it hands the scenario back to the queue
     double* lp_store = nullptr;        // fused closed loop: scenario state between chunks
@@ -126,12 +131,14 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_
     const HostProblem& hp = h->hp;
     BatchIO io = io_in;
     const Params<NX, NT, NU> p = to_params<NX, NT, NU>(hp);
-    int slots = (int)std::min<int64_t>(h->max_slots, (io.batch + h->num_sms - 1) / h->num_sms);
+    // (hand-over launches — io.qlist — read their QP count on the device: sized for a fraction of the batch)
+    const int64_t nq = io.qlist ? std::max<int64_t>(io.batch / 8, 1) : io.batch;
+    int slots = (int)std::min<int64_t>(h->max_slots, (nq + h->num_sms - 1) / h->num_sms);
     slots = std::max(slots, 1);
-    const int grid = (int)std::min<int64_t>(h->num_sms, (io.batch + slots - 1) / slots);
+    const int grid = (int)std::min<int64_t>(h->num_sms, (nq + slots - 1) / slots);
     const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
     // many QPs per warp slot: the warps of a CTA start their iterations together (shared instruction fetches, see cta_tick)
-    io.lockstep = slots >= 4 && io.batch >= (int64_t)3 * grid * slots;
+    io.lockstep = slots >= 4 && nq >= (int64_t)3 * grid * slots;
     if (h->force_lockstep >= 0) io.lockstep = h->force_lockstep;
     io.queue = next_queue(h);
     cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
@@ -151,11 +158,13 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     if (h->force_kernel == LBMPC_KERNEL_CTA) return cta_ok ? LBMPC_KERNEL_CTA : LBMPC_KERNEL_WARP;
     if (h->force_kernel == LBMPC_KERNEL_STREAM || h->force_kernel == LBMPC_KERNEL_STREAM_MIXED)
         return stream_ok ? h->force_kernel : LBMPC_KERNEL_WARP;
-    // very many QPs per SM, small polytope block, moderate horizon: one thread per QP with the iterate streamed from HBM.
-    // Measured (C-form LBMPC, N = 50): 6.2 M QP/s at batch 262144 against 4.5 M for the warp mapping, level near 131072, behind
-    // below (one iteration of a lane lasts ~0.5 ms, so the launch needs several QPs per lane to amortise its last QPs);
-    // thread-local loops over a 616-row set and N = 200 at batch 65536 lose to the CTA mapping.
+    // very many QPs per SM, small polytope block: one thread per QP with the iterate streamed from HBM, an iteration budget and a
+    // hand-over of the slow QPs to a shared-memory mapping (one iteration of a lane lasts ~0.5 ms x N/50, so the 20 - 40
+    // iteration QPs would otherwise hold the launch).  Thread-local loops over a 616-row set lose to the CTA mapping.
     if (stream_ok && h->st_min_batch > 0 && batch >= h->st_min_batch && h->hp.ng <= 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
+    // long horizons: shared memory holds 1 - 2 QPs per SM, the stream mapping 256; its slow iterations (2 ms at N = 200) are
+    // bounded by an iteration budget, the QPs beyond it are handed to the CTA mapping (launch_ipm_stream, evict)
+    if (stream_ok && h->st_min_batch_long > 0 && batch >= h->st_min_batch_long && h->hp.ng <= 64 && h->hp.N > 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
@@ -174,7 +183,7 @@ static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io_in, cudaStr
     BatchIO io = io_in;
     // four warps per QP; two warps per QP only when forced (experiments)
     const bool two = !h->cta_big && h->cta_blocks_per_sm[1] > 0 && h->cta_warps_force == 2;
-    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * h->cta_blocks_per_sm[two ? 1 : 0], io.batch);
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * h->cta_blocks_per_sm[two ? 1 : 0], io.batch);  // hand-over launches: CTAs without work leave at once
     io.queue = next_queue(h);
     cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
@@ -206,8 +215,12 @@ static cudaError_t stream_workspace(lbmpc_handle* h, int64_t warps, const Stream
     }
     return cudaSuccess;
 }
+static cudaError_t launch_ipm_cta(lbmpc_handle* h, const BatchIO& io_in, cudaStream_t st);
+template <int NX, int NT, int NU>
+static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_t st);
+
 template <bool LTV, typename FT, int WARPS>
-static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, size_t smem) {
+static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, size_t smem, bool evict = false) {
     const Params<4, 1, 1> p = to_params<4, 1, 1>(h->hp);
     const bool cs = io.cshift != nullptr;
     const StreamLayout<4> l(p.N, p.ng, cs, LTV);
@@ -222,22 +235,48 @@ static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const dou
     s.wsft = (FT*)h->st_wsft;
     e = cudaMemsetAsync(s.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    if (evict) {  // iteration budget: the QPs still running after it go to a shared-memory mapping (below)
+        if (h->st_left_cap < (size_t)io.batch + 1) {
+            cudaFree(h->st_left); h->st_left = nullptr; h->st_left_cap = 0;
+            e = cudaMalloc((void**)&h->st_left, sizeof(long long) * ((size_t)std::max<int64_t>(io.batch, h->max_batch) + 1));
+            if (e != cudaSuccess) return e;
+            h->st_left_cap = (size_t)std::max<int64_t>(io.batch, h->max_batch) + 1;
+        }
+        e = cudaMemsetAsync(h->st_left, 0, sizeof(long long), st);
+        if (e != cudaSuccess) return e;
+        s.evict_iters = h->st_evict_iters;
+        s.left_count = reinterpret_cast<unsigned long long*>(h->st_left);
+        s.left_list = h->st_left + 1;
+    }
     ipm_stream_kernel<4, LTV, FT, WARPS><<<(unsigned)ctas, 32 * WARPS, smem, st>>>(p, s, h->dG, h->dhg);
     h->launches += 1;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (evict) {  // same inputs / outputs, QP indices from the hand-over list, count read on the device
+        BatchIO lo = io;
+        lo.qlist = h->st_left + 1;
+        lo.qcount = reinterpret_cast<const unsigned long long*>(h->st_left);
+        const bool cta = h->cta_blocks_per_sm[0] > 0 && (h->cta_big || (h->max_slots <= 2 && h->cta_blocks_per_sm[0] >= h->max_slots));
+        e = cta ? launch_ipm_cta(h, lo, st) : launch_ipm<4, 1, 1>(h, lo, st);
+        if (e != cudaSuccess) return e;
+    }
     h->last_kernel = sizeof(FT) == 4 ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM;
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 // warps per CTA (= per SM): 8 (255 registers per thread) when their double buffers fit shared memory, else 6 (per-stage
 // Jacobians and a shift record together make the buffers 15 KB).  12 warps at 168 registers measured 1.5x SLOWER (spills).
 template <bool LTV, typename FT>
-static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st) {
+static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool evict) {
     const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV);
     const bool w8 = 8 * per_warp <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
-    return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp);
+    return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp, evict) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp, evict);
 }
-static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed) {
-    if (mixed) return jac ? launch_stream_t<true, float>(h, io, jac, st) : launch_stream_t<false, float>(h, io, jac, st);
-    return jac ? launch_stream_t<true, double>(h, io, jac, st) : launch_stream_t<false, double>(h, io, jac, st);
+// evict: iteration budget + hand-over (only for plain QPs: no per-stage dynamics, no row shift — the shared-memory mappings
+// have neither)
+static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed, bool evict = false) {
+    evict = evict && !jac && !io.row_shift && h->st_evict_iters > 0;
+    if (mixed) return jac ? launch_stream_t<true, float>(h, io, jac, st, false) : launch_stream_t<false, float>(h, io, jac, st, false);
+    return jac ? launch_stream_t<true, double>(h, io, jac, st, false) : launch_stream_t<false, double>(h, io, jac, st, evict);
 }
 
 static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int q, double inv_h2, double lambda,
@@ -259,7 +298,9 @@ static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream
         const int w = jac ? (h->force_kernel == LBMPC_KERNEL_STREAM_MIXED ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM)
                           : pick_kernel(h, io.batch);  // per-stage dynamics (LTV) exist in the stream mapping only
         if (w == LBMPC_KERNEL_CTA) return launch_ipm_cta(h, io, st);
-        if (w == LBMPC_KERNEL_STREAM || w == LBMPC_KERNEL_STREAM_MIXED) return launch_ipm_stream(h, io, jac, st, w == LBMPC_KERNEL_STREAM_MIXED);
+        if (w == LBMPC_KERNEL_STREAM || w == LBMPC_KERNEL_STREAM_MIXED)
+            return launch_ipm_stream(h, io, jac, st, w == LBMPC_KERNEL_STREAM_MIXED,
+                                     /*evict=*/h->force_kernel == LBMPC_KERNEL_AUTO || h->st_evict_forced);
     }
     return h->shape == 0 ? launch_ipm<4, 1, 1>(h, io, st) : launch_ipm<2, 2, 2>(h, io, st);
 }
@@ -406,8 +447,15 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
-        h->st_min_batch = (int64_t)h->num_sms * 1024;  // >= 4 QPs per resident lane; below that the shared-memory kernels win
+        // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
+        //   N = 50 : batch 65536 14.1 vs 14.5 ms, 131072 24.9 vs 28.7 ms, 262144 44.2 vs 58 ms  -> from ~76 k QPs on
+        //   N = 200: batch 65536 63.6 vs 104.5 ms (budget 16; 14: 71 ms, 22: 70 ms, 32: 81 ms)   -> from ~38 k QPs on
+        h->st_min_batch = (int64_t)h->num_sms * 512;
+        h->st_evict_iters = hp.N > 100 ? 16 : 12;
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
+        if (const char* e = getenv("LBMPC_STREAM_EVICT")) { h->st_evict_iters = atoi(e); h->st_evict_forced = true; }
+        h->st_min_batch_long = (int64_t)h->num_sms * 256;
+        if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH_LONG")) h->st_min_batch_long = atoll(e);
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
         if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use
             const StreamLayout<4> l(hp.N, hp.ng, false, false);
@@ -962,7 +1010,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     cudaFree(h->q_ulin); cudaFree(h->q_warm); cudaFree(h->q_doff); cudaFree(h->q_step); cudaFree(h->q_csh); cudaFree(h->q_jac);
     cudaFree(h->st_ws64); cudaFree(h->st_wsft);
     for (int i = 0; i < 6; ++i) cudaFree(h->og[i]);
-    cudaFree(h->lp_store); cudaFree(h->lp_rq);
+    cudaFree(h->lp_store); cudaFree(h->lp_rq); cudaFree(h->st_left);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -155,7 +155,8 @@ ipm_kernel_cta(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, c
         // ---- fetch the next QP and load its inputs ----
         if (tid == 0) {
             const unsigned long long t = atomicAdd(io.queue, 1ULL);
-            ctl[0] = t < (unsigned long long)io.batch ? (double)t : -1.0;
+            const unsigned long long nq = io.qlist ? *io.qcount : (unsigned long long)io.batch;
+            ctl[0] = t < nq ? (double)(io.qlist ? io.qlist[t] : (long long)t) : -1.0;
         }
         __syncthreads();
         const long long q = (long long)ctl[0];

@@ -42,6 +42,8 @@ struct BatchIO {
     int cs_stride;              // NX: state shift only; NX + NU: state and input shift
     int row_shift;              // stream mapping only: cshift moves the ROWS instead of the cost (first-order SQP)
     int lockstep;               // warp kernel: the warps of a CTA start every iteration together (see cta_tick)
+    const long long* qlist;     // optional: the launch solves QPs qlist[0 .. *qcount) instead of 0 .. batch (QPs the stream mapping
+    const unsigned long long* qcount;  // handed over after its iteration budget: lbmpc_b200.cu launch_ipm_stream)
 };
 
 // CTA-wide barrier that also counts the warps that still have a QP.  The warps of a CTA run independent QPs; at many
@@ -271,7 +273,8 @@ ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const
         long long q = -1;
         if (lane == 0) {
             const unsigned long long t = atomicAdd(io.queue, 1ULL);
-            q = t < (unsigned long long)io.batch ? (long long)t : -1;
+            const unsigned long long nq = io.qlist ? *io.qcount : (unsigned long long)io.batch;
+            q = t < nq ? (io.qlist ? io.qlist[t] : (long long)t) : -1;
         }
         q = __shfl_sync(kFull, q, 0);
         if (q < 0) break;

@@ -103,6 +103,12 @@ struct StreamIO {  // batch-major caller arrays (include/lbmpc.h)
     int cs_stride;  // doubles per stage of cshift: NX (state shift) or NX + 1 (state and input shift)
     int row_shift;  // 0: cshift moves the COST; 1: it moves the ROWS (they act on x_k - ex_k, u_k - eu_k; first-order SQP)
     int qwin;       // fused closed loop: data window length (0 otherwise)
+    // iteration budget of the mapping (0: none).  One iteration of a lane lasts ~0.5 ms x N/50, so the few QPs that need 20 - 40
+    // iterations would hold the whole launch; a QP that has not reached its verdict after `evict_iters` iterations is handed
+    // over (index appended to left_list) and solved from scratch by a shared-memory mapping right after this kernel.
+    int evict_iters;
+    long long* left_list;
+    unsigned long long* left_count;
     double *uc, *theta, *xtraj, *obj;
     int *iters, *status;
     unsigned long long* queue;
@@ -1511,6 +1517,9 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
                     } else {
                         S::finish(p, l, ln, io, w64, st);
                     }
+                    ln.q = -1;
+                } else if (!LOOP && io.evict_iters > 0 && ln.iters >= io.evict_iters) {
+                    io.left_list[atomicAdd(io.left_count, 1ULL)] = ln.q;
                     ln.q = -1;
                 }
             }

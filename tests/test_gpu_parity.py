@@ -600,3 +600,20 @@ def test_wide_steady_state_range_model(models, kernel):
     ref = OracleProblem("C", "LBMPC", mdl, 30).solve_batch(X0, nthreads=8)
     assert_parity(got, ref)
     assert (ref["status"] == 2).any() and np.abs(ref["theta"][ref["status"] == 0]).max() > 10.0
+
+
+def test_stream_iteration_budget_hands_over_to_shared_memory_mappings(models, monkeypatch):
+    """The stream mapping's iteration budget: QPs without a verdict after `budget` iterations are appended to a hand-over list
+    and solved (from scratch) by the warp / CTA mapping in a second launch that reads the list and its length on the device.
+    Forced here with a budget of 6 (most QPs need 7+, so most are handed over): verdicts, iterations and solutions agree with
+    the oracle for the QPs of BOTH launches, N = 50 (warp mapping takes over) and N = 200 (CTA mapping)."""
+    monkeypatch.setenv("LBMPC_STREAM_EVICT", "6")
+    mdl = models["LBMPC"]
+    for N, nb in ((50, 3000), (200, 300)):
+        X0 = sample_ics(nb, seed=N + 11)
+        sol = solver(mdl, "C", "LBMPC", N, max_batch=nb, kernel="stream")
+        got = sol.solve_batch(X0)
+        assert sol.kernel_launches == 2
+        ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, nthreads=8)
+        assert (ref["iters"] > 6).mean() > 0.5 and (ref["iters"] <= 6).any()
+        assert_parity(got, ref)
