@@ -264,7 +264,8 @@ static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const dou
     return cudaSuccess;
 }
 // warps per CTA (= per SM): 8 (255 registers per thread) when their double buffers fit shared memory, else 6 (per-stage
-// Jacobians and a shift record together make the buffers 15 KB).  12 warps at 168 registers measured 1.5x SLOWER (spills).
+// Jacobians and a shift record together make the buffers 15 KB).  More than 8 warps means three warps on some scheduler, i.e.
+// at most 168 registers per thread: 10 and 12 warps both measured 1.3 - 1.5x SLOWER (1.6 - 2 KB of spills in pass BU).
 template <bool LTV, typename FT>
 static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool evict) {
     const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV);
