@@ -152,8 +152,8 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_
 // Few QPs per SM: the launch lasts as long as its slowest QP, so the latency variant (one CTA per QP) wins; many QPs
 // per SM: the warp-per-QP kernel keeps more QPs resident.  LBMPC_KERNEL=warp|cta overrides (experiments).
 // returns LBMPC_KERNEL_WARP / _CTA / _STREAM / _STREAM_MIXED
-static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
-    const bool cta_ok = h->shape == 0 && h->cta_blocks_per_sm[0] > 0, stream_ok = h->shape == 0 && h->st_ctas_per_sm > 0;
+static int pick_kernel(const lbmpc_handle* h, int64_t batch, bool allow_stream = true) {
+    const bool cta_ok = h->shape == 0 && h->cta_blocks_per_sm[0] > 0, stream_ok = allow_stream && h->shape == 0 && h->st_ctas_per_sm > 0;
     if (h->force_kernel == LBMPC_KERNEL_WARP) return LBMPC_KERNEL_WARP;
     if (h->force_kernel == LBMPC_KERNEL_CTA) return cta_ok ? LBMPC_KERNEL_CTA : LBMPC_KERNEL_WARP;
     if (h->force_kernel == LBMPC_KERNEL_STREAM || h->force_kernel == LBMPC_KERNEL_STREAM_MIXED)
@@ -165,6 +165,8 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch) {
     // long horizons: shared memory holds 1 - 2 QPs per SM, the stream mapping 256; its slow iterations (2 ms at N = 200) are
     // bounded by an iteration budget, the QPs beyond it are handed to the CTA mapping (launch_ipm_stream, evict)
     if (stream_ok && h->st_min_batch_long > 0 && batch >= h->st_min_batch_long && h->hp.ng <= 64 && h->hp.N > 100) return LBMPC_KERNEL_STREAM;
+    // 616-row set: the thread-local row loops only pay off at very large batches (262144: 85 vs 133 ms for the CTA mapping; level at 65536)
+    if (stream_ok && h->st_min_batch > 0 && batch >= 3 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
@@ -294,10 +296,12 @@ static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int
     h->launches += 1;
 }
 
-static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, const double* jac = nullptr) {
+// allow_stream = false: closed-loop steps under disturbance — a fifth of those QPs is infeasible or slow, far more than the
+// iteration budget of the stream mapping is made for (measured: 3.1 M QP/s with it, 3.8 M with the warp mapping at 125 k scenarios)
+static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, const double* jac = nullptr, bool allow_stream = true) {
     if (h->shape == 0) {
         const int w = jac ? (h->force_kernel == LBMPC_KERNEL_STREAM_MIXED ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM)
-                          : pick_kernel(h, io.batch);  // per-stage dynamics (LTV) exist in the stream mapping only
+                          : pick_kernel(h, io.batch, allow_stream);  // per-stage dynamics (LTV) exist in the stream mapping only
         if (w == LBMPC_KERNEL_CTA) return launch_ipm_cta(h, io, st);
         if (w == LBMPC_KERNEL_STREAM || w == LBMPC_KERNEL_STREAM_MIXED)
             return launch_ipm_stream(h, io, jac, st, w == LBMPC_KERNEL_STREAM_MIXED,
@@ -916,7 +920,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
         io.dx0 = L.dx0; io.dx_ref = nullptr; io.d_off = (use_oracle && have) ? L.doff : nullptr;
         io.warm = (warm_shift && have) ? L.warm : nullptr;
         io.uc = L.uc; io.theta = L.theta; io.xtraj = nullptr; io.obj = L.obj; io.iters = L.iters; io.status = L.status;
-        CU_TRY(launch_ipm_any(h, io, st));
+        CU_TRY(launch_ipm_any(h, io, st, nullptr, /*allow_stream=*/false));
         plant_kernel<<<tg, 128, 0, st>>>(Sx, h->dA, h->dB, batch, hp.N, q, it, steps, xe, u_eq, wb, wbar != nullptr,
                                          seed, scenario0);
         h->launches += 1;
