@@ -83,16 +83,25 @@ struct StreamLayout {
 };
 
 // per-lane state that lives across the passes of one QP (registers)
-template <int NX>
+template <int NX, int CSTR = 1>
 struct StreamLane {
     static constexpr int NZ = NX + 1;
     long long q;          // QP index, -1: idle
     int iters;
     bool fresh;           // no step to apply yet: the next pass BU initialises the rows
     double th, dtha, dth, alpha, sigmu, iptt, mu;
-    double gGl[NZ], dG1[NZ], dG2[NZ], lin[NZ], cconst;
+    // values that are touched at ONE stage of a pass only (the polytope stage, the reference stage) or at its end: parked in
+    // shared memory on the device (one column per lane, stride CSTR) instead of holding 44 registers through every sweep
+    static constexpr int C_GGL = 0, C_DG1 = NZ, C_DG2 = 2 * NZ, C_LIN = 3 * NZ, C_CCONST = 4 * NZ, C_OBJ = 4 * NZ + 1, C_N = 4 * NZ + 2;
+    double* cold;
+    LB_HD double& gGl(int a) const { return cold[(C_GGL + a) * CSTR]; }
+    LB_HD double& dG1(int a) const { return cold[(C_DG1 + a) * CSTR]; }
+    LB_HD double& dG2(int a) const { return cold[(C_DG2 + a) * CSTR]; }
+    LB_HD double& lin(int a) const { return cold[(C_LIN + a) * CSTR]; }
+    LB_HD double& cconst() const { return cold[C_CCONST * CSTR]; }
+    LB_HD double& obj() const { return cold[C_OBJ * CSTR]; }
     // results of pass BU
-    double rp, lam, hlam, rd, cert, obj;
+    double rp, lam, hlam, rd, cert;
     bool piv_ok;
 };
 
@@ -194,7 +203,7 @@ template <int NX, bool LTV, typename FT, int LS>
 struct Stream {
     using P = Params<NX, 1, 1>;
     using SL = StreamLayout<NX>;
-    using Lane = StreamLane<NX>;
+    using Lane = StreamLane<NX, LS>;
     using C = Core<NX, 1, 1>;
     static constexpr int NZ = NX + 1, NV = NX + 2, NVB = NX + 1, NH = SL::NH, CH = SL::kPolyChunk;
 
@@ -268,8 +277,8 @@ struct Stream {
         if (k == p.kT) {
 #pragma unroll
             for (int a = 0; a < NZ; ++a) {
-                g[a] += ln.lin[a];
-                J += ln.lin[a] * vv[a];
+                g[a] += ln.lin(a);
+                J += ln.lin(a) * vv[a];
             }
         }
         if (Jacc) *Jacc += J;
@@ -296,8 +305,8 @@ struct Stream {
 #pragma unroll
                 for (int j = 0; j < NX; ++j) v += p.Lref[a * NX + j] * io.dx_ref[q * NX + j];
             }
-            ln.lin[a] = v;
-            ln.gGl[a] = ln.dG1[a] = ln.dG2[a] = 0.0;
+            ln.lin(a) = v;
+            ln.gGl(a) = ln.dG1(a) = ln.dG2(a) = 0.0;
         }
         if (io.dx_ref) {
 #pragma unroll
@@ -305,7 +314,7 @@ struct Stream {
 #pragma unroll
                 for (int j = 0; j < NX; ++j) cconst += io.dx_ref[q * NX + i] * p.Tm[i * NX + j] * io.dx_ref[q * NX + j];
         }
-        ln.cconst = cconst;
+        ln.cconst() = cconst;
         if (LTV) {
             const double* jq = io.jac + q * (long long)(N * SL::NJ);
             for (int i = 0; i < N * SL::NJ; ++i) st(w64, l.o_j + i, jq[i]);
@@ -362,17 +371,21 @@ struct Stream {
         ln.th = fresh ? th_old : th_old + alpha * ln.dth;
         const double th = ln.th;
         double Pm[NH], pv[NZ], pi[NZ], pc[NZ];
-        double HG[NH], gGl[NZ], dG[NZ];
         double rpm = 0.0, sl = 0.0, lam = 0.0, hl = 0.0, rd = 0.0, ci = 0.0, yd = 0.0, J = 0.0;
         bool ok = true;
 #pragma unroll
-        for (int a = 0; a < NH; ++a) HG[a] = 0.0;
-#pragma unroll
-        for (int a = 0; a < NZ; ++a) gGl[a] = dG[a] = 0.0;
+        for (int a = 0; a < NZ; ++a) ln.gGl(a) = 0.0;
         pp.start(PASS_BU);
         pp.issue(N);
         for (int k = N; k >= 0; --k) {
             const bool atkg = k == p.kg;
+            // polytope sums: alive at the one stage that carries the block only (declared per stage so that they do not hold
+            // 50 registers through the whole sweep)
+            double HG[NH], gGl[NZ], dG[NZ];
+#pragma unroll
+            for (int a = 0; a < NH; ++a) HG[a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) gGl[a] = dG[a] = 0.0;
             pp.issue((atkg && nch > 0) ? -1 : next_bwd(k));
             const auto vw = pp.acquire();
             double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
@@ -489,6 +502,8 @@ struct Stream {
                         }
                     }
                 }
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) ln.gGl(a) = gGl[a];
             }
             if (last) {
                 // ---- terminal stage: P = Wzz + Qd (+HG); pv = q | g_theta; pi = g; pc = G'lambda ----
@@ -614,15 +629,13 @@ struct Stream {
         rd = lb_nanmax(rd, lb_abs(pi[NX]));
         ci += lb_abs(pc[NX]) * p.fk_th[0];
         yd += pc[NX] * th;
-#pragma unroll
-        for (int a = 0; a < NZ; ++a) ln.gGl[a] = gGl[a];
         ln.rp = rpm;
         ln.mu = sl * p.inv_m;
         ln.lam = lam;
         ln.hlam = hl + yd;
         ln.rd = rd;
         ln.cert = ci;
-        ln.obj = J + ln.cconst;
+        ln.obj() = J + ln.cconst();
         ln.piv_ok = ok;
         // verdict (oracle/lbmpc_oracle.c solve_ws)
         const double mu = ln.mu;
@@ -645,7 +658,7 @@ struct Stream {
 #pragma unroll
         for (int j = 0; j < NX; ++j) dxa[j] = 0.0;
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) ln.dG1[a] = ln.dG2[a] = 0.0;
+        for (int a = 0; a < NZ; ++a) ln.dG1(a) = ln.dG2(a) = 0.0;
         pp.start(PASS_F1);
         pp.issue(0);
         for (int k = 0; k <= N; ++k) {
@@ -740,8 +753,8 @@ struct Stream {
                         const double t1 = w * rp - dsa * dla * is - Lm;
 #pragma unroll
                         for (int a = 0; a < NZ; ++a) {
-                            ln.dG1[a] += gi[a] * t1;
-                            ln.dG2[a] += gi[a] * is;
+                            ln.dG1(a) += gi[a] * t1;
+                            ln.dG2(a) += gi[a] * is;
                         }
                     }
                 }
@@ -775,7 +788,7 @@ struct Stream {
         const double sigmu = ln.sigmu;
         double pv[NZ], kgt[NZ];
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) kgt[a] = ln.gGl[a] + ln.dG1[a] + sigmu * ln.dG2[a];
+        for (int a = 0; a < NZ; ++a) kgt[a] = ln.gGl(a) + ln.dG1(a) + sigmu * ln.dG2(a);
         pp.start(PASS_B2);
         pp.issue(N);
         for (int k = N; k >= 0; --k) {
@@ -990,9 +1003,9 @@ struct Stream {
         ln.iters = 0;
         ln.fresh = true;
         ln.alpha = ln.sigmu = ln.dth = ln.dtha = 0.0;
-        ln.cconst = 0.0;
+        ln.cconst() = 0.0;
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) ln.lin[a] = ln.gGl[a] = ln.dG1[a] = ln.dG2[a] = 0.0;
+        for (int a = 0; a < NZ; ++a) ln.lin(a) = ln.gGl(a) = ln.dG1(a) = ln.dG2(a) = 0.0;
         const bool warm = lp.warm_shift && ll.t > 0;
         ln.th = warm ? ld(w64, l.lp_plan() + p.N) : 0.0;
     }
@@ -1140,7 +1153,7 @@ struct Stream {
             }
         }
         io.theta[q] = ln.th;
-        io.obj[q] = ln.obj;
+        io.obj[q] = ln.obj();
         io.iters[q] = ln.iters;
         io.status[q] = status;
     }
@@ -1149,6 +1162,8 @@ struct Stream {
     static LB_HD void loop_one(const P& p, const SL& l, const StreamLoopParams& lp, long long sc, const double* G, const double* hg,
                                double* w64, FT* wft, double* store_rec) {
         Lane ln;
+        double coldbuf[Lane::C_N * LS];
+        ln.cold = coldbuf;
         LoopLane ll;
         StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
         loop_begin(l, lp, ln, ll, w64, sc);
@@ -1180,6 +1195,8 @@ struct Stream {
     static LB_HD void solve_one(const P& p, const SL& l, const StreamIO<FT>& io, long long q, const double* G, const double* hg,
                                 double* w64, FT* wft) {
         Lane ln;
+        double coldbuf[Lane::C_N * LS];
+        ln.cold = coldbuf;
         const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
         StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
         init_qp(p, l, ln, io, q, w64, has_cs);
@@ -1224,7 +1241,8 @@ struct StreamSmem {  // byte offsets inside one buffer
         b = b > poly ? b : poly;
         return (b + 127) & ~127;
     }
-    static __host__ __device__ size_t warp_bytes(bool cs, bool ltv) { return 2 * (size_t)buf_bytes(cs, ltv) + 128; }  // + two mbarriers
+    static constexpr int kPark = StreamLane<NX, 32>::C_N * kLine;  // parked per-lane values (StreamLane::cold), one line per value
+    static __host__ __device__ size_t warp_bytes(bool cs, bool ltv) { return 2 * (size_t)buf_bytes(cs, ltv) + 128 + kPark; }  // + two mbarriers + park
 };
 
 template <int NX, bool LTV, typename FT>
@@ -1237,14 +1255,14 @@ struct StreamPipeTma {
     const FT* wftg;
     unsigned char* buf;   // two buffers
     uint64_t* bar;        // two mbarriers
-    int lane, pass, bufb, ring[2];
+    int lane, pass, bufb, ring0, ring1;  // (two scalars: a dynamically indexed array would pin the whole struct to local memory)
     unsigned n_issue, n_wait;
     bool has_cs, rows;
     __device__ void start(int pass_) { pass = pass_; }
     __device__ void issue(int item) {
         if (item == kStreamNone) return;
         const unsigned b = n_issue & 1u;
-        ring[b] = item;
+        if (b) ring1 = item; else ring0 = item;
         ++n_issue;
         __syncwarp();  // every lane is done reading buffer b (item n_issue - 2) and has fenced its global stores
         if (lane == 0) {
@@ -1277,7 +1295,7 @@ struct StreamPipeTma {
         const unsigned b = n_wait & 1u, parity = (n_wait >> 1) & 1u;
         ++n_wait;
         mbar_wait(bar + b, parity);
-        const int item = ring[b];
+        const int item = b ? ring1 : ring0;
         const unsigned src = smem_u32(buf + b * bufb) + 8u * (unsigned)lane;  // this lane's column (FP64 lines)
         View v;
         if (item >= 0) {
@@ -1417,6 +1435,7 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     }
     __syncwarp();
     typename S::Lane ln;
+    ln.cold = reinterpret_cast<double*>(pp.buf + 2 * pp.bufb + 128) + lane;
     ln.q = -1;
     ln.iters = 0;
     ln.fresh = true;
