@@ -165,8 +165,8 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch, bool allow_stream =
     // long horizons: shared memory holds 1 - 2 QPs per SM, the stream mapping 256; its slow iterations (2 ms at N = 200) are
     // bounded by an iteration budget, the QPs beyond it are handed to the CTA mapping (launch_ipm_stream, evict)
     if (stream_ok && h->st_min_batch_long > 0 && batch >= h->st_min_batch_long && h->hp.ng <= 64 && h->hp.N > 100) return LBMPC_KERNEL_STREAM;
-    // 616-row set: the thread-local row loops only pay off at very large batches (262144: 85 vs 133 ms for the CTA mapping; level at 65536)
-    if (stream_ok && h->st_min_batch > 0 && batch >= 3 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
+    // 616-row set: the thread-local row loops pay off at large batches only (65536: 29.5 vs 33.5 ms for the CTA mapping, 262144: 78 vs 133 ms)
+    if (stream_ok && h->st_min_batch > 0 && batch >= 2 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
@@ -270,9 +270,9 @@ static cudaError_t launch_stream_w(lbmpc_handle* h, const BatchIO& io, const dou
 // at most 168 registers per thread: 10 and 12 warps both measured 1.3 - 1.5x SLOWER (1.6 - 2 KB of spills in pass BU).
 template <bool LTV, typename FT>
 static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool evict) {
-    const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV);
-    const bool w8 = 8 * per_warp <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
-    return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp, evict) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp, evict);
+    const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV), poly = StreamSmem<4, FT>::poly_bytes(h->hp.ngp);
+    const bool w8 = 8 * per_warp + poly <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
+    return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp + poly, evict) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp + poly, evict);
 }
 // evict: iteration budget + hand-over (only for plain QPs: no per-stage dynamics, no row shift — the shared-memory mappings
 // have neither)
@@ -453,13 +453,15 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
         // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
-        //   N = 50 : batch 65536 14.1 vs 14.5 ms, 131072 24.9 vs 28.7 ms, 262144 44.2 vs 58 ms  -> from ~76 k QPs on
-        //   N = 200: batch 65536 63.6 vs 104.5 ms (budget 16; 14: 71 ms, 22: 70 ms, 32: 81 ms)   -> from ~38 k QPs on
-        h->st_min_batch = (int64_t)h->num_sms * 512;
+        //   N = 50 : batch 24576 5.95 vs 5.58 ms, 32768 6.32 vs 7.39, 65536 11.1 vs 14.5, 131072 19.5 vs 28.7  -> from ~31 k QPs on
+        //   N = 200: batch 16384 28.3 vs 26.5 ms, 24576 28.6 vs 39.5, 32768 30.2 vs 52.7, 49152 44.3 vs 78.6   -> from ~21 k QPs on
+        //   616-row set, N = 50 (no budget): 65536 29.5 vs 33.5 ms, 131072 47.0 vs 66.8, 262144 77.9 vs 133.3   -> from ~62 k QPs on
+        //   (profiles/r2_threshold_sweep.log; budget at N = 200: 16 iterations — 14: +12 %, 22: +10 %, 32: +27 %)
+        h->st_min_batch = (int64_t)h->num_sms * 208;
         h->st_evict_iters = hp.N > 100 ? 16 : 12;
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
         if (const char* e = getenv("LBMPC_STREAM_EVICT")) { h->st_evict_iters = atoi(e); h->st_evict_forced = true; }
-        h->st_min_batch_long = (int64_t)h->num_sms * 256;
+        h->st_min_batch_long = (int64_t)h->num_sms * 144;
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH_LONG")) h->st_min_batch_long = atoll(e);
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
         if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use
@@ -895,7 +897,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
         StreamIO<double> sio{};
         sio.batch = batch; sio.queue = next_queue(h); sio.ws64 = h->st_ws64; sio.wsft = (double*)h->st_wsft; sio.qwin = q;
         CU_TRY(cudaMemsetAsync(sio.queue, 0, sizeof(unsigned long long), st));
-        const size_t smem = kW * StreamSmem<4, double>::warp_bytes(false, false);
+        const size_t smem = kW * StreamSmem<4, double>::warp_bytes(false, false) + StreamSmem<4, double>::poly_bytes(hp.ngp);
         CU_TRY(cudaEventRecord(h->ev0, st));
         ipm_stream_kernel<4, false, double, kW, true><<<(unsigned)ctas, 32 * kW, smem, st>>>(p, sio, h->dG, h->dhg, lp);
         CU_TRY(cudaGetLastError());

@@ -1136,20 +1136,33 @@ struct Stream {
     static LB_HD void finish(const P& p, const SL& l, const Lane& ln, const StreamIO<FT>& io, const double* w64, int status) {
         const int N = p.N;
         const long long q = ln.q;
-        for (int k = 0; k <= N; ++k) {
-            const double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
-            double x[NX];
+        // the iterate comes back from the workspace in groups of KB stages, every load of a group issued before the first
+        // use: one stage at a time (5 dependent-latency loads, then the stores) cost ~2.5 k cycles per stage under a loaded
+        // HBM — 10 % of the kernel's warp time with the other 31 lanes of the warp waiting
+        constexpr int KB = 10;
+        for (int k0 = 0; k0 <= N; k0 += KB) {
+            double xs[KB][NX + 1];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) x[j] = ld(it, j);
-            if (io.xtraj) {
+            for (int i = 0; i < KB; ++i) {
+                const int k = k0 + i <= N ? k0 + i : N;
+                const double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = x[j];
+                for (int j = 0; j <= NX; ++j) xs[i][j] = ld(it, j);
             }
-            if (k < N) {
-                double v = ld(it, NX);
 #pragma unroll
-                for (int j = 0; j < NX; ++j) v -= p.Kout[j] * x[j];
-                io.uc[q * N + k] = v;
+            for (int i = 0; i < KB; ++i) {
+                const int k = k0 + i;
+                if (k > N) break;
+                if (io.xtraj) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) io.xtraj[(q * (N + 1) + k) * NX + j] = xs[i][j];
+                }
+                if (k < N) {
+                    double v = xs[i][NX];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v -= p.Kout[j] * xs[i][j];
+                    io.uc[q * N + k] = v;
+                }
             }
         }
         io.theta[q] = ln.th;
@@ -1243,6 +1256,9 @@ struct StreamSmem {  // byte offsets inside one buffer
     }
     static constexpr int kPark = StreamLane<NX, 32>::C_N * kLine;  // parked per-lane values (StreamLane::cold), one line per value
     static __host__ __device__ size_t warp_bytes(bool cs, bool ltv) { return 2 * (size_t)buf_bytes(cs, ltv) + 128 + kPark; }  // + two mbarriers + park
+    // small polytope blocks (the 24-row robust set) are staged once per CTA behind the warps' regions: the row loops of three
+    // passes read G and hg row by row, and with the L1 thrashed by the streamed records every one of those loads went to L2
+    static __host__ __device__ size_t poly_bytes(int ngp) { return ngp <= 64 ? (size_t)(NX + 2) * ngp * sizeof(double) : 0; }
 };
 
 template <int NX, bool LTV, typename FT>
@@ -1406,8 +1422,8 @@ __device__ __forceinline__ void stream_pass_fence() { asm volatile("fence.proxy.
 // the control steps of its chunk back to back and hands the scenario over through the store + the re-queue ring.
 template <int NX, bool LTV, typename FT, int WARPS, bool LOOP = false>
 __global__ void __launch_bounds__(32 * WARPS, 1)
-ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT> io, const double* __restrict__ G,
-                  const double* __restrict__ hg, const StreamLoopParams lp = StreamLoopParams{}) {
+ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT> io, const double* G,
+                  const double* hg, const StreamLoopParams lp = StreamLoopParams{}) {
     using S = Stream<NX, LTV, FT, 32>;
     using SM = StreamSmem<NX, FT>;
     extern __shared__ __align__(128) unsigned char stream_smem[];
@@ -1417,6 +1433,14 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV, LOOP ? io.qwin : 0);
     double* const w64 = io.ws64 + warp * (long long)l.n64 * 32 + lane;
     FT* const wft = io.wsft + warp * (long long)l.nft * 32 + lane;
+    if (SM::poly_bytes(p.ngp) > 0) {  // stage the polytope block; generic pointers, so the passes do not care where it lives
+        double* Gs = reinterpret_cast<double*>(stream_smem + (blockDim.x >> 5) * SM::warp_bytes(has_cs, LTV));
+        for (int i = threadIdx.x; i < (NX + 1) * p.ngp; i += blockDim.x) Gs[i] = G[i];
+        for (int i = threadIdx.x; i < p.ngp; i += blockDim.x) Gs[(NX + 1) * p.ngp + i] = i < p.ng ? hg[i] : 0.0;
+        __syncthreads();
+        G = Gs;
+        hg = Gs + (NX + 1) * p.ngp;
+    }
     StreamPipeTma<NX, LTV, FT> pp;
     pp.l = &l;
     pp.w64g = w64 - lane;
