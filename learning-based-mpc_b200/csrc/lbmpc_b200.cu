@@ -91,6 +91,7 @@ struct lbmpc_handle {
     long long* st_left = nullptr;      // [0]: count, [1..]: QPs handed over
     size_t st_left_cap = 0;
     int64_t st_min_batch_long = 0;     // long horizons (N > 100): stream + hand-over picked from this batch on
+    bool loop_allow_stream = true;     // closed-loop steps may take the stream mapping (LBMPC_LOOP_ALLOW_STREAM=0: never)
     int64_t st_loop_min_batch = 0;     // fused closed loop picked automatically from this many scenarios (0: only when forced)
     int st_loop_chunk = 10;            // control steps a lane runs before it hands the scenario back to the queue
     double* lp_store = nullptr;        // fused closed loop: scenario state between chunks
@@ -296,8 +297,9 @@ static void launch_oracle(lbmpc_handle* h, cudaStream_t st, long long batch, int
     h->launches += 1;
 }
 
-// allow_stream = false: closed-loop steps under disturbance — a fifth of those QPs is infeasible or slow, far more than the
-// iteration budget of the stream mapping is made for (measured: 3.1 M QP/s with it, 3.8 M with the warp mapping at 125 k scenarios)
+// allow_stream: closed-loop steps under disturbance hand a fifth of their QPs (infeasible or slow) over to the shared-memory
+// mapping; measured at 125 k scenarios x 50 steps: 4.50 M QP/s with the stream mapping + hand-over, 3.73 M with the warp mapping,
+// 3.11 M with the fused loop kernel (which has no iteration budget)
 static cudaError_t launch_ipm_any(lbmpc_handle* h, const BatchIO& io, cudaStream_t st, const double* jac = nullptr, bool allow_stream = true) {
     if (h->shape == 0) {
         const int w = jac ? (h->force_kernel == LBMPC_KERNEL_STREAM_MIXED ? LBMPC_KERNEL_STREAM_MIXED : LBMPC_KERNEL_STREAM)
@@ -458,8 +460,9 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         //   616-row set, N = 50 (no budget): 65536 29.5 vs 33.5 ms, 131072 47.0 vs 66.8, 262144 77.9 vs 133.3   -> from ~62 k QPs on
         //   (profiles/r2_threshold_sweep.log; budget at N = 200: 16 iterations — 14: +12 %, 22: +10 %, 32: +27 %)
         h->st_min_batch = (int64_t)h->num_sms * 208;
-        h->st_evict_iters = hp.N > 100 ? 16 : 12;
+        h->st_evict_iters = hp.N > 100 ? 16 : 14;  // N = 50: 14 vs 12 -> closed loop 4.80 vs 4.50 M QP/s, batch 262144 34.5 vs 35.3 ms (profiles/r2_evict_sweep.log)
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
+        if (const char* e = getenv("LBMPC_LOOP_ALLOW_STREAM")) h->loop_allow_stream = atoi(e) != 0;
         if (const char* e = getenv("LBMPC_STREAM_EVICT")) { h->st_evict_iters = atoi(e); h->st_evict_forced = true; }
         h->st_min_batch_long = (int64_t)h->num_sms * 144;
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH_LONG")) h->st_min_batch_long = atoll(e);
@@ -922,7 +925,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
         io.dx0 = L.dx0; io.dx_ref = nullptr; io.d_off = (use_oracle && have) ? L.doff : nullptr;
         io.warm = (warm_shift && have) ? L.warm : nullptr;
         io.uc = L.uc; io.theta = L.theta; io.xtraj = nullptr; io.obj = L.obj; io.iters = L.iters; io.status = L.status;
-        CU_TRY(launch_ipm_any(h, io, st, nullptr, /*allow_stream=*/false));
+        CU_TRY(launch_ipm_any(h, io, st, nullptr, /*allow_stream=*/h->loop_allow_stream));
         plant_kernel<<<tg, 128, 0, st>>>(Sx, h->dA, h->dB, batch, hp.N, q, it, steps, xe, u_eq, wb, wbar != nullptr,
                                          seed, scenario0);
         h->launches += 1;
