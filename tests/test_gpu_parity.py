@@ -617,3 +617,23 @@ def test_stream_iteration_budget_hands_over_to_shared_memory_mappings(models, mo
         ref = OracleProblem("C", "LBMPC", mdl, N).solve_batch(X0, nthreads=8)
         assert (ref["iters"] > 6).mean() > 0.5 and (ref["iters"] <= 6).any()
         assert_parity(got, ref)
+
+
+def test_mixed_storage_mode_on_gpu(models):
+    """LBMPC_KERNEL_STREAM_MIXED ("f32+f64", BASELINE.json north_star: stated separately from the FP64 parity): directions and
+    Riccati factors STORED in FP32, iterate / residuals / arithmetic FP64.  LBMPC shapes: same verdicts, iterations within
+    +-3, objective 1e-8, inputs 1e-6 for >= 95 % of the optimal QPs; and bit-identical to nothing else — the FP64 stream
+    mapping on the same inputs must keep the full FP64 rule (this test would catch the mixed mode leaking into it)."""
+    mdl = models["LBMPC"]
+    X0 = sample_ics(2048, seed=77)
+    ref = OracleProblem("C", "LBMPC", mdl, 50).solve_batch(X0, nthreads=8)
+    sol = solver(mdl, "C", "LBMPC", 50, max_batch=2048, kernel="mixed")
+    got = sol.solve_batch(X0)
+    assert sol.last_kernel == "mixed"
+    assert_parity(got, ref, tol=1e-6, frac_tight=0.95, max_dit=3, caps=(1e-4, 1e-3))
+    ok = ref["status"] == 0
+    assert np.abs(got["obj"][ok] - ref["obj"][ok]).max() / np.abs(ref["obj"][ok]).max() < 1e-8
+    sol64 = solver(mdl, "C", "LBMPC", 50, max_batch=2048, kernel="stream")
+    got64 = sol64.solve_batch(X0)
+    assert sol64.last_kernel == "stream"
+    assert_parity(got64, ref)
