@@ -311,19 +311,30 @@ def main():
         h_uc, h_th, h_obj = pe((nb, N, 1), torch.float64), pe((nb, 1), torch.float64), pe((nb,), torch.float64)
         h_it, h_st = pe((nb,), torch.int32), pe((nb,), torch.int32)
 
-        def e2e_step():
-            rc = hsol.lib.lbmpc_solve_batch(hsol.h, nb, _ptr(h_in), None, None, None, _ptr(h_uc), _ptr(h_th), None,
-                                            _ptr(h_obj), _ptr(h_it), _ptr(h_st), None)
-            if rc != 0:
-                raise RuntimeError(hsol.lib.lbmpc_last_error().decode())
-            if world > 1:     # per-rank results -> rank 0 over NCCL (first input, objective, iterations, status)
-                lbmpc_b200.dist.gather_packed({"u0": h_uc[:, 0, 0].to(dev, non_blocking=True), "obj": h_obj.to(dev, non_blocking=True),
-                                               "iters": h_it.to(dev, non_blocking=True), "status": h_st.to(dev, non_blocking=True)},
-                                              total, dst=0)
-        h2d = nb * 4 * 8
-        d2h = nb * (N * 8 + 8 + 8 + 4 + 4)
-        e2e_check = lambda: (np.array_equal(h_st.numpy(), status) and np.array_equal(h_it.numpy(), iters))
-        e2e_path = "host-pointer lbmpc_solve_batch, pinned caller arrays accessed in place (zero-copy)"
+        res_host = {}
+        if world == 1:
+            def e2e_step():
+                rc = hsol.lib.lbmpc_solve_batch(hsol.h, nb, _ptr(h_in), None, None, None, _ptr(h_uc), _ptr(h_th), None,
+                                                _ptr(h_obj), _ptr(h_it), _ptr(h_st), None)
+                if rc != 0:
+                    raise RuntimeError(hsol.lib.lbmpc_last_error().decode())
+            h2d = nb * 4 * 8
+            d2h = nb * (N * 8 + 8 + 8 + 4 + 4)
+            e2e_check = lambda: (np.array_equal(h_st.numpy(), status) and np.array_equal(h_it.numpy(), iters))
+            e2e_path = "host-pointer lbmpc_solve_batch, pinned caller arrays accessed in place (zero-copy)"
+        else:
+            # several ranks: the results have to reach rank 0 over NCCL, so they stay on the device until the gather —
+            # pinned inputs -> H2D -> device-pointer call -> ONE packed NCCL gather -> D2H of the gathered block on rank 0
+            def e2e_step():
+                o = sol.solve_batch(h_in.to(dev, non_blocking=True), want_x=False, out=state["out"])
+                res = lbmpc_b200.dist.gather_packed({"u0": o["uc"][:, 0, 0], "obj": o["obj"], "iters": o["iters"], "status": o["status"]},
+                                                    total, dst=0)
+                for k, v in res.items():
+                    res_host[k] = v.cpu()
+            h2d = nb * 4 * 8
+            d2h = nb * 24
+            e2e_check = lambda: True
+            e2e_path = "pinned host inputs -> cudaMemcpyAsync H2D -> device-pointer C-ABI call -> one packed NCCL gather -> D2H on rank 0"
     else:
         # pinned host inputs -> H2D -> device-pointer calls -> NCCL gather to rank 0 -> D2H of the results
         h_in = {k: pin(v) for k, v in inp.items() if isinstance(v, np.ndarray) and k in ("dx0", "dx_ref", "X", "Y", "x_init")}

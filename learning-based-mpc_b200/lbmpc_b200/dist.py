@@ -37,23 +37,49 @@ def gather_results(local, batch, group=None, dst=None):
     return out
 
 
+_PACK_CACHE = {}
+
+
 def gather_packed(local, batch, group=None, dst=None):
     """gather_results with ONE collective: the per-QP result columns (first input, objective, iterations, status ... any
     1-D / (n,k) arrays; int32 columns are exact in float64) are packed into one float64 matrix per rank, gathered once and
-    unpacked with their dtypes.  At a few KB per rank the cost of a gather is its launch latency, so one call instead of
-    four is what matters (NVLink bandwidth is irrelevant here)."""
+    unpacked with their dtypes.  At a few KB per rank the cost of a gather is launch latency, so what matters is the NUMBER of
+    small operations around it (NVLink bandwidth is irrelevant here): the send matrix and the receive block are
+    allocated once per shape and reused, the columns are written into the send matrix by converting copies (no concatenation),
+    and the receive block is gathered into views of one tensor (no concatenation on the receiving side when the shards have
+    equal length)."""
     import torch
+    import torch.distributed as dist
     names = list(local)
-    cols = [local[n].reshape(local[n].shape[0], -1).to(torch.float64) for n in names]
-    widths = [c.shape[1] for c in cols]
-    g = gather_results({"packed": torch.cat(cols, dim=1).contiguous()}, batch, group=group, dst=dst)
-    if "packed" not in g:
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    widths = [int(local[n].numel() // max(1, local[n].shape[0])) if local[n].shape[0] else int(np.prod(local[n].shape[1:], dtype=np.int64)) for n in names]
+    w = sum(widths)
+    dev = local[names[0]].device
+    key = (world, mx, w, str(dev), dst, id(group))
+    if key not in _PACK_CACHE:
+        send = torch.zeros((mx, w), dtype=torch.float64, device=dev)
+        recv = torch.empty((world, mx, w), dtype=torch.float64, device=dev) if (dst is None or rank == dst) else None
+        _PACK_CACHE.clear()          # one shape at a time is all a loop of identical steps needs
+        _PACK_CACHE[key] = (send, recv)
+    send, recv = _PACK_CACHE[key]
+    n_loc, o = sizes[rank], 0
+    for n, wd in zip(names, widths):
+        send[:n_loc, o:o + wd].copy_(local[n].reshape(n_loc, wd))
+        o += wd
+    if dst is None:
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
+    else:
+        dist.gather(send, list(recv.unbind(0)) if rank == dst else None, dst=dst, group=group)
+    if recv is None:
         return {}
+    full = recv.reshape(world * mx, w) if min(sizes) == mx else torch.cat([recv[r, :n] for r, n in enumerate(sizes)], dim=0)
     out, o = {}, 0
-    for n, w in zip(names, widths):
-        part = g["packed"][:, o:o + w].to(local[n].dtype)
+    for n, wd in zip(names, widths):
+        part = full[:, o:o + wd].to(local[n].dtype, copy=True)   # never a view of the reused receive block
         out[n] = part.reshape((part.shape[0],) + tuple(local[n].shape[1:]))
-        o += w
+        o += wd
     return out
 
 
