@@ -91,6 +91,7 @@ struct lbmpc_handle {
     long long* st_left = nullptr;      // [0]: count, [1..]: QPs handed over
     size_t st_left_cap = 0;
     int64_t st_min_batch_long = 0;     // long horizons (N > 100): stream + hand-over picked from this batch on
+    bool st_spread = true;             // small stream launches use 2 / 4 warps per CTA so that every SM takes part (LBMPC_STREAM_SPREAD=0: always 8)
     bool loop_allow_stream = true;     // closed-loop steps may take the stream mapping (LBMPC_LOOP_ALLOW_STREAM=0: never)
     int64_t st_loop_min_batch = 0;     // fused closed loop picked automatically from this many scenarios (0: only when forced)
     int st_loop_chunk = 10;            // control steps a lane runs before it hands the scenario back to the queue
@@ -273,6 +274,13 @@ template <bool LTV, typename FT>
 static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool evict) {
     const size_t per_warp = StreamSmem<4, FT>::warp_bytes(io.cshift != nullptr, LTV), poly = StreamSmem<4, FT>::poly_bytes(h->hp.ngp);
     const bool w8 = 8 * per_warp + poly <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
+    // fewer QPs than resident lanes: spread them over ALL SMs with fewer warps per CTA instead of filling a few SMs with eight
+    // (a lane's iteration is latency-bound; with 2 warps on an SM instead of 8 it runs ~2.5x faster)
+    if (!LTV && sizeof(FT) == 8 && h->st_spread) {
+        const int64_t wps = (io.batch + 32 * (int64_t)h->num_sms - 1) / (32 * (int64_t)h->num_sms);
+        if (wps <= 2) return launch_stream_w<LTV, FT, 2>(h, io, jac, st, 2 * per_warp + poly, evict);
+        if (wps <= 4) return launch_stream_w<LTV, FT, 4>(h, io, jac, st, 4 * per_warp + poly, evict);
+    }
     return w8 ? launch_stream_w<LTV, FT, 8>(h, io, jac, st, 8 * per_warp + poly, evict) : launch_stream_w<LTV, FT, 6>(h, io, jac, st, 6 * per_warp + poly, evict);
 }
 // evict: iteration budget + hand-over (only for plain QPs: no per-stage dynamics, no row shift — the shared-memory mappings
@@ -452,19 +460,21 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         if (const char* e = getenv("LBMPC_LOOP_CHUNK")) h->st_loop_chunk = std::max(1, atoi(e));
         if (const char* e = getenv("LBMPC_LOOP_MIN_BATCH")) h->st_loop_min_batch = atoll(e);
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
+        CU_TRY(optin(ipm_stream_kernel<4, false, double, 2>)); CU_TRY(optin(ipm_stream_kernel<4, false, double, 4>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
         // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
         //   N = 50 : batch 24576 5.95 vs 5.58 ms, 32768 6.32 vs 7.39, 65536 11.1 vs 14.5, 131072 19.5 vs 28.7  -> from ~31 k QPs on
-        //   N = 200: batch 16384 28.3 vs 26.5 ms, 24576 28.6 vs 39.5, 32768 30.2 vs 52.7, 49152 44.3 vs 78.6   -> from ~21 k QPs on
+        //   N = 200: batch 16384 28.3 vs 26.5 ms, 24576 28.6 vs 39.5, 32768 30.2 vs 52.7, 49152 44.3 vs 78.6   -> from ~15 k QPs on (spread launches, below)
         //   616-row set, N = 50 (no budget): 65536 29.5 vs 33.5 ms, 131072 47.0 vs 66.8, 262144 77.9 vs 133.3   -> from ~62 k QPs on
         //   (profiles/r2_threshold_sweep.log; budget at N = 200: 16 iterations — 14: +12 %, 22: +10 %, 32: +27 %)
         h->st_min_batch = (int64_t)h->num_sms * 208;
         h->st_evict_iters = hp.N > 100 ? 16 : 14;  // N = 50: 14 vs 12 -> closed loop 4.80 vs 4.50 M QP/s, batch 262144 34.5 vs 35.3 ms (profiles/r2_evict_sweep.log)
         if (const char* e = getenv("LBMPC_STREAM_WARPS")) h->st_warps_cap = atoi(e);
         if (const char* e = getenv("LBMPC_LOOP_ALLOW_STREAM")) h->loop_allow_stream = atoi(e) != 0;
+        if (const char* e = getenv("LBMPC_STREAM_SPREAD")) h->st_spread = atoi(e) != 0;
         if (const char* e = getenv("LBMPC_STREAM_EVICT")) { h->st_evict_iters = atoi(e); h->st_evict_forced = true; }
-        h->st_min_batch_long = (int64_t)h->num_sms * 144;
+        h->st_min_batch_long = (int64_t)h->num_sms * 104;  // with small launches spread over all SMs: 12288 22.6 vs 20.1 ms (CTA), 16384 23.3 vs 26.5 (profiles/r2_spread_sweep.log)
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH_LONG")) h->st_min_batch_long = atoll(e);
         if (const char* e = getenv("LBMPC_STREAM_MIN_BATCH")) h->st_min_batch = atoll(e);
         if (h->max_batch >= h->st_min_batch) {  // workspace of the resident warps for the default layout; other layouts grow it on first use

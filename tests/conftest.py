@@ -114,3 +114,29 @@ def drop_numerical(got, ref, max_frac=0.03):
     keep = ~bad
     f = lambda d: {k: (v[keep] if v is not None else None) for k, v in d.items()}
     return f(got), f(ref)
+
+
+def assert_other_minimiser(mdl, N, X0, got, ref, tol=1e-7, feas=1e-8):
+    """Second shape, C-form: where the minimiser is not unique (flat directions of a 0.01-weighted input cost at a vertex) the
+    two sides may return DIFFERENT minimisers.  The explanation is checked per QP instead of being asserted in prose: every
+    optimal QP whose inputs differ by more than `tol` must (a) reproduce its own predicted states from the dynamics
+    x+ = A x + B u (trackingMPC/constraintsFunction.m:24-27), (b) satisfy the input box, the state box on x_1..x_N and the terminal
+    set on [x_N; theta] (:28-38) to `feas`, and (c) attain the oracle's objective to 1e-8 — i.e. it is a feasible point with the
+    optimal value, hence a minimiser of the same QP.  Returns the number of such QPs."""
+    A, B = np.asarray(mdl["A"], float), np.asarray(mdl["B"], float)
+    ok = np.nonzero((ref["status"] == 0) & (got["status"] == 0))[0]
+    n_other = 0
+    for b in ok:
+        e = np.abs(got["uc"][b] - ref["uc"][b]).max() / max(1.0, np.abs(ref["uc"][b]).max())
+        if e < tol:
+            continue
+        n_other += 1
+        u, x, th = got["uc"][b].reshape(N, -1), got["xtraj"][b].reshape(N + 1, -1), got["theta"][b].reshape(-1)
+        assert np.abs(x[0] - X0[b]).max() < 1e-12
+        for k in range(N):
+            assert np.abs(A @ x[k] + B @ u[k] - x[k + 1]).max() < 1e-9, (b, k)
+            assert (mdl["F_u"] @ u[k] <= mdl["h_u"] + feas).all(), (b, k)
+            assert (mdl["F_x"] @ x[k + 1] <= mdl["h_x"] + feas).all(), (b, k)
+        assert (mdl["F_w_N"] @ np.concatenate([x[N], th]) <= mdl["h_w_N"] + feas).all(), b
+        assert abs(got["obj"][b] - ref["obj"][b]) <= 1e-8 * max(1.0, abs(ref["obj"][b])), b
+    return n_other
