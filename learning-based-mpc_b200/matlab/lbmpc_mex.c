@@ -12,7 +12,8 @@
  *              out.u_or_c (nu*N x batch), out.theta (nt x batch), out.x (nx x (N+1) x batch),
  *              out.f (1 x batch), out.iters, out.status (int32 1 x batch)
  *   d_off    = lbmpc_mex('oracle', h, q, bandwidth, lambda, dx0, du, X, Y, valid)
- *   out      = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm)   out.du_step added
+ *   out      = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm, twin, order)   out.du_step added
+ *              (twin, order optional, default 0: lbmpc_solve_sqp_ex — order 1 = oracle value AND Jacobian, a first-order SQP step)
  *   hist     = lbmpc_mex('closed_loop', h, steps, q, use_oracle, warm_shift, x_eq, u_eq, x_init, wbar, seed)
  *   lbmpc_mex('destroy', h)        v = lbmpc_mex('version')
  *
@@ -173,7 +174,7 @@ static void cmd_solve_sqp(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     mwSize d3[3];
     mxArray *uc, *th, *x, *f, *it, *st, *ds;
     if (nrhs < 10)
-        mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm, twin)");
+        mexErrMsgIdAndTxt("lbmpc:args", "usage: out = lbmpc_mex('solve_sqp', h, sqp_iters, q, bandwidth, lambda, dx0, dx_ref, X, Y, valid, warm, twin, order)");
     e = lookup(get_handle(prhs[1]));
     its = (int)mxGetScalar(prhs[2]);
     if ((int)mxGetM(prhs[6]) != e->nx) mexErrMsgIdAndTxt("lbmpc:args", "dx0 must be nx x batch");
@@ -186,11 +187,12 @@ static void cmd_solve_sqp(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     it = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
     st = mxCreateNumericMatrix(1, (mwSize)batch, mxINT32_CLASS, mxREAL);
     ds = mxCreateDoubleMatrix((mwSize)(its > 0 ? its : 1), (mwSize)batch, mxREAL);
-    rc = lbmpc_solve_sqp(e->h, batch, its, nrhs > 12 ? (int)mxGetScalar(prhs[12]) : 0, (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), mxGetScalar(prhs[5]),
-                         dptr(prhs[6]), dptr(prhs[7]), dptr(prhs[8]), dptr(prhs[9]), nrhs > 10 ? dptr(prhs[10]) : NULL,
-                         nrhs > 11 ? dptr(prhs[11]) : NULL, mxGetPr(uc), mxGetPr(th), mxGetPr(x), mxGetPr(f),
-                         (int32_t *)mxGetData(it), (int32_t *)mxGetData(st), mxGetPr(ds), NULL);
-    if (rc != LBMPC_OK) fail_rc("lbmpc_solve_sqp", rc);
+    rc = lbmpc_solve_sqp_ex(e->h, batch, its, nrhs > 12 ? (int)mxGetScalar(prhs[12]) : 0, nrhs > 13 ? (int)mxGetScalar(prhs[13]) : 0,
+                            (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), mxGetScalar(prhs[5]),
+                            dptr(prhs[6]), dptr(prhs[7]), dptr(prhs[8]), dptr(prhs[9]), nrhs > 10 ? dptr(prhs[10]) : NULL,
+                            nrhs > 11 ? dptr(prhs[11]) : NULL, mxGetPr(uc), mxGetPr(th), mxGetPr(x), mxGetPr(f),
+                            (int32_t *)mxGetData(it), (int32_t *)mxGetData(st), mxGetPr(ds), NULL);
+    if (rc != LBMPC_OK) fail_rc("lbmpc_solve_sqp_ex", rc);
     plhs[0] = mxCreateStructMatrix(1, 1, 7, names);
     mxSetField(plhs[0], 0, "u_or_c", uc); mxSetField(plhs[0], 0, "theta", th); mxSetField(plhs[0], 0, "x", x);
     mxSetField(plhs[0], 0, "f", f); mxSetField(plhs[0], 0, "iters", it); mxSetField(plhs[0], 0, "status", st);

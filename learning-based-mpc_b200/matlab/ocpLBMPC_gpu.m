@@ -12,10 +12,12 @@ function [sysHistory,art_refHistory,true_refHistory]...
 % The reference's problem is stated as the reference states it: costLBMPC.m:27 rolls the LEARNED model
 % (transitionLearned.m:13-14: u = K x + c on the learned state, x+ = A x + B u + g(x,u;data)) while
 % constraintsLBMPC.m:23 rolls the NOMINAL model, so the oracle moves the cost only and the X, U, X(-)D
-% and terminal rows stay on the nominal prediction.  The non-convex oracle term is frozen along the
-% previous solution and re-evaluated `sqp_iters` times per control step (lbmpc_solve_sqp with twin = 1:
-% the gap between the two state sequences obeys e+ = (A + B K) e + g_k, the input gap is K e, and both
-% enter the QP as a cost shift).  With data = 0 (first step) this is the exact QP of the reference.
+% and terminal rows stay on the nominal prediction.  The non-convex oracle term is linearised along the
+% previous solution `sqp_iters` times per control step (lbmpc_solve_sqp_ex with twin = 1, order = 1: oracle
+% value AND Jacobian give an LTV QP on the learned sequence whose rows follow the nominal one at the gap
+% e+ = (A + B K) e + g_k, input gap K e) — the same call the Python mirror lbmpc_b200.ocpLBMPC makes, which
+% reproduces the reference's saved LBMPC_N50_sys_full.mat history to 5e-6 on the inputs (tests/).
+% With data = 0 (first step) this is the exact QP of the reference.
 model = struct('A',A,'B',B,'K',Kstabil,'Q',Q,'R',R,'P',P,'T',T,'LAMBDA',LAMBDA,'PSI',PSI, ...
                'F_x',F_x,'h_x',h_x,'F_u',F_u,'h_u',h_u,'F_w_N',F_w_N,'h_w_N',h_w_N, ...
                'F_x_d',F_x_d,'h_x_d',h_x_d);
@@ -23,7 +25,7 @@ cfg = struct('form','F','variant','LBMPC','N',N,'max_batch',1);
 h = lbmpc_mex('create', model, cfg);
 cleaner = onCleanup(@() lbmpc_mex('destroy', h));
 q = 100;                                   % moving window (ocpLBMPC.m:18)
-sqp_iters = 2;                             % re-linearisations of the oracle per control step
+sqp_iters = 2;                             % linearisations of the oracle per control step (drivers.py default)
 for k = 1:iterations
     if k > 1
         X = [x(1:2)-x_wp(1:2); u-u_wp];                        % ocpLBMPC.m:14
@@ -35,7 +37,7 @@ for k = 1:iterations
         dx = dx_init;
     end
     % replaces fmincon(COSTFUN,opt_var,...,CONSFUN,options), ocpLBMPC.m:27-31
-    out = lbmpc_mex('solve_sqp', h, sqp_iters, size(data.X,2), 0.5, 0.001, dx, dx_ref, data.X, data.Y, [], opt_var(:), 1);
+    out = lbmpc_mex('solve_sqp', h, sqp_iters, size(data.X,2), 0.5, 0.001, dx, dx_ref, data.X, data.Y, [], opt_var(:), 1, 1);   % twin = 1, order = 1
     if out.status ~= 0
         warning('lbmpc:status', 'step %d: solver status %d', k, out.status);
     end
