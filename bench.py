@@ -327,10 +327,8 @@ def main():
             # pinned inputs -> H2D -> device-pointer call -> ONE packed NCCL gather -> D2H of the gathered block on rank 0
             def e2e_step():
                 o = sol.solve_batch(h_in.to(dev, non_blocking=True), want_x=False, out=state["out"])
-                res = lbmpc_b200.dist.gather_packed({"u0": o["uc"][:, 0, 0], "obj": o["obj"], "iters": o["iters"], "status": o["status"]},
-                                                    total, dst=0)
-                for k, v in res.items():
-                    res_host[k] = v.cpu()
+                res_host.update(lbmpc_b200.dist.gather_packed({"u0": o["uc"][:, 0, 0], "obj": o["obj"], "iters": o["iters"],
+                                                               "status": o["status"]}, total, dst=0, to_host=True))
             h2d = nb * 4 * 8
             d2h = nb * 24
             e2e_check = lambda: True
@@ -354,9 +352,10 @@ def main():
                 res = {"x_final": o["x"][:, -1, :].contiguous(), "iters_sum": o["iters"].sum(1, dtype=torch.int32),
                        "status_max": o["status"].max(1).values}
             if world > 1:
-                res = lbmpc_b200.dist.gather_packed(res, total, dst=0)
-            for k, v in res.items():
-                res_host[k] = v.cpu()                          # D2H (rank 0: the gathered arrays)
+                res_host.update(lbmpc_b200.dist.gather_packed(res, total, dst=0, to_host=True))   # one gather, one D2H on rank 0
+            else:
+                for k, v in res.items():
+                    res_host[k] = v.cpu()                      # D2H of the results
         h2d = sum(v.numel() * v.element_size() for v in h_in.values())
         d2h = {"solve": nb * 24, "oracle_solve": nb * 24, "closed_loop": nb * 40}[kind]
         e2e_check = lambda: True

@@ -40,14 +40,16 @@ def gather_results(local, batch, group=None, dst=None):
 _PACK_CACHE = {}
 
 
-def gather_packed(local, batch, group=None, dst=None):
+def gather_packed(local, batch, group=None, dst=None, to_host=False):
     """gather_results with ONE collective: the per-QP result columns (first input, objective, iterations, status ... any
     1-D / (n,k) arrays; int32 columns are exact in float64) are packed into one float64 matrix per rank, gathered once and
     unpacked with their dtypes.  At a few KB per rank the cost of a gather is launch latency, so what matters is the NUMBER of
     small operations around it (NVLink bandwidth is irrelevant here): the send matrix and the receive block are
     allocated once per shape and reused, the columns are written into the send matrix by converting copies (no concatenation),
     and the receive block is gathered into views of one tensor (no concatenation on the receiving side when the shards have
-    equal length)."""
+    equal length).  to_host=True: the receiving rank copies the gathered block to the host in ONE device-to-host copy (into a
+    page-locked buffer that is reused) and returns numpy arrays — what a caller that wants the results on the host should use
+    instead of one `.cpu()` per column."""
     import torch
     import torch.distributed as dist
     names = list(local)
@@ -61,7 +63,7 @@ def gather_packed(local, batch, group=None, dst=None):
     if key not in _PACK_CACHE:
         send = torch.zeros((mx, w), dtype=torch.float64, device=dev)
         recv = torch.empty((world, mx, w), dtype=torch.float64, device=dev) if (dst is None or rank == dst) else None
-        _PACK_CACHE.clear()          # one shape at a time is all a loop of identical steps needs
+        _PACK_CACHE.clear()          # one shape at a time is all a loop of identical steps needs (host block included)
         _PACK_CACHE[key] = (send, recv)
     send, recv = _PACK_CACHE[key]
     n_loc, o = sizes[rank], 0
@@ -75,6 +77,19 @@ def gather_packed(local, batch, group=None, dst=None):
     if recv is None:
         return {}
     full = recv.reshape(world * mx, w) if min(sizes) == mx else torch.cat([recv[r, :n] for r, n in enumerate(sizes)], dim=0)
+    if to_host:
+        hk = ("host",) + key
+        if hk not in _PACK_CACHE or _PACK_CACHE[hk].shape[0] < full.shape[0]:
+            pin = dev.type == "cuda"
+            _PACK_CACHE[hk] = torch.empty((world * mx, w), dtype=torch.float64, pin_memory=pin)
+        host = _PACK_CACHE[hk][: full.shape[0]]
+        host.copy_(full)                      # one D2H (synchronous for the caller: the results are on the host when it returns)
+        arr, out, o = host.numpy(), {}, 0
+        for n, wd in zip(names, widths):
+            dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64}[local[n].dtype]
+            out[n] = arr[:, o:o + wd].astype(dt).reshape((arr.shape[0],) + tuple(local[n].shape[1:]))
+            o += wd
+        return out
     out, o = {}, 0
     for n, wd in zip(names, widths):
         part = full[:, o:o + wd].to(local[n].dtype, copy=True)   # never a view of the reused receive block

@@ -60,6 +60,12 @@ def _worker(rank, world, port, batch, q):
             assert packed[k].dtype == full[k].dtype and torch.equal(packed[k], full[k]), k
     else:
         assert packed == {}
+    hosted = gather_packed(local, batch, dst=0, to_host=True)   # ... and its one-copy-to-the-host form
+    if rank == 0:
+        for k in full:
+            assert hosted[k].dtype == full[k].numpy().dtype and np.array_equal(hosted[k], full[k].numpy()), k
+    else:
+        assert hosted == {}
     stats = reduce_stats(local["status"], local["iters"], local["obj"])
     if rank == 0:
         q.put(({k: v.numpy() for k, v in full.items()}, stats))
