@@ -171,7 +171,13 @@ int lbmpc_oracle_apply(lbmpc_handle *h, int64_t batch, int32_t q, double bandwid
  * and kernels use the same rule so iteration parity stays exact.
  *   x_init nx x batch (absolute); x_eq nx; wbar nx or NULL;
  *   x_hist nx x (steps+1) x batch OUT; u_hist steps x batch OUT; theta_hist steps x batch OUT;
- *   iters_hist/status_hist steps x batch OUT (any OUT may be NULL).  C-form handles only. */
+ *   iters_hist/status_hist steps x batch OUT (any OUT may be NULL).
+ * F-form handles run the loops of ocpLBMPC.m:10-47 / ocpLMPC.m:11-40 instead: the decision variables are c and the plant input is
+ * u = K (x - x_wp) + c + u_wp (transitionTrue.m:11-12); every solve starts from the previous, UNSHIFTED opt_var (ocpLBMPC.m:31;
+ * warm_shift is ignored); the window follows update_data.m:3-10 and starts from one all-zero sample like the scripts; an LBMPC
+ * handle with use_oracle = 1 solves each step by two first-order SQP iterations with the learned term in the cost only
+ * (costLBMPC.m:27 vs constraintsLBMPC.m:23; lbmpc_solve_sqp_ex twin = 1, order = 1), otherwise by one exact QP.  u_hist holds
+ * the absolute plant input, theta_hist the artificial-reference parameter.  Per-step launches only (the fused kernel is C-form). */
 int lbmpc_closed_loop(lbmpc_handle *h, int64_t batch, int32_t steps, int32_t q, int32_t use_oracle,
                       int32_t warm_shift, const double *x_eq, double u_eq, const double *x_init,
                       const double *wbar, uint64_t seed, uint64_t scenario0, double *x_hist,

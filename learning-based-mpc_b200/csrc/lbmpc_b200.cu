@@ -699,23 +699,11 @@ int lbmpc_solve_sqp(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t t
                               iters, status, du_step, stream);
 }
 
-int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t order, int32_t q, double bandwidth,
-                       double lambda, const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
-                       const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
-                       int32_t* status, double* du_step, void* stream) {
-    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
-    if (order != 0 && order != 1) return fail(LBMPC_EINVAL, "order must be 0 (frozen oracle value) or 1 (value and Jacobian)");
-    if (batch < 0 || sqp_iters < 1) return fail(LBMPC_EINVAL, "batch must be >= 0 and sqp_iters >= 1");
-    if (batch == 0) return LBMPC_OK;
-    if (!dx0 || !X || !Y || !u || !theta || !obj || !iters || !status) return fail(LBMPC_EINVAL, "required array is NULL");
-    if (h->shape != 0) return fail(LBMPC_ESHAPE, "solve_sqp: 4-state Moore-Greitzer model (the L2NW oracle is defined on xi = [x1;x2;u])");
-    if (h->hp.form == LBMPC_FORM_F && !twin)
-        return fail(LBMPC_ESHAPE, "solve_sqp: the F-form rolls the learned model in the cost only (costLBMPC.m:27 vs constraintsLBMPC.m:23): twin = 1");
-    if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
-    if (!(bandwidth > 0)) return fail(LBMPC_EINVAL, "bandwidth must be positive");
-    if (!h->dev_ptrs && batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
-    cudaStream_t st = (cudaStream_t)stream;
-    CU_TRY(cudaSetDevice(h->device));
+// device-pointer core of lbmpc_solve_sqp_ex (also the per-step solve of the F-form LBMPC closed loop): scratch sized on demand,
+// then `sqp_iters` times { oracle (value, or value + Jacobian) along the previous solution -> one QP -> bookkeeping }
+static int sqp_core(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t order, int32_t q, double bandwidth, double lambda,
+                    const double* d_dx0, const double* d_ref, const double* d_X, const double* d_Y, const double* d_V, const double* d_warm,
+                    double* d_u, double* d_th, double* d_xt, double* d_obj, int* d_it, int* d_st, bool du_step, cudaStream_t st) {
     const HostProblem& hp = h->hp;
     const size_t b = (size_t)batch, N = hp.N, nx = hp.nx, nt = hp.nt;
     if (h->sqp_batch < batch || h->sqp_iters < sqp_iters) {
@@ -729,29 +717,10 @@ int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_
     }
     if (order == 1 && !h->q_jac) CU_TRY(dmalloc(&h->q_jac, (size_t)h->sqp_batch * nx * 3 * N));
     if (twin && !h->q_csh) CU_TRY(dmalloc(&h->q_csh, (size_t)h->sqp_batch * (nx + 1) * (N + 1)));
-    // device views of the inputs / outputs
-    const double *d_dx0 = dx0, *d_ref = dx_ref, *d_X = X, *d_Y = Y, *d_V = valid, *d_warm = warm;
-    double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
-    int *d_it = iters, *d_st = status;
-    double *tX = nullptr, *tY = nullptr, *tV = nullptr;
-    if (!h->dev_ptrs) {
-        CU_TRY(staging(h, 2, b * 3 * q, &tX)); CU_TRY(staging(h, 3, b * 4 * q, &tY));
-        if (valid) CU_TRY(staging(h, 5, b * q, &tV));
-        CU_TRY(cudaMemcpyAsync(tX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(tY, Y, 8 * b * 4 * q, cudaMemcpyHostToDevice, st));
-        if (valid) CU_TRY(cudaMemcpyAsync(tV, valid, 8 * b * q, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, 8 * b * nx, cudaMemcpyHostToDevice, st));
-        if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, 8 * b * nx, cudaMemcpyHostToDevice, st));
-        if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, 8 * b * (N + nt), cudaMemcpyHostToDevice, st));
-        d_dx0 = h->s_dx0; d_ref = dx_ref ? h->s_ref : nullptr; d_X = tX; d_Y = tY; d_V = tV; d_warm = warm ? h->s_warm : nullptr;
-        const SmallOut so = small_out(h->s_small, b, nt);
-        d_u = h->s_uc; d_th = so.theta; d_xt = x_traj ? h->s_x : nullptr; d_obj = so.obj; d_it = so.iters; d_st = so.status;
-    }
     if (d_warm) CU_TRY(cudaMemcpy2DAsync(h->q_ulin, 8 * N, d_warm, 8 * (N + nt), 8 * N, b, cudaMemcpyDeviceToDevice, st));
     else CU_TRY(cudaMemsetAsync(h->q_ulin, 0, 8 * b * N, st));
     const double inv_h2 = 1.0 / (bandwidth * bandwidth);
     const unsigned ug = (unsigned)((batch + 3) / 4);
-    CU_TRY(cudaEventRecord(h->ev0, st));
     for (int j = 0; j < sqp_iters; ++j) {
         if (order == 1) {  // value + Jacobian of the oracle along the learned rollout, gap to the nominal rollout (twin)
             const double* Kfb = hp.form == LBMPC_FORM_F ? h->dK : nullptr;
@@ -797,6 +766,52 @@ int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_
         h->launches += 1;
         CU_TRY(cudaGetLastError());
     }
+    return LBMPC_OK;
+}
+
+int lbmpc_solve_sqp_ex(lbmpc_handle* h, int64_t batch, int32_t sqp_iters, int32_t twin, int32_t order, int32_t q, double bandwidth,
+                       double lambda, const double* dx0, const double* dx_ref, const double* X, const double* Y, const double* valid,
+                       const double* warm, double* u, double* theta, double* x_traj, double* obj, int32_t* iters,
+                       int32_t* status, double* du_step, void* stream) {
+    if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
+    if (order != 0 && order != 1) return fail(LBMPC_EINVAL, "order must be 0 (frozen oracle value) or 1 (value and Jacobian)");
+    if (batch < 0 || sqp_iters < 1) return fail(LBMPC_EINVAL, "batch must be >= 0 and sqp_iters >= 1");
+    if (batch == 0) return LBMPC_OK;
+    if (!dx0 || !X || !Y || !u || !theta || !obj || !iters || !status) return fail(LBMPC_EINVAL, "required array is NULL");
+    if (h->shape != 0) return fail(LBMPC_ESHAPE, "solve_sqp: 4-state Moore-Greitzer model (the L2NW oracle is defined on xi = [x1;x2;u])");
+    if (h->hp.form == LBMPC_FORM_F && !twin)
+        return fail(LBMPC_ESHAPE, "solve_sqp: the F-form rolls the learned model in the cost only (costLBMPC.m:27 vs constraintsLBMPC.m:23): twin = 1");
+    if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
+    if (!(bandwidth > 0)) return fail(LBMPC_EINVAL, "bandwidth must be positive");
+    if (!h->dev_ptrs && batch > h->max_batch) return fail(LBMPC_EINVAL, "batch exceeds config.max_batch (host-pointer staging)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(h->device));
+    const HostProblem& hp = h->hp;
+    const size_t b = (size_t)batch, N = hp.N, nx = hp.nx, nt = hp.nt;
+    // device views of the inputs / outputs
+    const double *d_dx0 = dx0, *d_ref = dx_ref, *d_X = X, *d_Y = Y, *d_V = valid, *d_warm = warm;
+    double *d_u = u, *d_th = theta, *d_xt = x_traj, *d_obj = obj;
+    int *d_it = iters, *d_st = status;
+    double *tX = nullptr, *tY = nullptr, *tV = nullptr;
+    if (!h->dev_ptrs) {
+        CU_TRY(staging(h, 2, b * 3 * q, &tX)); CU_TRY(staging(h, 3, b * 4 * q, &tY));
+        if (valid) CU_TRY(staging(h, 5, b * q, &tV));
+        CU_TRY(cudaMemcpyAsync(tX, X, 8 * b * 3 * q, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(tY, Y, 8 * b * 4 * q, cudaMemcpyHostToDevice, st));
+        if (valid) CU_TRY(cudaMemcpyAsync(tV, valid, 8 * b * q, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(h->s_dx0, dx0, 8 * b * nx, cudaMemcpyHostToDevice, st));
+        if (dx_ref) CU_TRY(cudaMemcpyAsync(h->s_ref, dx_ref, 8 * b * nx, cudaMemcpyHostToDevice, st));
+        if (warm) CU_TRY(cudaMemcpyAsync(h->s_warm, warm, 8 * b * (N + nt), cudaMemcpyHostToDevice, st));
+        d_dx0 = h->s_dx0; d_ref = dx_ref ? h->s_ref : nullptr; d_X = tX; d_Y = tY; d_V = tV; d_warm = warm ? h->s_warm : nullptr;
+        const SmallOut so = small_out(h->s_small, b, nt);
+        d_u = h->s_uc; d_th = so.theta; d_xt = x_traj ? h->s_x : nullptr; d_obj = so.obj; d_it = so.iters; d_st = so.status;
+    }
+    CU_TRY(cudaEventRecord(h->ev0, st));
+    {
+        const int rc = sqp_core(h, batch, sqp_iters, twin, order, q, bandwidth, lambda, d_dx0, d_ref, d_X, d_Y, d_V, d_warm, d_u, d_th, d_xt, d_obj,
+                                d_it, d_st, du_step != nullptr, st);
+        if (rc != LBMPC_OK) return rc;
+    }
     CU_TRY(cudaEventRecord(h->ev1, st));
     h->timed = true;
     if (h->dev_ptrs) {
@@ -827,8 +842,8 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
     if (!h) return fail(LBMPC_EINVAL, "handle is NULL");
     if (batch <= 0 || steps <= 0) return fail(LBMPC_EINVAL, "batch and steps must be positive");
     if (!x_eq || !x_init) return fail(LBMPC_EINVAL, "x_eq / x_init is NULL");
-    if (h->shape != 0 || h->hp.form != LBMPC_FORM_C)
-        return fail(LBMPC_ESHAPE, "closed loop: C-form handle on the 4-state Moore-Greitzer model");
+    if (h->shape != 0) return fail(LBMPC_ESHAPE, "closed loop: the 4-state Moore-Greitzer model");
+    const bool fform = h->hp.form == LBMPC_FORM_F;
     if (q < 1 || q > 32 * kOracleMaxPerLane) return fail(LBMPC_ESHAPE, "q must be in [1, 512]");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaSetDevice(h->device));
@@ -876,7 +891,7 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
     // Fused closed loop (stream mapping): one persistent kernel runs every control step of every scenario.  Picked when
     // the stream mapping is forced, or automatically for scenario counts where it measures faster than one oracle / solve /
     // plant launch triple per step.
-    const bool fused = h->shape == 0 && h->st_ctas_per_sm > 0 && hp.ng <= 64 && q <= 512 &&
+    const bool fused = !fform && h->shape == 0 && h->st_ctas_per_sm > 0 && hp.ng <= 64 && q <= 512 &&
                        (h->force_kernel == LBMPC_KERNEL_STREAM ||
                         (h->force_kernel == LBMPC_KERNEL_AUTO && h->st_loop_min_batch > 0 && batch >= h->st_loop_min_batch));
     if (fused) {
@@ -920,11 +935,30 @@ int lbmpc_closed_loop(lbmpc_handle* h, int64_t batch, int32_t steps, int32_t q, 
         h->last_kernel = LBMPC_KERNEL_STREAM;
     }
     const unsigned tg = (unsigned)((batch + 127) / 128);
-    if (!fused) loop_init_kernel<<<tg, 128, 0, st>>>(Sx, xi_dev, batch, steps, xe);
+    if (!fused) loop_init_kernel<<<tg, 128, 0, st>>>(Sx, xi_dev, batch, steps, xe, fform ? 1 : 0, q);
     if (!fused) h->launches += 1;
     CU_TRY(cudaGetLastError());
     const double inv_h2 = 1.0 / (0.5 * 0.5);  // oracleL2NW.m:9 bandwidth = 0.5
-    for (int it = 0; it < steps && !fused; ++it) {
+    for (int it = 0; it < steps && !fused && fform; ++it) {
+        // F-form loop (ocpLBMPC.m:10-47, ocpLMPC.m:11-40): every solve starts from the previous opt_var (zeros at the first step);
+        // LBMPC with the oracle: the learned term acts on the cost only (costLBMPC.m:27 vs constraintsLBMPC.m:23) -> two first-order
+        // SQP iterations on the data window (what lbmpc_b200.ocpLBMPC does per scenario); otherwise one exact QP
+        if (use_oracle && hp.variant == LBMPC_VARIANT_LBMPC) {
+            const int rc = sqp_core(h, batch, 2, /*twin=*/1, /*order=*/1, q, 0.5, 0.001, L.dx0, nullptr, L.X, L.Y, L.V, L.warm, L.uc, L.theta,
+                                    nullptr, L.obj, L.iters, L.status, false, st);
+            if (rc != LBMPC_OK) return rc;
+        } else {
+            BatchIO io{};
+            io.batch = batch; io.queue = h->dqueue; io.prof = nullptr;
+            io.dx0 = L.dx0; io.dx_ref = nullptr; io.d_off = nullptr; io.warm = L.warm;
+            io.uc = L.uc; io.theta = L.theta; io.xtraj = nullptr; io.obj = L.obj; io.iters = L.iters; io.status = L.status;
+            CU_TRY(launch_ipm_any(h, io, st));
+        }
+        plant_kernel<<<tg, 128, 0, st>>>(Sx, h->dA, h->dB, batch, hp.N, q, it, steps, xe, u_eq, wb, wbar != nullptr, seed, scenario0, h->dK);
+        h->launches += 1;
+        CU_TRY(cudaGetLastError());
+    }
+    for (int it = 0; it < steps && !fused && !fform; ++it) {
         const bool have = it > 0;
         if (use_oracle && have) {
             launch_oracle(h, st, batch, q, inv_h2, 0.001, L.dx0, L.warm, (long long)(N + 1), L.X, L.Y, L.V, L.doff);

@@ -794,7 +794,11 @@ struct LoopState {
 __global__ void __launch_bounds__(128)
 plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict__ B, long long batch, int N,
              int q, int step, int steps, double4 x_eq, double u_eq, double4 wbar, int use_w,
-             unsigned long long seed, unsigned long long scen0) {
+             unsigned long long seed, unsigned long long scen0, const double* __restrict__ Kfb = nullptr) {
+    // Kfb != nullptr: F-form loop (ocpLBMPC.m:10-47 / ocpLMPC.m:11-40): the decision variables are c, the plant input is
+    // u = K (x - x_wp) + c + u_wp (transitionTrue.m:11-12), the next solve starts from the UNSHIFTED opt_var (ocpLBMPC.m:31) and the
+    // data window follows update_data.m:3-10 (appends while the 1-based iteration index is below q, then drops the oldest column:
+    // with the zero column the scripts start from it holds at most q - 1 samples).
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const double xe[4] = {x_eq.x, x_eq.y, x_eq.z, x_eq.w}, wb[4] = {wbar.x, wbar.y, wbar.z, wbar.w};
@@ -810,7 +814,12 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
     double* wm = S.warm + b * (N + 1);
     const double* plan = ok ? S.uc + b * N : wm;
     const double th_plan = ok ? S.theta[b] : wm[N];
-    const double du0 = plan[0], u0 = du0 + u_eq;
+    double du0 = plan[0];
+    if (Kfb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) du0 += Kfb[j] * dx[j];
+    }
+    const double u0 = du0 + u_eq;
     double k1[4], k2[4], k3[4], k4[4], t[4], xn[4];
     const double delta = 0.01;
     mg_rhs(x, u0, k1);
@@ -846,14 +855,14 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
     double* Xb = S.X + b * 3 * q;
     double* Yb = S.Y + b * 4 * q;
     double* Vb = S.V + b * q;
-    if (nd >= q) {  // get_data.m:8 : drop the oldest sample
+    if (nd >= (Kfb ? q - 1 : q)) {  // get_data.m:8 / update_data.m:8 : drop the oldest sample
         for (int i = 0; i + 1 < q; ++i) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) Xb[i * 3 + a] = Xb[(i + 1) * 3 + a];
 #pragma unroll
             for (int a = 0; a < 4; ++a) Yb[i * 4 + a] = Yb[(i + 1) * 4 + a];
         }
-        nd = q - 1;
+        nd = (Kfb ? q - 1 : q) - 1;
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) Xb[nd * 3 + a] = xs[a];
@@ -862,9 +871,14 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
     Vb[nd] = 1.0;
     S.nd[b] = nd + 1;
     // warm-start shift (in place when the plan is the previous warm start)
-    const double last = plan[N - 1];
-    for (int k = 0; k + 1 < N; ++k) wm[k] = plan[k + 1];
-    wm[N - 1] = last;
+    if (Kfb) {  // F-form: opt_var is reused as it is
+        if (ok)
+            for (int k = 0; k < N; ++k) wm[k] = plan[k];
+    } else {
+        const double last = plan[N - 1];
+        for (int k = 0; k + 1 < N; ++k) wm[k] = plan[k + 1];
+        wm[N - 1] = last;
+    }
     wm[N] = th_plan;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -879,7 +893,7 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
 }
 
 __global__ void loop_init_kernel(LoopState S, const double* __restrict__ x_init, long long batch, int steps,
-                                 double4 x_eq) {
+                                 double4 x_eq, int fform = 0, int q = 0) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const double xe[4] = {x_eq.x, x_eq.y, x_eq.z, x_eq.w};
@@ -890,7 +904,8 @@ __global__ void loop_init_kernel(LoopState S, const double* __restrict__ x_init,
         S.dx0[b * 4 + j] = v - xe[j];
         if (S.x_hist) S.x_hist[(b * (steps + 1)) * 4 + j] = v;
     }
-    S.nd[b] = 0;
+    S.nd[b] = fform ? 1 : 0;   // F-form scripts start from one all-zero sample (LBMPC_RunExample.m: data.X = zeros(3,1), data.Y = zeros(4,1))
+    if (fform) S.V[b * q] = 1.0;
 }
 
 // ---------------------------------------------------------------------------------------------

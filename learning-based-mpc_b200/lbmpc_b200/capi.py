@@ -332,7 +332,9 @@ class Solver:
     def closed_loop(self, x_init, steps, x_eq, u_eq, q=100, use_oracle=False, warm_shift=True, wbar=None, seed=0,
                     scenario0=0):
         """Batch of closed-loop scenarios.  Returns dict x (batch,steps+1,nx), u, theta, iters, status (numpy arrays for a
-        host-pointer handle; torch tensors on x_init's device, filled asynchronously, for a device-pointer handle)."""
+        host-pointer handle; torch tensors on x_init's device, filled asynchronously, for a device-pointer handle).
+        C-form handles: LBMPC_casadi.m:160-223; F-form handles: ocpLBMPC.m:10-47 / ocpLMPC.m:11-40 (u = K dx + c to the plant,
+        unshifted opt_var, update_data window; LBMPC + use_oracle: two first-order SQP iterations per step) — include/lbmpc.h."""
         if self.device_pointers:
             import torch
             nb, dev = x_init.shape[0], x_init.device

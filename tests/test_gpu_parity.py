@@ -645,3 +645,42 @@ def test_mixed_storage_mode_on_gpu(models):
     got64 = sol64.solve_batch(X0)
     assert sol64.last_kernel == "stream"
     assert_parity(got64, ref)
+
+
+def test_fform_closed_loop_on_device_matches_drivers_and_reference(fx, models):
+    """lbmpc_closed_loop on F-form handles: the loops of ocpLBMPC.m:10-47 / ocpLMPC.m:11-40 for a BATCH of scenarios on the
+    device (u = K (x - x_wp) + c + u_wp to the RK4 plant, transitionTrue.m:11-12; the next solve starts from the unshifted
+    opt_var, ocpLBMPC.m:31; data window per update_data.m:3-10; LBMPC: two first-order SQP iterations per step with the learned
+    term in the cost only).  Checked (a) scenario by scenario against the Python mirrors of the two .m drivers, which make the
+    same solver calls one scenario at a time, and (b) for the reference's own initial state against its saved histories
+    LBMPC_N50_sys_full.mat / LMPC_N50_sys_full.mat (first input 2e-7, the rest as in
+    test_fform_closed_loop_drivers_vs_reference_histories).  BASELINE configs[0] / SURVEY 8d config 1 as a batch."""
+    import lbmpc_b200
+    steps, nb = 14, 5
+    dx_all = np.vstack([DX0, DX0 + 0.04 * np.random.default_rng(9).standard_normal((nb - 1, 4)) * np.array([1.0, 1.0, 0.2, 0.2])])
+    for variant in ("LBMPC", "LMPC"):
+        mdl = models[variant]
+        sol = solver(mdl, "F", variant, 50, max_batch=nb)
+        got = sol.closed_loop(X_EQ + dx_all, steps, X_EQ, U_EQ, q=100, use_oracle=True)
+        assert (got["status"] == 0).all()
+        mats = [mdl[k] for k in ("K", "Q", "R", "P", "T")] + [np.vstack([mdl["LAMBDA"], mdl["PSI"]]), mdl["LAMBDA"], mdl["PSI"], 1]
+        rows = [mdl[k] for k in ("F_x", "h_x", "F_u", "h_u", "F_w_N", "h_w_N")]
+        for b in range(nb):
+            hist0 = [np.concatenate([dx_all[b], [0.0]]).reshape(5, 1), np.zeros((1, 1)), np.zeros((4, 1))]
+            if variant == "LBMPC":
+                sysH, artH, _ = lbmpc_b200.ocpLBMPC(X_EQ + dx_all[b], X_EQ, dx_all[b], np.zeros(4), U_EQ, 50, 0.01, steps, None, np.zeros(51),
+                                                    {"X": np.zeros((3, 1)), "Y": np.zeros((4, 1))}, mdl["A"], mdl["B"], *mats, *rows,
+                                                    mdl["F_x_d"], mdl["h_x_d"], *hist0)
+            else:
+                sysH, artH, _ = lbmpc_b200.ocpLMPC(X_EQ + dx_all[b], dx_all[b], X_EQ, np.zeros(4), U_EQ, 50, 0.01, steps, None, np.zeros(51),
+                                                   *mats, *rows, *hist0, A=mdl["A"], B=mdl["B"])
+            # sysH columns 1.. = [x - x_wp; u_k - u_wp] of step k with x BEFORE the plant step in ocpLBMPC.m:37-40 and AFTER it in
+            # ocpLMPC.m:30-33 (there the plant call overwrites x)
+            xs = got["x"][b, :steps] if variant == "LBMPC" else got["x"][b, 1:steps + 1]
+            assert np.abs(xs - X_EQ - sysH[:4, 1:].T).max() < 1e-9, (variant, b)
+            assert np.abs(got["u"][b] - U_EQ - sysH[4, 1:]).max() < 1e-9, (variant, b)
+        ref = fx[f"{variant}_N50__sysH"]
+        assert abs(got["u"][0, 0] - U_EQ - ref[4, 1]) < 2e-7
+        xs = got["x"][0, :steps] if variant == "LBMPC" else got["x"][0, 1:steps + 1]
+        err = np.abs(np.vstack([(xs - X_EQ).T, got["u"][0][None, :] - U_EQ]) - ref[:, 1:steps + 1])
+        assert err[[0, 1, 2, 4]].max() < 3e-5 and err[3].max() < 2e-4, err.max(1)
