@@ -851,24 +851,17 @@ plant_kernel(LoopState S, const double* __restrict__ A, const double* __restrict
         ys[a] = v;
     }
     const double xs[3] = {dx[0], dx[1], du0};
-    int nd = S.nd[b];
+    // the window is a RING: sample number nd goes to slot nd mod capacity (the Nadaraya-Watson sums do not depend on the order of the
+    // samples, so dropping the oldest one — get_data.m:8 / update_data.m:8 — is overwriting it; no O(q) shift per step and scenario)
+    const int cap = Kfb ? (q > 1 ? q - 1 : 1) : q;
+    const int nd = S.nd[b], slot = nd % cap;
     double* Xb = S.X + b * 3 * q;
     double* Yb = S.Y + b * 4 * q;
-    double* Vb = S.V + b * q;
-    if (nd >= (Kfb ? q - 1 : q)) {  // get_data.m:8 / update_data.m:8 : drop the oldest sample
-        for (int i = 0; i + 1 < q; ++i) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) Xb[i * 3 + a] = Xb[(i + 1) * 3 + a];
+    for (int a = 0; a < 3; ++a) Xb[slot * 3 + a] = xs[a];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) Yb[i * 4 + a] = Yb[(i + 1) * 4 + a];
-        }
-        nd = (Kfb ? q - 1 : q) - 1;
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) Xb[nd * 3 + a] = xs[a];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) Yb[nd * 4 + a] = ys[a];
-    Vb[nd] = 1.0;
+    for (int a = 0; a < 4; ++a) Yb[slot * 4 + a] = ys[a];
+    S.V[b * q + slot] = 1.0;
     S.nd[b] = nd + 1;
     // warm-start shift (in place when the plan is the previous warm start)
     if (Kfb) {  // F-form: opt_var is reused as it is
