@@ -276,7 +276,7 @@ static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const dou
     const bool w8 = 8 * per_warp + poly <= (size_t)h->max_smem_optin && h->st_warps_cap != 6;
     // fewer QPs than resident lanes: spread them over ALL SMs with fewer warps per CTA instead of filling a few SMs with eight
     // (a lane's iteration is latency-bound; with 2 warps on an SM instead of 8 it runs ~2.5x faster)
-    if (!LTV && sizeof(FT) == 8 && h->st_spread) {
+    if (sizeof(FT) == 8 && h->st_spread && 4 * per_warp + poly <= (size_t)h->max_smem_optin) {
         const int64_t wps = (io.batch + 32 * (int64_t)h->num_sms - 1) / (32 * (int64_t)h->num_sms);
         if (wps <= 2) return launch_stream_w<LTV, FT, 2>(h, io, jac, st, 2 * per_warp + poly, evict);
         if (wps <= 4) return launch_stream_w<LTV, FT, 4>(h, io, jac, st, 4 * per_warp + poly, evict);
@@ -461,6 +461,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         if (const char* e = getenv("LBMPC_LOOP_MIN_BATCH")) h->st_loop_min_batch = atoll(e);
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 6>)); CU_TRY(optin(ipm_stream_kernel<4, true, double, 6>));
         CU_TRY(optin(ipm_stream_kernel<4, false, double, 2>)); CU_TRY(optin(ipm_stream_kernel<4, false, double, 4>));
+        CU_TRY(optin(ipm_stream_kernel<4, true, double, 2>));  CU_TRY(optin(ipm_stream_kernel<4, true, double, 4>));
         CU_TRY(optin(ipm_stream_kernel<4, false, float, 6>));  CU_TRY(optin(ipm_stream_kernel<4, true, float, 6>));
         h->st_ctas_per_sm = 1;
         // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
