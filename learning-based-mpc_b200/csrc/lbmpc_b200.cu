@@ -173,8 +173,9 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch, bool allow_stream =
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
     // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, 1.1x at 24 and is
-    // still level at 440 QPs/SM: always picked.
-    if (h->cta_big) return LBMPC_KERNEL_CTA;
+    // level from ~80 QPs/SM on, where the warp mapping is 2 - 4 % ahead.
+    // (profiles/r2_kernel_sweep.json, 616-row set: CTA 0.81 / 2.36 / 8.60 / 33.5 ms vs warp 0.97 / 2.49 / 8.46 / 32.3 ms at batch 1024 / 4096 / 16384 / 65536)
+    if (h->cta_big) return batch >= (int64_t)h->num_sms * 80 ? LBMPC_KERNEL_WARP : LBMPC_KERNEL_CTA;
     if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return LBMPC_KERNEL_CTA;
     // (a two-warps-per-QP CTA variant exists — LBMPC_CTA_WARPS=2 — but 35 KB of shared memory per CTA keep it at 6 CTAs per SM,
     //  and even four warps per QP gain only 9 % over the warp mapping at 4 QPs per SM: not picked automatically)
