@@ -48,6 +48,8 @@ struct lbmpc_handle {
     HostProblem hp;
     int shape = 0;  // 0: <4,1,1>  1: <2,2,2>
     int max_slots = 0, stage_g = 0, num_sms = 0;
+    bool poly_global = false;          // warp mapping: polytope slacks / multipliers in a global array (large sets)
+    double* dpoly = nullptr;
     int cta_blocks_per_sm[2] = {0, 0};  // [0] > 0: the CTA-per-QP latency kernel (4 warps per QP) is available: resident CTAs per SM
     size_t cta_smem = 0;
     int cta_warps_force = 0;           // 2 / 4: warps per QP of the CTA kernel (LBMPC_CTA_WARPS, experiments)
@@ -110,13 +112,16 @@ static unsigned long long* next_queue(lbmpc_handle* h) { return h->dqueue + (h->
 template <int NX, int NT, int NU>
 static int plan_slots(lbmpc_handle* h, size_t max_smem) {
     const HostProblem& hp = h->hp;
+    // large polytope block: its slacks / multipliers (2 ngp doubles per QP) live in a global array, not in the slot
+    h->poly_global = hp.ng > 64;
+    if (const char* e = getenv("LBMPC_POLY_GLOBAL")) h->poly_global = atoi(e) != 0 && hp.ng > 0;
     for (int stage = 1; stage >= 0; --stage) {
         for (int s = kMaxSlots; s >= 1; --s) {
-            const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, s, stage != 0);
+            const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, s, stage != 0, h->poly_global);
             // staging the polytope must not cost more than one slot of residency
             if (plan.bytes <= max_smem) {
                 if (stage == 1) {
-                    const SmemPlan<NX, NT, NU> alt(hp.N, hp.ngp, std::min(s + 1, kMaxSlots), false);
+                    const SmemPlan<NX, NT, NU> alt(hp.N, hp.ngp, std::min(s + 1, kMaxSlots), false, h->poly_global);
                     if (s < kMaxSlots && alt.bytes <= max_smem && hp.ng <= 64) continue;  // tiny block: keep it in L1/L2
                 }
                 h->max_slots = s;
@@ -138,14 +143,18 @@ static cudaError_t launch_ipm(lbmpc_handle* h, const BatchIO& io_in, cudaStream_
     int slots = (int)std::min<int64_t>(h->max_slots, (nq + h->num_sms - 1) / h->num_sms);
     slots = std::max(slots, 1);
     const int grid = (int)std::min<int64_t>(h->num_sms, (nq + slots - 1) / slots);
-    const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0);
+    const SmemPlan<NX, NT, NU> plan(hp.N, hp.ngp, slots, h->stage_g != 0, h->poly_global);
+    if (h->poly_global && !h->dpoly) {  // one slab for the largest launch shape: num_sms CTAs x max_slots warps
+        cudaError_t ea = cudaMalloc((void**)&h->dpoly, sizeof(double) * (size_t)h->num_sms * kMaxSlots * 2 * hp.ngp);
+        if (ea != cudaSuccess) return ea;
+    }
     // many QPs per warp slot: the warps of a CTA start their iterations together (shared instruction fetches, see cta_tick)
     io.lockstep = slots >= 4 && nq >= (int64_t)3 * grid * slots;
     if (h->force_lockstep >= 0) io.lockstep = h->force_lockstep;
     io.queue = next_queue(h);
     cudaError_t e = cudaMemsetAsync(io.queue, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g);
+    ipm_kernel<NX, NT, NU><<<grid, 32 * slots, plan.bytes, st>>>(p, io, h->dG, h->dhg, slots, h->stage_g, h->poly_global ? h->dpoly : nullptr);
     h->launches += 1;
     h->last_kernel = LBMPC_KERNEL_WARP;
     return cudaGetLastError();
@@ -167,15 +176,17 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch, bool allow_stream =
     // long horizons: shared memory holds 1 - 2 QPs per SM, the stream mapping 256; its slow iterations (2 ms at N = 200) are
     // bounded by an iteration budget, the QPs beyond it are handed to the CTA mapping (launch_ipm_stream, evict)
     if (stream_ok && h->st_min_batch_long > 0 && batch >= h->st_min_batch_long && h->hp.ng <= 64 && h->hp.N > 100) return LBMPC_KERNEL_STREAM;
-    // 616-row set: the thread-local row loops pay off at large batches only (65536: 29.5 vs 33.5 ms for the CTA mapping, 262144: 78 vs 133 ms)
-    if (stream_ok && h->st_min_batch > 0 && batch >= 2 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
+    // 616-row set: the thread-local row loops pay off at large batches only (warp mapping 28.7 / 42.8 / 56.9 ms vs stream 29.0 / 38.0 / 45.3 ms
+    // at batch 65536 / 98304 / 131072)
+    if (stream_ok && h->st_min_batch > 0 && 2 * batch >= 5 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
     // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, 1.1x at 24 and is
     // level from ~80 QPs/SM on, where the warp mapping is 2 - 4 % ahead.
-    // (profiles/r2_kernel_sweep.json, 616-row set: CTA 0.81 / 2.36 / 8.60 / 33.5 ms vs warp 0.97 / 2.49 / 8.46 / 32.3 ms at batch 1024 / 4096 / 16384 / 65536)
-    if (h->cta_big) return batch >= (int64_t)h->num_sms * 80 ? LBMPC_KERNEL_WARP : LBMPC_KERNEL_CTA;
+    // 616-row set, with the polytope slacks / multipliers of the warp mapping in a global array (7 instead of 5 QPs per SM):
+    // CTA 0.81 / 1.34 / 2.39 / 4.42 / 8.6 ms vs warp 0.86 / 1.36 / 2.30 / 4.03 / 7.55 ms at batch 1024 / 2048 / 4096 / 8192 / 16384
+    if (h->cta_big) return batch >= (int64_t)h->num_sms * 20 ? LBMPC_KERNEL_WARP : LBMPC_KERNEL_CTA;
     if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return LBMPC_KERNEL_CTA;
     // (a two-warps-per-QP CTA variant exists — LBMPC_CTA_WARPS=2 — but 35 KB of shared memory per CTA keep it at 6 CTAs per SM,
     //  and even four warps per QP gain only 9 % over the warp mapping at 4 QPs per SM: not picked automatically)
@@ -468,7 +479,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
         //   N = 50 : batch 24576 5.95 vs 5.58 ms, 32768 6.32 vs 7.39, 65536 11.1 vs 14.5, 131072 19.5 vs 28.7  -> from ~31 k QPs on
         //   N = 200: batch 16384 28.3 vs 26.5 ms, 24576 28.6 vs 39.5, 32768 30.2 vs 52.7, 49152 44.3 vs 78.6   -> from ~15 k QPs on (spread launches, below)
-        //   616-row set, N = 50 (no budget): 65536 29.5 vs 33.5 ms, 131072 47.0 vs 66.8, 262144 77.9 vs 133.3   -> from ~62 k QPs on
+        //   616-row set, N = 50 (no budget): 65536 29.0 vs 28.7 ms, 98304 38.0 vs 42.8, 131072 45.3 vs 56.9           -> from ~77 k QPs on
         //   (profiles/r2_threshold_sweep.log; budget at N = 200: 16 iterations — 14: +12 %, 22: +10 %, 32: +27 %)
         h->st_min_batch = (int64_t)h->num_sms * 208;
         h->st_evict_iters = hp.N > 100 ? 16 : 14;  // N = 50: 14 vs 12 -> closed loop 4.80 vs 4.50 M QP/s, batch 262144 34.5 vs 35.3 ms (profiles/r2_evict_sweep.log)
@@ -1058,7 +1069,7 @@ void lbmpc_destroy(lbmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     free_loop(h->loop);
-    cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dK); cudaFree(h->dqueue); cudaFree(h->dprof);
+    cudaFree(h->dpoly); cudaFree(h->dG); cudaFree(h->dhg); cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dK); cudaFree(h->dqueue); cudaFree(h->dprof);
     cudaFree(h->s_dx0); cudaFree(h->s_ref); cudaFree(h->s_doff); cudaFree(h->s_warm); cudaFree(h->s_uc);
     cudaFree(h->s_x); cudaFree(h->s_small); cudaFree(h->s_csh);
     if (h->hs_small) cudaFreeHost(h->hs_small);

@@ -91,13 +91,21 @@ struct Layout {
     static constexpr int TS = NX * NZ, BS = (TS + NZ) | 1;
     int Np, ngp, bm, nb;
     int o_r1, o_r2, o_r3, o_blk, o_sg, o_lg, o_misc, stride;
+    // large polytope blocks (616 rows = 9.9 KB of slacks / multipliers per QP): optionally kept in a global (L2-resident) array
+    // instead of the slot, which is what bounds the resident QPs per SM for that set; lanes stride over rows, so the accesses
+    // are coalesced.  nullptr: in the slot.
+    double* gsg = nullptr;
+    LB_HD double* sgp(double* s) const { return gsg ? gsg : s + o_sg; }
+    LB_HD double* lgp(double* s) const { return gsg ? gsg + ngp : s + o_lg; }
+    LB_HD const double* sgp(const double* s) const { return gsg ? gsg : s + o_sg; }
+    LB_HD const double* lgp(const double* s) const { return gsg ? gsg + ngp : s + o_lg; }
     static LB_HD int block_len(int N) {  // ~0.6 sqrt(N), at least N/32 (one lane per block)
         int m = 1;
         while (25 * m * m < 9 * N) ++m;
         const int mmin = (N + 31) / 32;
         return m > mmin ? m : mmin;
     }
-    LB_HD Layout(int N, int ngp_) {
+    LB_HD Layout(int N, int ngp_, bool poly_global = false) {
         Np = N + 1;
         ngp = ngp_;
         bm = block_len(N);
@@ -107,8 +115,8 @@ struct Layout {
         o_r2 = o;  o += RS2 * Np;
         o_r3 = o;  o += RS3 * Np;
         o_blk = o; o += BS * nb;
-        o_sg = o;  o += ngp;
-        o_lg = o;  o += ngp;
+        o_sg = o;  o += poly_global ? 0 : ngp;
+        o_lg = o;  o += poly_global ? 0 : ngp;
         o_misc = o; o += M_SIZE;
         stride = o | 1;  // odd
     }
@@ -283,8 +291,8 @@ struct Core {
     static LB_HD void init_rows_gen(const P& p, const L& l, double* s, const double* G,
                                     const double* hg, int i) {
         const double slack = gen_slack(p, l, s, G, hg, i);
-        s[l.o_sg + i] = slack > 1.0 ? slack : 1.0;
-        s[l.o_lg + i] = 1.0;
+        l.sgp(s)[i] = slack > 1.0 ? slack : 1.0;
+        l.lgp(s)[i] = 1.0;
     }
 
     // ============================================================================================
@@ -600,7 +608,7 @@ struct Core {
     static LB_HD void assemble_gen_row(const P& p, const L& l, const double* s, const double* G,
                                        const double* hg, int i, double* acc, RedAsm& red) {
         const double slack = gen_slack(p, l, s, G, hg, i);
-        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double S = l.sgp(s)[i], Lm = l.lgp(s)[i];
         const double rp = S - slack, w = Lm * lb_rcp(S), t = w * rp;
         red.rp = lb_nanmax(red.rp, lb_abs(rp));
         red.sl += S * Lm;
@@ -1366,7 +1374,7 @@ struct Core {
     static LB_HD void gen_row_asm_scalars(const P& p, const L& l, const double* s, const double* G, const double* hg, int i,
                                           double* rb, RedAsm& red) {
         const double slack = gen_slack(p, l, s, G, hg, i);
-        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double S = l.sgp(s)[i], Lm = l.lgp(s)[i];
         const double rp = S - slack, w = Lm * lb_rcp(S), t = w * rp;
         red.rp = lb_nanmax(red.rp, lb_abs(rp));
         red.sl += S * Lm;
@@ -1411,7 +1419,7 @@ struct Core {
                                           double* rb, RedStep& red) {
         const double* m = s + l.o_misc;
         const double slack = gen_slack(p, l, s, G, hg, i);
-        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double S = l.sgp(s)[i], Lm = l.lgp(s)[i];
         const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
         double adva = 0.0;
 #pragma unroll
@@ -1442,7 +1450,7 @@ struct Core {
                                      const double* hg, int i, double* acc, RedStep& red) {
         const double* m = s + l.o_misc;
         const double slack = gen_slack(p, l, s, G, hg, i);
-        const double S = s[l.o_sg + i], Lm = s[l.o_lg + i];
+        const double S = l.sgp(s)[i], Lm = l.lgp(s)[i];
         const double rp = S - slack, is = lb_rcp(S), w = Lm * is;
         double g[NZ], adva = 0.0;
 #pragma unroll
@@ -1505,8 +1513,8 @@ struct Core {
                                     int i, double sigmu, double& S, double& Lm, double& ds, double& dl, double& is) {
         const double* m = s + l.o_misc;
         const double slack = gen_slack(p, l, s, G, hg, i);
-        S = s[l.o_sg + i];
-        Lm = s[l.o_lg + i];
+        S = l.sgp(s)[i];
+        Lm = l.lgp(s)[i];
         const double rp = S - slack;
         is = lb_rcp(S);
         const double w = Lm * is;
@@ -1538,8 +1546,8 @@ struct Core {
                                      double sigmu, double alpha) {
         double S, Lm, ds, dl, is;
         gen_final_dir(p, l, s, G, hg, i, sigmu, S, Lm, ds, dl, is);
-        s[l.o_sg + i] = S + alpha * ds;
-        s[l.o_lg + i] = Lm + alpha * dl;
+        l.sgp(s)[i] = S + alpha * ds;
+        l.lgp(s)[i] = Lm + alpha * dl;
     }
 
     // stage: objective contribution 0.5 v'W v (+ lin'z at kT)

@@ -128,8 +128,8 @@ struct SmemPlan {
     static constexpr int kXchPerSlot = 104;  // >= Coop::kXch doubles per QP (even)
     int slots, stride, xch_off, zero_off, g_off, hg_off, meta_off;  // offsets in doubles
     size_t bytes;
-    __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g) {
-        const L l(N, ngp);
+    __host__ __device__ SmemPlan(int N, int ngp, int slots_, bool stage_g, bool poly_global = false) {
+        const L l(N, ngp, poly_global);
         slots = slots_;
         stride = l.stride;
         int o = slots * stride;
@@ -208,15 +208,16 @@ __device__ __forceinline__ void affine_forward(const Params<NX, NT, NU>& p, cons
 template <int NX, int NT, int NU>
 __global__ void __launch_bounds__(32 * kMaxSlots, 1)
 ipm_kernel(const __grid_constant__ Params<NX, NT, NU> p, const BatchIO io, const double* __restrict__ Gglob,
-           const double* __restrict__ hgglob, const int slots, const int stage_g) {
+           const double* __restrict__ hgglob, const int slots, const int stage_g, double* gpoly = nullptr) {
     using C = Core<NX, NT, NU>;
     using L = Layout<NX, NT, NU>;
     constexpr int NZ = NX + NT, NH = L::NH, NACC = NH + 2 * NZ;
     constexpr bool kCoop = (NT == 1 && NU == 1 && NX >= 2 && NX <= 4);  // one-warp Riccati factorisation
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const L l(p.N, p.ngp);
-    const SmemPlan<NX, NT, NU> plan(p.N, p.ngp, slots, stage_g != 0);
+    L l(p.N, p.ngp, gpoly != nullptr);
+    if (gpoly) l.gsg = gpoly + ((size_t)blockIdx.x * slots + warp) * 2 * p.ngp;  // this warp's slacks / multipliers of the polytope rows
+    const SmemPlan<NX, NT, NU> plan(p.N, p.ngp, slots, stage_g != 0, gpoly != nullptr);
     double* const slot = smem + warp * l.stride;
     double* const m = slot + l.o_misc;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + plan.meta_off);
