@@ -122,7 +122,9 @@ static int plan_slots(lbmpc_handle* h, size_t max_smem) {
             if (plan.bytes <= max_smem) {
                 if (stage == 1) {
                     const SmemPlan<NX, NT, NU> alt(hp.N, hp.ngp, std::min(s + 1, kMaxSlots), false, h->poly_global);
-                    if (s < kMaxSlots && alt.bytes <= max_smem && hp.ng <= 64) continue;  // tiny block: keep it in L1/L2
+                    // one more resident QP beats a staged block: tiny blocks stay in L1, and for the 616-row set (slacks / multipliers
+                    // in the global array) 8 QPs per SM reading G from L2 run 7.06 ms at batch 16384 against 7.52 ms with 7 QPs and G staged
+                    if (s < kMaxSlots && alt.bytes <= max_smem) continue;
                 }
                 h->max_slots = s;
                 h->stage_g = stage;
@@ -176,16 +178,16 @@ static int pick_kernel(const lbmpc_handle* h, int64_t batch, bool allow_stream =
     // long horizons: shared memory holds 1 - 2 QPs per SM, the stream mapping 256; its slow iterations (2 ms at N = 200) are
     // bounded by an iteration budget, the QPs beyond it are handed to the CTA mapping (launch_ipm_stream, evict)
     if (stream_ok && h->st_min_batch_long > 0 && batch >= h->st_min_batch_long && h->hp.ng <= 64 && h->hp.N > 100) return LBMPC_KERNEL_STREAM;
-    // 616-row set: the thread-local row loops pay off at large batches only (warp mapping 28.7 / 42.8 / 56.9 ms vs stream 29.0 / 38.0 / 45.3 ms
+    // 616-row set: the thread-local row loops pay off at large batches only (warp mapping 26.6 / 39.5 ms vs stream 29.0 / 38.0 / 45.3 ms
     // at batch 65536 / 98304 / 131072)
-    if (stream_ok && h->st_min_batch > 0 && 2 * batch >= 5 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
+    if (stream_ok && h->st_min_batch > 0 && batch >= 3 * h->st_min_batch && h->hp.ng > 64 && h->hp.N <= 100) return LBMPC_KERNEL_STREAM;
     if (!cta_ok) return LBMPC_KERNEL_WARP;
     // measured on B200 (C-form, N = 50).  24-row polytope (LBMPC): one CTA per QP wins while every QP is resident (4 CTAs per SM:
     // 1.24x at 1 QP/SM, 1.13x at 4); beyond that the QPs that queue behind the resident CTAs cost more than the faster iterations gain.  616-row
     // polytope (LMPC): the row phases dominate an iteration, the CTA kernel wins 1.5x at 1 QP/SM, 1.2x at 7, 1.1x at 24 and is
     // level from ~80 QPs/SM on, where the warp mapping is 2 - 4 % ahead.
     // 616-row set, with the polytope slacks / multipliers of the warp mapping in a global array (7 instead of 5 QPs per SM):
-    // CTA 0.81 / 1.34 / 2.39 / 4.42 / 8.6 ms vs warp 0.86 / 1.36 / 2.30 / 4.03 / 7.55 ms at batch 1024 / 2048 / 4096 / 8192 / 16384
+    // CTA 0.81 / 1.34 / 2.39 / 4.42 / 8.6 ms vs warp 0.88 / 1.35 / 2.28 / - / 7.06 ms at batch 1024 / 2048 / 4096 / 8192 / 16384
     if (h->cta_big) return batch >= (int64_t)h->num_sms * 20 ? LBMPC_KERNEL_WARP : LBMPC_KERNEL_CTA;
     if (batch <= (int64_t)h->num_sms * h->cta_blocks_per_sm[0]) return LBMPC_KERNEL_CTA;
     // (a two-warps-per-QP CTA variant exists — LBMPC_CTA_WARPS=2 — but 35 KB of shared memory per CTA keep it at 6 CTAs per SM,
@@ -479,7 +481,7 @@ int lbmpc_create(const lbmpc_model* model, const lbmpc_config* cfg, int device, 
         // measured on B200 (C-form LBMPC, stream with iteration budget + hand-over vs the best shared-memory mapping):
         //   N = 50 : batch 24576 5.95 vs 5.58 ms, 32768 6.32 vs 7.39, 65536 11.1 vs 14.5, 131072 19.5 vs 28.7  -> from ~31 k QPs on
         //   N = 200: batch 16384 28.3 vs 26.5 ms, 24576 28.6 vs 39.5, 32768 30.2 vs 52.7, 49152 44.3 vs 78.6   -> from ~15 k QPs on (spread launches, below)
-        //   616-row set, N = 50 (no budget): 65536 29.0 vs 28.7 ms, 98304 38.0 vs 42.8, 131072 45.3 vs 56.9           -> from ~77 k QPs on
+        //   616-row set, N = 50 (no budget): 65536 29.0 vs 26.6 ms, 98304 38.0 vs 39.5, 131072 45.3 vs ~52            -> from ~92 k QPs on
         //   (profiles/r2_threshold_sweep.log; budget at N = 200: 16 iterations — 14: +12 %, 22: +10 %, 32: +27 %)
         h->st_min_batch = (int64_t)h->num_sms * 208;
         h->st_evict_iters = hp.N > 100 ? 16 : 14;  // N = 50: 14 vs 12 -> closed loop 4.80 vs 4.50 M QP/s, batch 262144 34.5 vs 35.3 ms (profiles/r2_evict_sweep.log)
