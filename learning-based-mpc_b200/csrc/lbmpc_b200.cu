@@ -300,6 +300,7 @@ static cudaError_t launch_stream_t(lbmpc_handle* h, const BatchIO& io, const dou
 // evict: iteration budget + hand-over (only for plain QPs: no per-stage dynamics, no row shift — the shared-memory mappings
 // have neither)
 static cudaError_t launch_ipm_stream(lbmpc_handle* h, const BatchIO& io, const double* jac, cudaStream_t st, bool mixed, bool evict = false) {
+    if (io.row_shift && !jac) return cudaErrorInvalidValue;  // row shifts are compiled into the LTV kernel only
     evict = evict && !jac && !io.row_shift && h->st_evict_iters > 0;
     if (mixed) return jac ? launch_stream_t<true, float>(h, io, jac, st, false) : launch_stream_t<false, float>(h, io, jac, st, false);
     return jac ? launch_stream_t<true, double>(h, io, jac, st, false) : launch_stream_t<false, double>(h, io, jac, st, evict);

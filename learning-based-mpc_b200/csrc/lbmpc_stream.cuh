@@ -1210,7 +1210,7 @@ struct Stream {
         Lane ln;
         double coldbuf[Lane::C_N * LS];
         ln.cold = coldbuf;
-        const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
+        const bool has_cs = io.cshift != nullptr, rsh = LTV && io.row_shift != 0;  // row shifts come with LTV dynamics only (first-order SQP)
         StreamPipeDirect<NX, FT, LS> pp(l, w64, wft);
         init_qp(p, l, ln, io, q, w64, has_cs);
         for (;;) {
@@ -1429,7 +1429,9 @@ ipm_stream_kernel(const __grid_constant__ Params<NX, 1, 1> p, const StreamIO<FT>
     extern __shared__ __align__(128) unsigned char stream_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    const bool has_cs = io.cshift != nullptr, rsh = io.row_shift != 0;
+    // row shifts exist only together with per-stage dynamics (first-order SQP): a compile-time false in the plain kernel, which
+    // frees the shift registers of every pass there
+    const bool has_cs = io.cshift != nullptr, rsh = LTV && io.row_shift != 0;
     const StreamLayout<NX> l(p.N, p.ng, has_cs, LTV, LOOP ? io.qwin : 0);
     double* const w64 = io.ws64 + warp * (long long)l.n64 * 32 + lane;
     FT* const wft = io.wsft + warp * (long long)l.nft * 32 + lane;
