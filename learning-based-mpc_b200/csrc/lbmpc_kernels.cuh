@@ -567,6 +567,12 @@ oracle_kernel(const double* __restrict__ A, const double* __restrict__ B, const 
 #pragma unroll
         for (int a = 0; a < NX; ++a) ys[r][a] = on ? Y[(qp * q + i) * NX + a] : 0.0;
         vs[r] = on ? (valid ? valid[qp * q + i] : 1.0) : -1.0;  // -1: slot unused
+        // a masked sample with Y = 0 (a window slot that has not been written yet) adds nothing to either sum: treat it as unused,
+        // so that a partly filled window — the first q steps of every closed loop — costs only its own exponentials
+        bool zero = vs[r] == 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) zero = zero && ys[r][a] == 0.0;
+        if (zero) vs[r] = -1.0;
     }
     double Am[NX * NX], Bm[NX * NU], Km[NU * NX], x[NX];
 #pragma unroll
