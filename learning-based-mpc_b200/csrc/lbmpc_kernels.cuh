@@ -665,6 +665,10 @@ oracle_jac_kernel(const double* __restrict__ A, const double* __restrict__ B, co
 #pragma unroll
         for (int a = 0; a < NX; ++a) ys[r][a] = on ? Y[(qp * q + i) * NX + a] : 0.0;
         vs[r] = on ? (valid ? valid[qp * q + i] : 1.0) : -1.0;
+        bool zero = vs[r] == 0.0;  // unwritten window slot (mask 0, Y = 0): contributes to no sum, see oracle_kernel
+#pragma unroll
+        for (int a = 0; a < NX; ++a) zero = zero && ys[r][a] == 0.0;
+        if (zero) vs[r] = -1.0;
     }
     double Am[NX * NX], Bm[NX], Km[NX], x[NX], xn[NX];
 #pragma unroll
