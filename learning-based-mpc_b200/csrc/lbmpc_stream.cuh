@@ -328,28 +328,45 @@ struct Stream {
         double x[NX];
 #pragma unroll
         for (int j = 0; j < NX; ++j) x[j] = io.dx0[q * NX + j];
-        for (int k = 0; k <= N; ++k) {
-            double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
+        // the caller's warm start and offsets of KB stages are fetched before the (sequential) rollout over them: loaded stage by
+        // stage, every stage waited for its own scattered loads — 5 % of the warp time of a closed-loop launch, where every QP
+        // brings both arrays (same remedy as in finish())
+        constexpr int KB = 8;
+        for (int k0 = 0; k0 <= N; k0 += KB) {
+            double wm[KB], dk[KB][NX];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) st(it, SL::F_X + j, x[j]);
-            if (k == N) break;
-            AB ab;
-            load_ab(p, w64 + (l.o_j + k * SL::NJ) * LS, ab);
-            double u = io.warm ? io.warm[q * (N + 1) + k] : 0.0;
+            for (int i = 0; i < KB; ++i) {
+                const int k = k0 + i < N ? k0 + i : N - 1;
+                wm[i] = io.warm ? io.warm[q * (N + 1) + k] : 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) u += p.Kinit[j] * x[j];
-            st(it, SL::F_U, u);
-            double xn[NX];
-#pragma unroll
-            for (int a = 0; a < NX; ++a) {
-                double v = io.d_off ? io.d_off[(q * N + k) * NX + a] : 0.0;
-#pragma unroll
-                for (int j = 0; j < NX; ++j) v += ab.A[a * NX + j] * x[j];
-                v += ab.B[a] * u;
-                xn[a] = v;
+                for (int a = 0; a < NX; ++a) dk[i][a] = io.d_off ? io.d_off[(q * N + k) * NX + a] : 0.0;
             }
 #pragma unroll
-            for (int a = 0; a < NX; ++a) x[a] = xn[a];
+            for (int i = 0; i < KB; ++i) {
+                const int k = k0 + i;
+                if (k > N) break;
+                double* it = w64 + (l.o_it + k * SL::RS_IT) * LS;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) st(it, SL::F_X + j, x[j]);
+                if (k == N) break;
+                AB ab;
+                load_ab(p, w64 + (l.o_j + k * SL::NJ) * LS, ab);
+                double u = wm[i];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) u += p.Kinit[j] * x[j];
+                st(it, SL::F_U, u);
+                double xn[NX];
+#pragma unroll
+                for (int a = 0; a < NX; ++a) {
+                    double v = dk[i][a];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) v += ab.A[a * NX + j] * x[j];
+                    v += ab.B[a] * u;
+                    xn[a] = v;
+                }
+#pragma unroll
+                for (int a = 0; a < NX; ++a) x[a] = xn[a];
+            }
         }
     }
 
