@@ -439,6 +439,15 @@ def main():
                         "note": "algorithmic I/O only; the warp / CTA mappings keep the iterate in shared memory, the stream mapping "
                                 "streams it from HBM (profiles/)"}}
 
+    if kernel_used in ("stream", "mixed") and kind != "closed_loop":
+        # the stream mapping keeps the iterate in HBM: 178 doubles per stage and iteration by design — overhead, not
+        # algorithmic traffic, reported so that the second bound of this mapping is visible next to the FP64 one
+        design = float(iters.sum()) * 178 * 8 * (N + 1)
+        roofline["hbm"]["stream_design_bytes_per_launch"] = design
+        roofline["hbm"]["stream_design_gbs"] = design / (k_ms * 1e-3) * 1e-9
+        if peaks.get("hbm_gbs"):
+            roofline["hbm"]["stream_design_frac_of_peak"] = roofline["hbm"]["stream_design_gbs"] / peaks["hbm_gbs"]
+
     # ---------------- CPU baseline (oracle port, bounded sample) ----------------
     from oracle_py import OracleProblem
     threads = os.cpu_count() or 1
